@@ -1,0 +1,150 @@
+/* scb.h -- C ABI of the B200-native seamlessClone(NORMAL_CLONE) hot path.
+ *
+ * Plain C, POD only: opaque handles, raw pointers + (rows, cols, channels, stride), int status
+ * codes.  No OpenCV, torch or C++ types cross this boundary, so any host language can bind it
+ * (ctypes / cgo / JNI / N-API); see INTEGRATION.md for the stubs.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/seamlessClone-CUDA/):
+ *
+ *   scb_create / scb_destroy / scb_sync
+ *       seamlessClone_imp_create_instance / _destroy / _sync      seamlessClone_imp.cu:239-263, 354-370
+ *       (one context = one device + one stream + grow-only workspace + table cache;
+ *        the reference never calls cudaSetDevice -- every entry point here does)
+ *   scb_plan_create / scb_plan_destroy
+ *       SeamlessClone::init_resize -> initMask (ring-zero, bbox, 3x erode, leftTop)
+ *                                                                  seamlessClone_imp.cpp:978-1116
+ *       plus the DST tables the reference rebuilds on every call (initDSTMatrix_kernel :569-603)
+ *   scb_plan_execute
+ *       SeamlessClone::seamlessCloneGPU -> run()                   seamlessClone_imp.cpp:430-486, 2105-2135
+ *   scb_seamless_clone
+ *       cv::seamlessClone(src, dst, mask, p, blend, NORMAL_CLONE)  call sites seamlessClone-OpenCV/seamlessClone_OpenCV.cpp:104,110
+ *       == seamlessClone_imp_run without its double execution      seamlessClone_imp.cu:265-352
+ *   my_seamlessclone_api_imp_*
+ *       the four extern "C" names of seamlessclone_cuda.h:4-63 (which return cv::Mat by value and
+ *       so are not a C ABI); same names and argument meaning, POD image views instead of cv::Mat*
+ *   scb_plan_get_intermediate
+ *       the SCDEBUG YAML dumps compared by compare/vs.py:12-34 (g*.yml vs OpenCV's mod_diff*.yml)
+ */
+#ifndef SCB_H_
+#define SCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_VERSION 100
+
+/* status codes */
+enum {
+    SCB_OK = 0,
+    SCB_ERR_INVALID_ARGUMENT = 1,  /* null pointers, wrong channel counts, sizes that disagree   */
+    SCB_ERR_ROI_OUT_OF_BOUNDS = 2, /* OpenCV: (-215) assertion on roi inside dst                 */
+    SCB_ERR_UNSUPPORTED = 3,       /* flags != NORMAL_CLONE, ROI side > 8194, bbox smaller than 3 */
+    SCB_ERR_CUDA = 4,              /* a CUDA call failed; scb_last_error has the text            */
+    SCB_ERR_NO_DEVICE = 5,
+    SCB_ERR_OUT_OF_MEMORY = 6
+};
+
+/* cv::seamlessClone flags (photo.hpp); only NORMAL_CLONE is implemented */
+enum { SCB_NORMAL_CLONE = 1, SCB_MIXED_CLONE = 2, SCB_MONOCHROME_TRANSFER = 3 };
+
+/* where the pixel buffers of a call live */
+enum { SCB_MEM_HOST = 0, SCB_MEM_DEVICE = 1 };
+
+/* scb_plan_execute flags */
+enum {
+    SCB_EXEC_DEFAULT = 0,
+    SCB_EXEC_BLEND_PREFILLED = 1 /* blend already holds a copy of dst (or aliases it): write the ROI interior only */
+};
+
+/* scb_plan_get_intermediate selectors; all float32, planar [3][rows][cols] */
+enum {
+    SCB_INT_GRADIENT_X = 0, /* [3][h][w]    blended forward-difference gradient                  */
+    SCB_INT_GRADIENT_Y = 1, /* [3][h][w]                                                         */
+    SCB_INT_RHS = 2,        /* [3][ny][nx]  divergence minus Dirichlet boundary (OpenCV mod_diff) */
+    SCB_INT_SPECTRUM = 3,   /* [3][nx][ny]  forward 2-D DST, TRANSPOSED, before the division      */
+    SCB_INT_SOLVED = 4,     /* [3][ny][nx]  solved field before clamp / truncation                */
+    SCB_INT_ERODED_MASK = 5 /* [1][h][w]    eroded mask as float 0..255                           */
+};
+
+typedef struct scb_context scb_context;
+typedef struct scb_plan scb_plan;
+
+/* borrowed view of an 8-bit image; stride in bytes; channels 1 (mask) or 3 (BGR interleaved) */
+typedef struct scb_image {
+    void* data;
+    int32_t rows, cols, channels;
+    int64_t stride;
+} scb_image;
+
+typedef struct scb_geometry {
+    int32_t x, y, w, h;  /* bounding box of the ring-zeroed mask, in src/mask coordinates */
+    int32_t rx, ry;      /* ROI origin in dst: (px - w/2, py - h/2)                       */
+    int32_t nx, ny;      /* unknowns per channel: w-2, h-2                                */
+    int32_t empty;       /* mask had no interior non-zero pixel: blend = dst              */
+    int32_t log2m_x, log2m_y; /* convolution lengths chosen for the two DST axes           */
+} scb_geometry;
+
+/* ---- context ---- */
+/* external_stream: a cudaStream_t/CUstream to adopt (not owned), or NULL to create one. */
+int scb_create(int device, void* external_stream, scb_context** out);
+int scb_destroy(scb_context* ctx);
+int scb_sync(scb_context* ctx);
+void* scb_stream(scb_context* ctx);
+const char* scb_last_error(const scb_context* ctx); /* ctx may be NULL: error of the last failed scb_create on this thread */
+const char* scb_status_string(int status);
+uint64_t scb_kernel_launches(const scb_context* ctx); /* kernels this library has launched on ctx so far */
+int scb_device_count(void);
+
+/* pinned host memory helpers (cudaMallocHost / cudaFreeHost) */
+int scb_host_alloc(void** out, size_t bytes);
+int scb_host_free(void* p);
+
+/* ---- plan: everything that depends on (mask, sizes, p) only ---- */
+int scb_plan_create(scb_context* ctx, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                    int dst_rows, int dst_cols, int px, int py, scb_plan** out);
+int scb_plan_destroy(scb_plan* plan);
+int scb_plan_geometry(const scb_plan* plan, scb_geometry* out);
+/* Asynchronous on the context stream for SCB_MEM_DEVICE; for SCB_MEM_HOST returns when blend is complete. */
+int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags);
+int scb_plan_set_debug(scb_plan* plan, int on);
+int scb_plan_get_intermediate(scb_plan* plan, int which, float* out_host, size_t capacity_floats, size_t* written);
+
+/* ---- one-shot, OpenCV-shaped ---- */
+int scb_seamless_clone(scb_context* ctx, const scb_image* src, const scb_image* dst, const scb_image* mask,
+                       int px, int py, scb_image* blend, int clone_flags, int mem_kind);
+
+/* ---- batch of independent jobs (all HOST or all DEVICE) ---- */
+typedef struct scb_job {
+    scb_image src, dst, mask, blend;
+    int32_t px, py;
+    int32_t status; /* out */
+} scb_job;
+int scb_clone_batch(scb_context* ctx, scb_job* jobs, int n_jobs, int mem_kind);
+
+/* ---- row/column-sharded single solve (one rank per GPU; the caller exchanges At / Ct between the passes) ---- */
+/* Runs pass A (stencil + row DST) for interior rows [y0, y1) into `at` ([3][nx][ny] device buffer). */
+int scb_plan_rows_forward(scb_plan* plan, const scb_image* src, const scb_image* dst, int mem_kind, int y0, int y1, float* at_dev, double* lowrows_dev);
+/* Runs pass B for columns [x0, x1): reads at_dev ([3][nx][ny]), writes ct_dev ([3][ny][nx]). lowspec_dev may be NULL. */
+int scb_plan_cols(scb_plan* plan, int x0, int x1, const float* at_dev, float* ct_dev, const float* lowspec_dev);
+/* Reduces the low-frequency row sums ([3][lowkx][ny], complete over all rows) into lowspec ([3][lowkx][lowky]). */
+int scb_plan_lowfreq_finish(scb_plan* plan, const double* lowrows_dev, float* lowspec_dev);
+/* Runs pass C for interior rows [y0, y1): reads ct_dev, writes the blend interior rows. */
+int scb_plan_rows_inverse(scb_plan* plan, const float* ct_dev, scb_image* blend, int mem_kind, int y0, int y1);
+int scb_plan_lowk(const scb_plan* plan, int* lowkx, int* lowky);
+
+/* ---- the reference's four entry points (seamlessclone_cuda.h:4-63), POD views instead of cv::Mat* ---- */
+void* my_seamlessclone_api_imp_create_instance(int gpu_id);
+/* face = patch (src), body = dst; blend_out must be a caller-allocated image of dst's size. Returns a status code. */
+int my_seamlessclone_api_imp_run(void* instance_ptr, const scb_image* face, const scb_image* body, const scb_image* mask,
+                                 int centerX, int centerY, int gpu_id, int bSync, scb_image* blend_out);
+void my_seamlessclone_api_imp_destroy(void* instance_ptr);
+void my_seamlessclone_api_imp_sync(void* instance_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB_H_ */

@@ -1,0 +1,813 @@
+// scb_api.cu -- host driver + C ABI (include/scb.h) of the B200-native NORMAL_CLONE hot path.
+//
+// Mirrors, and replaces, the reference's instance layer:
+//   /root/reference/seamlessClone-CUDA/seamlessClone_imp.cu:239-370   create / run / destroy / sync
+//   /root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp:430-486  seamlessCloneGPU (upload, run, download, scatter)
+//   /root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp:978-1116 initMask / init_resize
+// with the differences SURVEY.md 8b asks for: POD-only ABI, status codes instead of assert/exit,
+// cudaSetDevice on every entry, ROI-only transfers, no host sync inside the hot path other than the
+// one that reports a HOST-resident result, dst never modified, mask never modified.
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/scb.h"
+#include "scb_kernels.cuh"
+#include "scb_platform.h"
+#include "scb_tables.h"
+
+using namespace scb;
+
+#ifdef SCB_EMU
+static inline cudaError_t scbMallocAsync(void** p, size_t n, cudaStream_t) { return emu_malloc(p, n); }
+static inline cudaError_t scbFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
+#else
+static inline cudaError_t scbMallocAsync(void** p, size_t n, cudaStream_t s) { return cudaMallocAsync(p, n, s); }
+static inline cudaError_t scbFreeAsync(void* p, cudaStream_t s) { return cudaFreeAsync(p, s); }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+struct DevLenTab {
+    LenTabDev dev{};
+    void* block = nullptr;
+};
+
+struct scb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    std::map<int, DevLenTab> lentabs;   // keyed by n
+    std::map<int, float*> filters;      // keyed by ROI extent
+    char* ws = nullptr;
+    size_t ws_cap = 0;
+    int* bbox_dev = nullptr;
+    int* bbox_pinned = nullptr;  // [0..3] init pattern, [4..7] result
+    int sm_count = 148;
+    int max_smem = 232448;
+};
+
+struct scb_plan {
+    scb_context* ctx = nullptr;
+    scb_geometry g{};
+    int src_rows = 0, src_cols = 0, dst_rows = 0, dst_cols = 0;
+    unsigned char* E = nullptr;
+    long long e_pitch = 0;
+    LenTabDev tx{}, ty{};
+    const float* fx = nullptr;
+    const float* fy = nullptr;
+    int lowkx = 0, lowky = 0;
+    bool debug = false;
+    float *dbg_vx = nullptr, *dbg_vy = nullptr, *dbg_rhs = nullptr, *dbg_spec = nullptr, *dbg_u = nullptr;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(scb_context* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define SCB_CUDA(c, expr)                                                                               \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(c, e__ == cudaErrorMemoryAllocation ? SCB_ERR_OUT_OF_MEMORY : SCB_ERR_CUDA,     \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                           \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int ensure_ws(scb_context* c, size_t bytes) {
+    if (bytes <= c->ws_cap) return SCB_OK;
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->ws) SCB_CUDA(c, cudaFree(c->ws));
+    c->ws = nullptr;
+    c->ws_cap = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    SCB_CUDA(c, cudaMalloc(&c->ws, want));
+    c->ws_cap = want;
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch over the convolution length
+// ------------------------------------------------------------------------------------------------
+template <int LOG2M>
+struct Nch {
+    static constexpr int value = (LOG2M <= 13) ? 3 : 1;  // 3 x 16384-point lines do not fit in 227 KB
+};
+template <int LOG2M>
+static constexpr size_t smem_bytes() { return (size_t)Nch<LOG2M>::value * FftCfg<LOG2M>::PADDED * sizeof(float2); }
+
+template <int LOG2M>
+static cudaError_t configure_one() {
+    cudaError_t e;
+    const int s = (int)smem_bytes<LOG2M>();
+    e = cudaFuncSetAttribute(rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cols_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rows_inv_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
+}
+
+#define SCB_FOR_LOG2M(X) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
+
+static cudaError_t configure_all() {
+    cudaError_t e = cudaSuccess;
+#define X(L) if (e == cudaSuccess) e = configure_one<L>();
+    SCB_FOR_LOG2M(X)
+#undef X
+    return e;
+}
+
+template <int LOG2M>
+static void launch_rows_fwd_t(scb_context* c, int nlines, const RowsFwdParams& p) {
+    auto k = rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>;
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+}
+template <int LOG2M>
+static void launch_cols_t(scb_context* c, int nlines, const ColsParams& p) {
+    auto k = cols_kernel<LOG2M, Nch<LOG2M>::value>;
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+}
+template <int LOG2M>
+static void launch_rows_inv_t(scb_context* c, int nlines, const RowsInvParams& p) {
+    auto k = rows_inv_kernel<LOG2M, Nch<LOG2M>::value>;
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+}
+
+static void launch_rows_fwd(scb_context* c, int log2m, int nlines, const RowsFwdParams& p) {
+    if (nlines <= 0) return;
+    switch (log2m) {
+#define X(L) case L: launch_rows_fwd_t<L>(c, nlines, p); break;
+        SCB_FOR_LOG2M(X)
+#undef X
+    }
+    c->launches++;
+}
+static void launch_cols(scb_context* c, int log2m, int nlines, const ColsParams& p) {
+    if (nlines <= 0) return;
+    switch (log2m) {
+#define X(L) case L: launch_cols_t<L>(c, nlines, p); break;
+        SCB_FOR_LOG2M(X)
+#undef X
+    }
+    c->launches++;
+}
+static void launch_rows_inv(scb_context* c, int log2m, int nlines, const RowsInvParams& p) {
+    if (nlines <= 0) return;
+    switch (log2m) {
+#define X(L) case L: launch_rows_inv_t<L>(c, nlines, p); break;
+        SCB_FOR_LOG2M(X)
+#undef X
+    }
+    c->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table caches
+// ------------------------------------------------------------------------------------------------
+static int get_lentab(scb_context* c, int n, LenTabDev* out) {
+    auto it = c->lentabs.find(n);
+    if (it != c->lentabs.end()) {
+        *out = it->second.dev;
+        return SCB_OK;
+    }
+    HostLenTab h = build_len_tab(n);
+    const size_t M = (size_t)1 << h.log2m;
+    const size_t off_chirp = 0;
+    const size_t off_bhat = align_up(off_chirp + (n + 1) * sizeof(float2), 256);
+    const size_t off_tw = align_up(off_bhat + M * sizeof(float2), 256);
+    const size_t off_sin = align_up(off_tw + M * sizeof(float2), 256);
+    const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
+    std::vector<char> host(total, 0);
+    std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
+    std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
+    std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
+    std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
+    DevLenTab d;
+    SCB_CUDA(c, cudaMalloc(&d.block, total));
+    SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));  // `host` dies at scope exit
+    char* b = (char*)d.block;
+    d.dev.n = n;
+    d.dev.log2m = h.log2m;
+    d.dev.lowk = h.lowk;
+    d.dev.chirp = (const float2*)(b + off_chirp);
+    d.dev.bhat_t = (const float2*)(b + off_bhat);
+    d.dev.tw = (const float2*)(b + off_tw);
+    d.dev.sinlow = (const double*)(b + off_sin);
+    c->lentabs[n] = d;
+    *out = d.dev;
+    return SCB_OK;
+}
+
+static int get_filter(scb_context* c, int extent, const float** out) {
+    auto it = c->filters.find(extent);
+    if (it != c->filters.end()) {
+        *out = it->second;
+        return SCB_OK;
+    }
+    std::vector<float> f = build_filter(extent);
+    float* d = nullptr;
+    SCB_CUDA(c, cudaMalloc(&d, f.size() * sizeof(float)));
+    SCB_CUDA(c, cudaMemcpyAsync(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->filters[extent] = d;
+    *out = d;
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int scb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int scb_create(int device, void* external_stream, scb_context** out) {
+    if (!out) return fail(nullptr, SCB_ERR_INVALID_ARGUMENT, "scb_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+        return fail(nullptr, SCB_ERR_NO_DEVICE, "scb_create: no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, SCB_ERR_INVALID_ARGUMENT, "scb_create: device index out of range");
+    scb_context* c = new scb_context();
+    c->device = device;
+    auto bail = [&](const char* what, cudaError_t e) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        delete c;
+        return (int)SCB_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if (external_stream) {
+        c->stream = (cudaStream_t)external_stream;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if ((e = configure_all()) != cudaSuccess) return bail("cudaFuncSetAttribute (is this an sm_100a device?)", e);
+    if ((e = cudaMalloc(&c->bbox_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost(&c->bbox_pinned, 8 * sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
+    c->bbox_pinned[0] = INT_MAX;
+    c->bbox_pinned[1] = INT_MAX;
+    c->bbox_pinned[2] = -1;
+    c->bbox_pinned[3] = -1;
+    *out = c;
+    return SCB_OK;
+}
+
+extern "C" int scb_destroy(scb_context* c) {
+    if (!c) return SCB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->lentabs) cudaFree(kv.second.block);
+    for (auto& kv : c->filters) cudaFree(kv.second);
+    if (c->ws) cudaFree(c->ws);
+    if (c->bbox_dev) cudaFree(c->bbox_dev);
+    if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SCB_OK;
+}
+
+extern "C" int scb_sync(scb_context* c) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" void* scb_stream(scb_context* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" const char* scb_last_error(const scb_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+extern "C" uint64_t scb_kernel_launches(const scb_context* c) { return c ? c->launches : 0; }
+extern "C" const char* scb_status_string(int s) {
+    switch (s) {
+        case SCB_OK: return "ok";
+        case SCB_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case SCB_ERR_ROI_OUT_OF_BOUNDS: return "ROI outside dst";
+        case SCB_ERR_UNSUPPORTED: return "unsupported";
+        case SCB_ERR_CUDA: return "CUDA error";
+        case SCB_ERR_NO_DEVICE: return "no CUDA device";
+        case SCB_ERR_OUT_OF_MEMORY: return "out of device memory";
+    }
+    return "unknown status";
+}
+extern "C" int scb_host_alloc(void** out, size_t bytes) {
+    if (!out) return SCB_ERR_INVALID_ARGUMENT;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? SCB_OK : SCB_ERR_OUT_OF_MEMORY;
+}
+extern "C" int scb_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SCB_OK : SCB_ERR_CUDA; }
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+static void plan_free_debug(scb_plan* p) {
+    cudaFree(p->dbg_vx);
+    cudaFree(p->dbg_vy);
+    cudaFree(p->dbg_rhs);
+    cudaFree(p->dbg_spec);
+    cudaFree(p->dbg_u);
+    p->dbg_vx = p->dbg_vy = p->dbg_rhs = p->dbg_spec = p->dbg_u = nullptr;
+}
+
+extern "C" int scb_plan_destroy(scb_plan* p) {
+    if (!p) return SCB_OK;
+    cudaSetDevice(p->ctx->device);
+    if (p->E) scbFreeAsync(p->E, p->ctx->stream);
+    plan_free_debug(p);
+    delete p;
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                               int dst_rows, int dst_cols, int px, int py, scb_plan** out) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (!out) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: out is null");
+    *out = nullptr;
+    if (!mask || !mask->data) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask is null (pass an all-255 mask for 'no mask')");
+    if (mask->channels != 1) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask must be single channel 8-bit (convert colour masks to grey first)");
+    if (mask->rows != src_rows || mask->cols != src_cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask and src sizes differ");
+    if (src_rows < 3 || src_cols < 3 || dst_rows < 3 || dst_cols < 3) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: images must be at least 3x3");
+    if (mask->stride < mask->cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask stride smaller than a row");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+
+    MaskView mv;
+    mv.rows = mask->rows;
+    mv.cols = mask->cols;
+    if (mask_mem_kind == SCB_MEM_HOST) {
+        const size_t pitch = align_up((size_t)mask->cols, 16);
+        int rc = ensure_ws(c, pitch * mask->rows);
+        if (rc) return rc;
+        SCB_CUDA(c, cudaMemcpy2DAsync(c->ws, pitch, mask->data, (size_t)mask->stride, (size_t)mask->cols, (size_t)mask->rows, cudaMemcpyHostToDevice, c->stream));
+        mv.data = (const unsigned char*)c->ws;
+        mv.pitch = (long long)pitch;
+    } else if (mask_mem_kind == SCB_MEM_DEVICE) {
+        mv.data = (const unsigned char*)mask->data;
+        mv.pitch = mask->stride;
+    } else {
+        return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: bad mem kind");
+    }
+    // bbox of the ring-zeroed mask (OpenCV: copyMakeBorder + boundingRect)
+    SCB_CUDA(c, cudaMemcpyAsync(c->bbox_dev, c->bbox_pinned, 4 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    {
+        const long long total = (long long)mv.rows * mv.cols;
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
+        SCB_LAUNCH(mask_bbox_kernel, dim3((unsigned)blocks), dim3(256), 0, c->stream, mv, c->bbox_dev);
+        c->launches++;
+    }
+    SCB_CUDA(c, cudaMemcpyAsync(c->bbox_pinned + 4, c->bbox_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCB_CUDA(c, cudaGetLastError());
+    const int minx = c->bbox_pinned[4], miny = c->bbox_pinned[5], maxx = c->bbox_pinned[6], maxy = c->bbox_pinned[7];
+
+    scb_plan* p = new scb_plan();
+    p->ctx = c;
+    p->src_rows = src_rows;
+    p->src_cols = src_cols;
+    p->dst_rows = dst_rows;
+    p->dst_cols = dst_cols;
+    scb_geometry& g = p->g;
+    if (maxx < 0) {  // nothing inside the ring: OpenCV returns dst unchanged
+        g.empty = 1;
+        *out = p;
+        return SCB_OK;
+    }
+    g.x = minx;
+    g.y = miny;
+    g.w = maxx - minx + 1;
+    g.h = maxy - miny + 1;
+    g.rx = px - g.w / 2;  // truncating division on the BBOX size, like cv::seamlessClone
+    g.ry = py - g.h / 2;
+    g.nx = g.w - 2;
+    g.ny = g.h - 2;
+    auto bad = [&](int code, const char* msg) {
+        delete p;
+        return fail(c, code, msg);
+    };
+    if (g.rx < 0 || g.ry < 0 || g.rx + g.w > dst_cols || g.ry + g.h > dst_rows)
+        return bad(SCB_ERR_ROI_OUT_OF_BOUNDS, "seamlessClone: ROI (mask bounding box centred at p) does not fit inside dst");
+    if (g.w < 3 || g.h < 3) return bad(SCB_ERR_UNSUPPORTED, "seamlessClone: mask bounding box must be at least 3x3 (OpenCV itself crashes on such masks)");
+    g.log2m_x = choose_log2m(g.nx);
+    g.log2m_y = choose_log2m(g.ny);
+    if (g.log2m_x > kMaxLog2M || g.log2m_y > kMaxLog2M) return bad(SCB_ERR_UNSUPPORTED, "seamlessClone: ROI side larger than 8194 pixels is not supported");
+
+    // eroded mask, ROI sized
+    p->e_pitch = (long long)align_up((size_t)g.w, 16);
+    {
+        void* e = nullptr;
+        cudaError_t ce = scbMallocAsync(&e, (size_t)p->e_pitch * g.h, c->stream);
+        if (ce != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
+        p->E = (unsigned char*)e;
+    }
+    SCB_LAUNCH(mask_erode_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, c->stream, mv, g.x, g.y, g.w, g.h, p->E, p->e_pitch);
+    c->launches++;
+    int rc;
+    if ((rc = get_lentab(c, g.nx, &p->tx)) || (rc = get_lentab(c, g.ny, &p->ty)) || (rc = get_filter(c, g.w, &p->fx)) || (rc = get_filter(c, g.h, &p->fy))) {
+        scb_plan_destroy(p);
+        return rc;
+    }
+    p->lowkx = p->tx.lowk;
+    p->lowky = p->ty.lowk;
+    if (mask_mem_kind == SCB_MEM_HOST) SCB_CUDA(c, cudaStreamSynchronize(c->stream));  // the staged mask lives in the shared workspace
+    *out = p;
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_geometry(const scb_plan* p, scb_geometry* out) {
+    if (!p || !out) return SCB_ERR_INVALID_ARGUMENT;
+    *out = p->g;
+    return SCB_OK;
+}
+extern "C" int scb_plan_lowk(const scb_plan* p, int* lowkx, int* lowky) {
+    if (!p) return SCB_ERR_INVALID_ARGUMENT;
+    if (lowkx) *lowkx = p->lowkx;
+    if (lowky) *lowky = p->lowky;
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_set_debug(scb_plan* p, int on) {
+    if (!p) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    plan_free_debug(p);
+    p->debug = false;
+    if (on && !p->g.empty) {
+        const size_t roi = (size_t)3 * p->g.w * p->g.h * sizeof(float), in = (size_t)3 * p->g.nx * p->g.ny * sizeof(float);
+        SCB_CUDA(c, cudaMalloc(&p->dbg_vx, roi));
+        SCB_CUDA(c, cudaMalloc(&p->dbg_vy, roi));
+        SCB_CUDA(c, cudaMalloc(&p->dbg_rhs, in));
+        SCB_CUDA(c, cudaMalloc(&p->dbg_spec, in));
+        SCB_CUDA(c, cudaMalloc(&p->dbg_u, in));
+        p->debug = true;
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_get_intermediate(scb_plan* p, int which, float* out_host, size_t capacity, size_t* written) {
+    if (!p || !out_host) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: empty plan");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const size_t roi = (size_t)3 * p->g.w * p->g.h, in = (size_t)3 * p->g.nx * p->g.ny;
+    const float* src = nullptr;
+    size_t n = 0;
+    switch (which) {
+        case SCB_INT_GRADIENT_X: src = p->dbg_vx; n = roi; break;
+        case SCB_INT_GRADIENT_Y: src = p->dbg_vy; n = roi; break;
+        case SCB_INT_RHS: src = p->dbg_rhs; n = in; break;
+        case SCB_INT_SPECTRUM: src = p->dbg_spec; n = in; break;
+        case SCB_INT_SOLVED: src = p->dbg_u; n = in; break;
+        case SCB_INT_ERODED_MASK: {
+            n = (size_t)p->g.w * p->g.h;
+            if (capacity < n) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: buffer too small");
+            std::vector<unsigned char> tmp((size_t)p->e_pitch * p->g.h);
+            SCB_CUDA(c, cudaMemcpyAsync(tmp.data(), p->E, tmp.size(), cudaMemcpyDeviceToHost, c->stream));
+            SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int y = 0; y < p->g.h; ++y)
+                for (int x = 0; x < p->g.w; ++x) out_host[(size_t)y * p->g.w + x] = (float)tmp[(size_t)y * p->e_pitch + x];
+            if (written) *written = n;
+            return SCB_OK;
+        }
+        default: return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: unknown selector");
+    }
+    if (!p->debug || !src) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: call scb_plan_set_debug(plan, 1) and execute first");
+    if (capacity < n) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: buffer too small");
+    SCB_CUDA(c, cudaMemcpyAsync(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (written) *written = n;
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// execute
+// ------------------------------------------------------------------------------------------------
+static int check_image(scb_context* c, const scb_image* im, int rows, int cols, const char* name) {
+    if (!im || !im->data) return fail(c, SCB_ERR_INVALID_ARGUMENT, std::string(name) + " is null");
+    if (im->channels != 3) return fail(c, SCB_ERR_INVALID_ARGUMENT, std::string(name) + " must be 8-bit 3-channel (BGR interleaved)");
+    if (im->rows != rows || im->cols != cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, std::string(name) + " has a different size than the plan was made for");
+    if (im->stride < (int64_t)3 * cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, std::string(name) + " stride smaller than a row");
+    return SCB_OK;
+}
+
+struct Workspace {
+    unsigned char *stD = nullptr, *stS = nullptr, *stO = nullptr;
+    long long pD = 0, pS = 0, pO = 0;
+    float *At = nullptr, *Ct = nullptr, *lowspec = nullptr;
+    double* R = nullptr;
+};
+
+static int carve(scb_plan* p, bool host, Workspace* w) {
+    scb_context* c = p->ctx;
+    const scb_geometry& g = p->g;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t in = (size_t)3 * g.nx * g.ny;
+    w->pD = w->pS = (long long)align_up((size_t)3 * g.w, 128);
+    w->pO = (long long)align_up((size_t)3 * g.nx, 128);
+    const size_t oAt = take(in * sizeof(float)), oCt = take(in * sizeof(float));
+    const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
+    const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
+    size_t oD = 0, oS = 0, oO = 0;
+    if (host) {
+        oD = take((size_t)w->pD * g.h);
+        oS = take((size_t)w->pS * g.h);
+        oO = take((size_t)w->pO * g.ny);
+    }
+    int rc = ensure_ws(c, off);
+    if (rc) return rc;
+    w->At = (float*)(c->ws + oAt);
+    w->Ct = (float*)(c->ws + oCt);
+    w->R = (double*)(c->ws + oR);
+    w->lowspec = (float*)(c->ws + oLow);
+    if (host) {
+        w->stD = (unsigned char*)(c->ws + oD);
+        w->stS = (unsigned char*)(c->ws + oS);
+        w->stO = (unsigned char*)(c->ws + oO);
+    }
+    return SCB_OK;
+}
+
+static StencilSrc make_stencil(const scb_plan* p, const unsigned char* D, long long dp, const unsigned char* S, long long sp) {
+    StencilSrc s;
+    s.D = D;
+    s.d_pitch = dp;
+    s.S = S;
+    s.s_pitch = sp;
+    s.E = p->E;
+    s.e_pitch = p->e_pitch;
+    s.w = p->g.w;
+    s.h = p->g.h;
+    return s;
+}
+
+static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y0, int y1) {
+    scb_context* c = p->ctx;
+    if (y1 <= y0) return;
+    LowRowsParams lp;
+    lp.st = st;
+    lp.sinx = p->tx.sinlow;
+    lp.nx = p->g.nx;
+    lp.ny = p->g.ny;
+    lp.lowkx = p->lowkx;
+    lp.R = R;
+    lp.rhs_in = nullptr;
+    lp.y0 = y0;
+    SCB_LAUNCH(lowfreq_rows_kernel, dim3(y1 - y0), dim3(kLowThreads), 0, c->stream, lp);
+    c->launches++;
+}
+static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec) {
+    scb_context* c = p->ctx;
+    LowColsParams lc;
+    lc.R = R;
+    lc.siny = p->ty.sinlow;
+    lc.ny = p->g.ny;
+    lc.lowkx = p->lowkx;
+    lc.lowky = p->lowky;
+    lc.lowspec = lowspec;
+    SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, c->stream, lc);
+    c->launches++;
+}
+static void run_rows_fwd(scb_plan* p, const StencilSrc& st, float* At, int y0, int y1) {
+    RowsFwdParams a;
+    a.st = st;
+    a.tx = p->tx;
+    a.nx = p->g.nx;
+    a.ny = p->g.ny;
+    a.At = At;
+    a.rhs_dump = p->debug ? p->dbg_rhs : nullptr;
+    a.rhs_in = nullptr;
+    a.y0 = y0;
+    launch_rows_fwd(p->ctx, p->g.log2m_x, y1 - y0, a);
+}
+static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
+    ColsParams b;
+    b.ty = p->ty;
+    b.nx = p->g.nx;
+    b.ny = p->g.ny;
+    b.At = At;
+    b.Ct = Ct;
+    b.fx = p->fx;
+    b.fy = p->fy;
+    b.lowspec = lowspec;
+    b.lowkx = p->lowkx;
+    b.lowky = p->lowky;
+    b.spec_dump = p->debug ? p->dbg_spec : nullptr;
+    b.inv_scale = (float)(1.0 / (double)(p->g.ny + 1));
+    b.x0 = x0;
+    launch_cols(p->ctx, p->g.log2m_y, x1 - x0, b);
+}
+static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1) {
+    RowsInvParams r;
+    r.tx = p->tx;
+    r.nx = p->g.nx;
+    r.ny = p->g.ny;
+    r.Ct = Ct;
+    r.out = out;
+    r.out_pitch = out_pitch;
+    r.u_dump = p->debug ? p->dbg_u : nullptr;
+    r.inv_scale = (float)(1.0 / (double)(p->g.nx + 1));
+    r.y0 = y0;
+    launch_rows_inv(p->ctx, p->g.log2m_x, y1 - y0, r);
+}
+
+extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags) {
+    if (!p) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    int rc;
+    if ((rc = check_image(c, src, p->src_rows, p->src_cols, "src"))) return rc;
+    if ((rc = check_image(c, dst, p->dst_rows, p->dst_cols, "dst"))) return rc;
+    if ((rc = check_image(c, blend, p->dst_rows, p->dst_cols, "blend"))) return rc;
+    if (mem_kind != SCB_MEM_HOST && mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_execute: bad mem kind");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const bool host = (mem_kind == SCB_MEM_HOST);
+    const bool copy_dst = (blend->data != dst->data) && !(exec_flags & SCB_EXEC_BLEND_PREFILLED);
+    const scb_geometry& g = p->g;
+    const size_t row_bytes = (size_t)3 * p->dst_cols;
+
+    if (g.empty) {  // OpenCV: blend = dst
+        if (copy_dst) {
+            if (host) {
+                for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
+            } else {
+                SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, c->stream));
+            }
+        }
+        return SCB_OK;
+    }
+
+    Workspace w;
+    if ((rc = carve(p, host, &w))) return rc;
+    const unsigned char* dROI = (const unsigned char*)dst->data + (size_t)g.ry * dst->stride + (size_t)3 * g.rx;
+    const unsigned char* sROI = (const unsigned char*)src->data + (size_t)g.y * src->stride + (size_t)3 * g.x;
+    unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
+    StencilSrc st;
+    unsigned char* out;
+    long long out_pitch;
+    if (host) {
+        // ROI-only transfers (the reference uploads the whole dst every call: seamlessClone_imp.cpp:419-421)
+        SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, c->stream));
+        SCB_CUDA(c, cudaMemcpy2DAsync(w.stS, (size_t)w.pS, sROI, (size_t)src->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, c->stream));
+        st = make_stencil(p, w.stD, w.pD, w.stS, w.pS);
+        out = w.stO;
+        out_pitch = w.pO;
+    } else {
+        if (copy_dst) SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, c->stream));
+        st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
+        out = bInt;
+        out_pitch = blend->stride;
+    }
+    if (p->debug) {
+        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, c->stream, st, p->dbg_vx, p->dbg_vy);
+        c->launches++;
+    }
+    run_lowfreq_rows(p, st, w.R, 0, g.ny);
+    run_lowfreq_cols(p, w.R, w.lowspec);
+    run_rows_fwd(p, st, w.At, 0, g.ny);
+    run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
+    run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+    SCB_CUDA(c, cudaGetLastError());
+    if (host) {
+        // blend = dst.copy() on the host while the GPU works, then only the ROI interior comes back
+        if (copy_dst)
+            for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
+        SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, c->stream));
+        SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+        SCB_CUDA(c, cudaGetLastError());
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const scb_image* dst, const scb_image* mask,
+                                  int px, int py, scb_image* blend, int clone_flags, int mem_kind) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (clone_flags != SCB_NORMAL_CLONE) return fail(c, SCB_ERR_UNSUPPORTED, "seamlessClone: only NORMAL_CLONE is implemented (no CPU fallback for MIXED_CLONE / MONOCHROME_TRANSFER)");
+    if (!src || !dst || !blend) return fail(c, SCB_ERR_INVALID_ARGUMENT, "seamlessClone: null image");
+    scb_plan* p = nullptr;
+    int rc = scb_plan_create(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, &p);
+    if (rc) return rc;
+    rc = scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
+    scb_plan_destroy(p);
+    return rc;
+}
+
+extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int mem_kind) {
+    if (!c || (!jobs && n_jobs > 0)) return SCB_ERR_INVALID_ARGUMENT;
+    int worst = SCB_OK;
+    for (int i = 0; i < n_jobs; ++i) {
+        scb_job& j = jobs[i];
+        j.status = scb_seamless_clone(c, &j.src, &j.dst, &j.mask, j.px, j.py, &j.blend, SCB_NORMAL_CLONE, mem_kind);
+        if (j.status != SCB_OK) worst = j.status;
+    }
+    if (mem_kind == SCB_MEM_DEVICE) {
+        int rc = scb_sync(c);
+        if (rc) return rc;
+    }
+    return worst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded single solve: the caller (one rank per GPU) owns At / Ct and exchanges them between passes
+// ------------------------------------------------------------------------------------------------
+static int check_range(scb_context* c, int a, int b, int n, const char* what) {
+    if (a < 0 || b < a || b > n) return fail(c, SCB_ERR_INVALID_ARGUMENT, std::string(what) + ": bad range");
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_rows_forward(scb_plan* p, const scb_image* src, const scb_image* dst, int mem_kind, int y0, int y1, float* at_dev, double* lowrows_dev) {
+    if (!p || !at_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
+    if (mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_UNSUPPORTED, "sharded solve: images must be device resident");
+    int rc;
+    if ((rc = check_image(c, src, p->src_rows, p->src_cols, "src"))) return rc;
+    if ((rc = check_image(c, dst, p->dst_rows, p->dst_cols, "dst"))) return rc;
+    if ((rc = check_range(c, y0, y1, p->g.ny, "scb_plan_rows_forward"))) return rc;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const scb_geometry& g = p->g;
+    const unsigned char* dROI = (const unsigned char*)dst->data + (size_t)g.ry * dst->stride + (size_t)3 * g.rx;
+    const unsigned char* sROI = (const unsigned char*)src->data + (size_t)g.y * src->stride + (size_t)3 * g.x;
+    StencilSrc st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
+    if (lowrows_dev) run_lowfreq_rows(p, st, lowrows_dev, y0, y1);
+    run_rows_fwd(p, st, at_dev, y0, y1);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_lowfreq_finish(scb_plan* p, const double* lowrows_dev, float* lowspec_dev) {
+    if (!p || !lowrows_dev || !lowspec_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    run_lowfreq_cols(p, lowrows_dev, lowspec_dev);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_cols(scb_plan* p, int x0, int x1, const float* at_dev, float* ct_dev, const float* lowspec_dev) {
+    if (!p || !at_dev || !ct_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
+    int rc;
+    if ((rc = check_range(c, x0, x1, p->g.nx, "scb_plan_cols"))) return rc;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    run_cols(p, at_dev, ct_dev, lowspec_dev, x0, x1);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_rows_inverse(scb_plan* p, const float* ct_dev, scb_image* blend, int mem_kind, int y0, int y1) {
+    if (!p || !ct_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
+    if (mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_UNSUPPORTED, "sharded solve: images must be device resident");
+    int rc;
+    if ((rc = check_image(c, blend, p->dst_rows, p->dst_cols, "blend"))) return rc;
+    if ((rc = check_range(c, y0, y1, p->g.ny, "scb_plan_rows_inverse"))) return rc;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const scb_geometry& g = p->g;
+    unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
+    run_rows_inv(p, ct_dev, bInt, blend->stride, y0, y1);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the reference's four names (seamlessclone_cuda.h:4-63)
+// ------------------------------------------------------------------------------------------------
+extern "C" void* my_seamlessclone_api_imp_create_instance(int gpu_id) {
+    scb_context* c = nullptr;
+    if (scb_create(gpu_id, nullptr, &c) != SCB_OK) {
+        std::fprintf(stderr, "my_seamlessclone_api_imp_create_instance: %s\n", scb_last_error(nullptr));
+        return nullptr;
+    }
+    return c;
+}
+extern "C" int my_seamlessclone_api_imp_run(void* inst, const scb_image* face, const scb_image* body, const scb_image* mask,
+                                            int centerX, int centerY, int /*gpu_id*/, int bSync, scb_image* blend_out) {
+    scb_context* c = (scb_context*)inst;
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    int rc = scb_seamless_clone(c, face, body, mask, centerX, centerY, blend_out, SCB_NORMAL_CLONE, SCB_MEM_HOST);
+    if (rc == SCB_OK && bSync) rc = scb_sync(c);
+    return rc;
+}
+extern "C" void my_seamlessclone_api_imp_destroy(void* inst) { scb_destroy((scb_context*)inst); }
+extern "C" void my_seamlessclone_api_imp_sync(void* inst) {
+    if (inst) scb_sync((scb_context*)inst);
+}

@@ -1,0 +1,434 @@
+// scb_kernels.cuh -- device code of the NORMAL_CLONE hot path.
+//
+// Data layout in HBM (one clone job; ROI = w x h, unknowns nx = w-2, ny = h-2):
+//   D, S      u8 interleaved BGR rows (caller's dst at the ROI origin / src at the mask-bbox origin,
+//             or pitched staging copies of exactly those rectangles when the caller's images are on the host)
+//   E         u8 h x w, mask after ring-zero + 3x erosion, cropped to the ROI        (plan-time)
+//   At        f32 [3][nx][ny]   row-transformed RHS, stored TRANSPOSED so that the column pass reads lines
+//   Ct        f32 [3][ny][nx]   after the column pass (forward, / eigenvalues, inverse), transposed back
+//   out       u8 interleaved, the ROI interior of `blend`
+// Three line passes, each one CTA per line and all three channels of the line together:
+//   rows_fwd : stencil (gradients (+) mask blend (+) divergence (+) Dirichlet injection) -> DST-I along x
+//   cols     : DST-I along y -> / (fx + fy - 4) -> inverse DST-I along y
+//   rows_inv : inverse DST-I along x -> clamp + truncate -> u8
+// so a pixel makes three HBM round trips (7+12 | 12+12 | 12+3 = 58 B per solved RGB pixel).
+//
+// What each piece replaces in the reference (/root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp):
+//   rhs_pixel            pre_process_kernel_gradient :1920-1964 + pre_process_kernel_lapXY :1966-2018
+//   rows_fwd/cols/rows_inv   dst() :1694-1811 (dft_kernel_0/1, cufftExecC2C x2, dft_copy_kernel_transpose),
+//                        updateUij_kernel_fft :1642-1669, scale_kernel_fft_transpose :1672-1691
+//   compose in rows_inv  post_processing :2078-2103
+//   mask_* kernels       setMaskBoundaryToConstant :967-976, calBoundingBox :927-963, myErode :892-925
+// Arithmetic follows OpenCV (the parity target), not the reference where the two differ.
+#pragma once
+
+#include "scb_fft.cuh"
+#include "scb_platform.h"
+
+namespace scb {
+
+struct LenTabDev {
+    int n, log2m, lowk;
+    const float2* chirp;
+    const float2* bhat_t;
+    const float2* tw;
+    const double* sinlow;
+};
+
+struct StencilSrc {
+    const unsigned char* D;  // dst pixel (0,0) of the ROI
+    long long d_pitch;
+    const unsigned char* S;  // src pixel at the mask-bbox origin
+    long long s_pitch;
+    const unsigned char* E;  // eroded mask, ROI sized
+    long long e_pitch;
+    int w, h;
+};
+
+// RHS of the Poisson system at interior pixel (x, y), 0 <= x < w-2, 0 <= y < h-2, all 3 channels.
+//   v   = grad(D) * (255-E)/255 + grad(S) * E/255      two rounded products, one rounded sum -- never an FMA
+//   lap = (vx[X] - vx[X-1]) + (vy[Y] - vy[Y-1])
+//   g   = lap - (dst pixels just outside the interior)  == OpenCV's  lap - Laplacian(bound)
+SCB_D void rhs_pixel(const StencilSrc& s, int x, int y, float g[3]) {
+    const int X = x + 1, Y = y + 1;
+    const unsigned char* d1 = s.D + (long long)Y * s.d_pitch + 3 * (X - 1);
+    const unsigned char* d0 = d1 - s.d_pitch + 3;
+    const unsigned char* d2 = d1 + s.d_pitch + 3;
+    const unsigned char* s1 = s.S + (long long)Y * s.s_pitch + 3 * (X - 1);
+    const unsigned char* s0 = s1 - s.s_pitch + 3;
+    const unsigned char* s2 = s1 + s.s_pitch + 3;
+    const unsigned char* e1 = s.E + (long long)Y * s.e_pitch + X;
+    const float inv255 = 1.0f / 255.0f;
+    const int ec = __ldg(e1), el = __ldg(e1 - 1), eu = __ldg(e1 - s.e_pitch);
+    const float mc = __fmul_rn((float)ec, inv255), mic = __fmul_rn((float)(255 - ec), inv255);
+    const float ml = __fmul_rn((float)el, inv255), mil = __fmul_rn((float)(255 - el), inv255);
+    const float mu = __fmul_rn((float)eu, inv255), miu = __fmul_rn((float)(255 - eu), inv255);
+    SCB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        const float Dl = (float)__ldg(d1 + c), Dc = (float)__ldg(d1 + 3 + c), Dr = (float)__ldg(d1 + 6 + c);
+        const float Du = (float)__ldg(d0 + c), Dd = (float)__ldg(d2 + c);
+        const float Sl = (float)__ldg(s1 + c), Sc = (float)__ldg(s1 + 3 + c), Sr = (float)__ldg(s1 + 6 + c);
+        const float Su = (float)__ldg(s0 + c), Sd = (float)__ldg(s2 + c);
+        const float vxc = __fadd_rn(__fmul_rn(Dr - Dc, mic), __fmul_rn(Sr - Sc, mc));
+        const float vxl = __fadd_rn(__fmul_rn(Dc - Dl, mil), __fmul_rn(Sc - Sl, ml));
+        const float vyc = __fadd_rn(__fmul_rn(Dd - Dc, mic), __fmul_rn(Sd - Sc, mc));
+        const float vyu = __fadd_rn(__fmul_rn(Dc - Du, miu), __fmul_rn(Sc - Su, mu));
+        const float lap = __fadd_rn(__fsub_rn(vxc, vxl), __fsub_rn(vyc, vyu));
+        float bnd = 0.f;
+        if (X == 1) bnd += Dl;
+        if (X == s.w - 2) bnd += Dr;
+        if (Y == 1) bnd += Du;
+        if (Y == s.h - 2) bnd += Dd;
+        g[c] = __fsub_rn(lap, bnd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass A: stencil -> forward DST-I along x.   grid = ny CTAs, block = FftCfg::T
+// ---------------------------------------------------------------------------------------------
+struct RowsFwdParams {
+    StencilSrc st;
+    LenTabDev tx;
+    int nx, ny;
+    float* At;            // [3][nx][ny]
+    float* rhs_dump;      // [3][ny][nx] or null
+    const float* rhs_in;  // [3][ny][nx] or null: bypass the stencil (sharded / test entry)
+    int y0;               // first interior row handled by this launch (row-sharded solves)
+};
+
+template <int LOG2M, int NCH>
+__global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_fwd_kernel(RowsFwdParams p) {
+    using C = FftCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, buf);
+    const int tid = threadIdx.x, y = p.y0 + blockIdx.x, n = p.nx;
+    for (int c0 = 0; c0 < 3; c0 += NCH) {
+        for (int j = tid; j < C::M; j += C::T) {
+            float g[3] = {0.f, 0.f, 0.f};
+            float2 ch = make_float2(0.f, 0.f);
+            if (j >= 1 && j <= n) {
+                if (p.rhs_in) {
+                    SCB_UNROLL
+                    for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.nx + (j - 1)];
+                } else {
+                    rhs_pixel(p.st, j - 1, y, g);
+                }
+                ch = __ldg(p.tx.chirp + j);
+                if (p.rhs_dump) {
+                    SCB_UNROLL
+                    for (int c = 0; c < NCH; ++c) p.rhs_dump[((size_t)(c0 + c) * p.ny + y) * p.nx + (j - 1)] = g[c0 + c];
+                }
+            }
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) buf[c * C::PADDED + padi(j)] = make_float2(g[c0 + c] * ch.x, g[c0 + c] * ch.y);
+        }
+        __syncthreads();
+        fft_convolve<LOG2M, NCH>(buf, p.tx.tw, p.tx.bhat_t, tid);
+        for (int k = tid + 1; k <= n; k += C::T) {
+            const float2 ch = __ldg(p.tx.chirp + k);
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                const float2 v = buf[c * C::PADDED + padi(k)];
+                const float s = ch.x * v.y + ch.y * v.x;  // Im(c[k] * conv[k]) = sum_j x[j] sin(pi j k / N)
+                p.At[((size_t)(c0 + c) * p.nx + (k - 1)) * p.ny + y] = -2.0f * s;  // OpenCV: Im of the odd-extension FFT
+            }
+        }
+        if (NCH < 3) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B: forward DST-I along y, eigenvalue division, inverse DST-I along y.  grid = nx CTAs
+// ---------------------------------------------------------------------------------------------
+struct ColsParams {
+    LenTabDev ty;
+    int nx, ny;
+    const float* At;       // [3][nx][ny]
+    float* Ct;             // [3][ny][nx]
+    const float* fx;       // nx   OpenCV filter_X
+    const float* fy;       // ny   OpenCV filter_Y
+    const float* lowspec;  // [3][lowkx][lowky] exact low-frequency corner of the forward spectrum, or null
+    int lowkx, lowky;
+    float* spec_dump;      // [3][nx][ny] forward 2-D spectrum before the division, or null
+    float inv_scale;       // 1 / (ny + 1)
+    int x0;                // first column handled by this launch (column-sharded solves)
+};
+
+template <int LOG2M, int NCH>
+__global__ void __launch_bounds__(FftCfg<LOG2M>::T) cols_kernel(ColsParams p) {
+    using C = FftCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, buf);
+    const int tid = threadIdx.x, kx = p.x0 + blockIdx.x, n = p.ny;
+    const float fxv = __ldg(p.fx + kx);
+    for (int c0 = 0; c0 < 3; c0 += NCH) {
+        for (int j = tid; j < C::M; j += C::T) {
+            const bool in = (j >= 1 && j <= n);
+            const float2 ch = in ? __ldg(p.ty.chirp + j) : make_float2(0.f, 0.f);
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                const float v = in ? __ldg(p.At + ((size_t)(c0 + c) * p.nx + kx) * p.ny + (j - 1)) : 0.f;
+                buf[c * C::PADDED + padi(j)] = make_float2(v * ch.x, v * ch.y);
+            }
+        }
+        __syncthreads();
+        fft_convolve<LOG2M, NCH>(buf, p.ty.tw, p.ty.bhat_t, tid);
+        for (int j = tid; j < C::M; j += C::T) {
+            const bool in = (j >= 1 && j <= n);
+            float2 ch = make_float2(0.f, 0.f);
+            float den = 1.f;
+            if (in) {
+                ch = __ldg(p.ty.chirp + j);
+                // OpenCV: res /= (filter_X[i] + filter_Y[j] - 4), evaluated left to right in float32
+                den = __fsub_rn(__fadd_rn(fxv, __ldg(p.fy + (j - 1))), 4.0f);
+            }
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                float2 o = make_float2(0.f, 0.f);
+                if (in) {
+                    const float2 v = buf[c * C::PADDED + padi(j)];
+                    float s = -2.0f * (ch.x * v.y + ch.y * v.x);
+                    if (p.lowspec && kx < p.lowkx && (j - 1) < p.lowky) s = __ldg(p.lowspec + ((size_t)(c0 + c) * p.lowkx + kx) * p.lowky + (j - 1));
+                    if (p.spec_dump) p.spec_dump[((size_t)(c0 + c) * p.nx + kx) * p.ny + (j - 1)] = s;
+                    const float q = __fdiv_rn(s, den);
+                    o = make_float2(q * ch.x, q * ch.y);
+                }
+                buf[c * C::PADDED + padi(j)] = o;
+            }
+        }
+        __syncthreads();
+        fft_convolve<LOG2M, NCH>(buf, p.ty.tw, p.ty.bhat_t, tid);
+        for (int k = tid + 1; k <= n; k += C::T) {
+            const float2 ch = __ldg(p.ty.chirp + k);
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                const float2 v = buf[c * C::PADDED + padi(k)];
+                p.Ct[((size_t)(c0 + c) * p.ny + (k - 1)) * p.nx + kx] = (ch.x * v.y + ch.y * v.x) * p.inv_scale;
+            }
+        }
+        if (NCH < 3) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass C: inverse DST-I along x, clamp, truncate, interleaved u8 store.   grid = ny CTAs
+// ---------------------------------------------------------------------------------------------
+struct RowsInvParams {
+    LenTabDev tx;
+    int nx, ny;
+    const float* Ct;     // [3][ny][nx]
+    unsigned char* out;  // interior origin pixel of blend (or of the staging image)
+    long long out_pitch;
+    float* u_dump;       // [3][ny][nx] solved field before clamp/truncate, or null
+    float inv_scale;     // 1 / (nx + 1)
+    int y0;
+};
+
+SCB_D unsigned char compose_u8(float v) {
+    // OpenCV solve(): v < 0 -> 0, v > 255 -> 255, else static_cast<uchar>(v)  (truncation toward zero)
+    return v < 0.f ? (unsigned char)0 : (v > 255.f ? (unsigned char)255 : (unsigned char)__float2int_rz(v));
+}
+
+template <int LOG2M, int NCH>
+__global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_inv_kernel(RowsInvParams p) {
+    using C = FftCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, buf);
+    const int tid = threadIdx.x, y = p.y0 + blockIdx.x, n = p.nx;
+    for (int c0 = 0; c0 < 3; c0 += NCH) {
+        for (int j = tid; j < C::M; j += C::T) {
+            const bool in = (j >= 1 && j <= n);
+            const float2 ch = in ? __ldg(p.tx.chirp + j) : make_float2(0.f, 0.f);
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                const float v = in ? __ldg(p.Ct + ((size_t)(c0 + c) * p.ny + y) * p.nx + (j - 1)) : 0.f;
+                buf[c * C::PADDED + padi(j)] = make_float2(v * ch.x, v * ch.y);
+            }
+        }
+        __syncthreads();
+        fft_convolve<LOG2M, NCH>(buf, p.tx.tw, p.tx.bhat_t, tid);
+        for (int k = tid + 1; k <= n; k += C::T) {
+            const float2 ch = __ldg(p.tx.chirp + k);
+            unsigned char* px = p.out + (long long)y * p.out_pitch + 3 * (k - 1);
+            SCB_UNROLL
+            for (int c = 0; c < NCH; ++c) {
+                const float2 v = buf[c * C::PADDED + padi(k)];
+                const float u = (ch.x * v.y + ch.y * v.x) * p.inv_scale;
+                if (p.u_dump) p.u_dump[((size_t)(c0 + c) * p.ny + y) * p.nx + (k - 1)] = u;
+                px[c0 + c] = compose_u8(u);
+            }
+        }
+        if (NCH < 3) __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact low-frequency corner of the forward spectrum (float64 direct sums)
+//   The Bluestein passes have a white float32 error floor; dividing by eigenvalues ~ (pi k / N)^2
+//   amplifies it at the lowest bins only.  Recomputing the kLowK x kLowK corner exactly removes
+//   > 95 % of the solve's error energy for ~1 % extra work (DESIGN.md "low-frequency refinement").
+// ---------------------------------------------------------------------------------------------
+static constexpr int kLowKDev = 8;
+static constexpr int kLowThreads = 128;
+
+template <int NACC>
+SCB_D void block_reduce_store(double (&acc)[NACC], double* red /* [kLowThreads/32][NACC] */, int tid) {
+    SCB_UNROLL
+    for (int i = 0; i < NACC; ++i) {
+        double v = acc[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        acc[i] = v;
+    }
+    if ((tid & 31) == 0) {
+        SCB_UNROLL
+        for (int i = 0; i < NACC; ++i) red[(tid >> 5) * NACC + i] = acc[i];
+    }
+    __syncthreads();
+}
+
+struct LowRowsParams {
+    StencilSrc st;
+    const double* sinx;  // [lowkx][nx]
+    int nx, ny, lowkx;
+    double* R;           // [3][lowkx][ny]   R = sum_x g[y][x] sin(pi (x+1)(k+1) / Nx)
+    const float* rhs_in;
+    int y0;
+};
+
+__global__ void __launch_bounds__(kLowThreads) lowfreq_rows_kernel(LowRowsParams p) {
+    __shared__ double red[(kLowThreads / 32) * 3 * kLowKDev];
+    const int tid = threadIdx.x, y = p.y0 + blockIdx.x;
+    double acc[3 * kLowKDev];
+    SCB_UNROLL
+    for (int i = 0; i < 3 * kLowKDev; ++i) acc[i] = 0.0;
+    for (int x = tid; x < p.nx; x += kLowThreads) {
+        float g[3];
+        if (p.rhs_in) {
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.nx + x];
+        } else {
+            rhs_pixel(p.st, x, y, g);
+        }
+        SCB_UNROLL
+        for (int k = 0; k < kLowKDev; ++k) {
+            if (k < p.lowkx) {
+                const double s = __ldg(p.sinx + (size_t)k * p.nx + x);
+                SCB_UNROLL
+                for (int c = 0; c < 3; ++c) acc[c * kLowKDev + k] += (double)g[c] * s;
+            }
+        }
+    }
+    block_reduce_store<3 * kLowKDev>(acc, red, tid);
+    if (tid < 3 * kLowKDev) {
+        double s = 0.0;
+        for (int w = 0; w < kLowThreads / 32; ++w) s += red[w * 3 * kLowKDev + tid];
+        const int c = tid / kLowKDev, k = tid % kLowKDev;
+        if (k < p.lowkx) p.R[((size_t)c * p.lowkx + k) * p.ny + y] = s;
+    }
+}
+
+struct LowColsParams {
+    const double* R;     // [3][lowkx][ny]
+    const double* siny;  // [lowky][ny]
+    int ny, lowkx, lowky;
+    float* lowspec;      // [3][lowkx][lowky]  = 4 * sum_y sum_x g sin sin   (OpenCV's unnormalised forward)
+};
+
+__global__ void __launch_bounds__(kLowThreads) lowfreq_cols_kernel(LowColsParams p) {
+    __shared__ double red[(kLowThreads / 32) * kLowKDev];
+    const int tid = threadIdx.x;
+    const int c = blockIdx.x / p.lowkx, kx = blockIdx.x % p.lowkx;
+    double acc[kLowKDev];
+    SCB_UNROLL
+    for (int i = 0; i < kLowKDev; ++i) acc[i] = 0.0;
+    const double* r = p.R + ((size_t)c * p.lowkx + kx) * p.ny;
+    for (int y = tid; y < p.ny; y += kLowThreads) {
+        const double rv = r[y];
+        SCB_UNROLL
+        for (int k = 0; k < kLowKDev; ++k)
+            if (k < p.lowky) acc[k] += rv * __ldg(p.siny + (size_t)k * p.ny + y);
+    }
+    block_reduce_store<kLowKDev>(acc, red, tid);
+    if (tid < p.lowky) {
+        double s = 0.0;
+        for (int w = 0; w < kLowThreads / 32; ++w) s += red[w * kLowKDev + tid];
+        p.lowspec[((size_t)c * p.lowkx + kx) * p.lowky + tid] = (float)(4.0 * s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask preparation (plan time)
+// ---------------------------------------------------------------------------------------------
+struct MaskView {
+    const unsigned char* data;
+    long long pitch;
+    int rows, cols;
+};
+
+// bbox of non-zero pixels of the ring-zeroed mask.  bbox = {minx, miny, maxx, maxy}, pre-set to
+// {INT_MAX, INT_MAX, -1, -1}.  OpenCV: copyMakeBorder(mask(1..-1), 0) + boundingRect.
+__global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
+    int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+    const long long total = (long long)m.rows * m.cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / m.cols), x = (int)(i - (long long)y * m.cols);
+        if (x == 0 || y == 0 || x == m.cols - 1 || y == m.rows - 1) continue;
+        if (__ldg(m.data + (long long)y * m.pitch + x)) {
+            minx = min(minx, x);
+            miny = min(miny, y);
+            maxx = max(maxx, x);
+            maxy = max(maxy, y);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        minx = min(minx, __shfl_xor_sync(0xffffffffu, minx, off));
+        miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, off));
+        maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, off));
+        maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, off));
+    }
+    if ((threadIdx.x & 31) == 0 && maxx >= 0) {
+        atomicMin(bbox + 0, minx);
+        atomicMin(bbox + 1, miny);
+        atomicMax(bbox + 2, maxx);
+        atomicMax(bbox + 3, maxy);
+    }
+}
+
+// E = erode(ring-zeroed mask, 3x3 ones, iterations = 3) cropped to the ROI: a 7x7 minimum over the
+// FULL mask (pixels outside the ROI take part; outside the image the border does not lower the min).
+__global__ void __launch_bounds__(256) mask_erode_kernel(MaskView m, int x0, int y0, int w, int h, unsigned char* E, long long e_pitch) {
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= w || Y >= h) return;
+    int v = 255;
+    for (int dy = -3; dy <= 3; ++dy) {
+        const int yy = y0 + Y + dy;
+        if (yy < 0 || yy >= m.rows) continue;
+        for (int dx = -3; dx <= 3; ++dx) {
+            const int xx = x0 + X + dx;
+            if (xx < 0 || xx >= m.cols) continue;
+            const bool ring = (xx == 0 || yy == 0 || xx == m.cols - 1 || yy == m.rows - 1);
+            const int pv = ring ? 0 : (int)__ldg(m.data + (long long)yy * m.pitch + xx);
+            v = min(v, pv);
+        }
+    }
+    E[(long long)Y * e_pitch + X] = (unsigned char)v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug: blended gradients over the whole ROI (test hook for the 1e-4 intermediate checks)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gradients_dump_kernel(StencilSrc s, float* vx, float* vy /* [3][h][w] */) {
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= s.w || Y >= s.h) return;
+    const int Xn = (X < s.w - 1) ? X + 1 : X - 1, Yn = (Y < s.h - 1) ? Y + 1 : Y - 1;  // BORDER_REFLECT_101
+    const int e = __ldg(s.E + (long long)Y * s.e_pitch + X);
+    const float inv255 = 1.0f / 255.0f;
+    const float m = __fmul_rn((float)e, inv255), mi = __fmul_rn((float)(255 - e), inv255);
+    for (int c = 0; c < 3; ++c) {
+        const float Dc = (float)s.D[(long long)Y * s.d_pitch + 3 * X + c], Dr = (float)s.D[(long long)Y * s.d_pitch + 3 * Xn + c];
+        const float Dd = (float)s.D[(long long)Yn * s.d_pitch + 3 * X + c];
+        const float Sc = (float)s.S[(long long)Y * s.s_pitch + 3 * X + c], Sr = (float)s.S[(long long)Y * s.s_pitch + 3 * Xn + c];
+        const float Sd = (float)s.S[(long long)Yn * s.s_pitch + 3 * X + c];
+        vx[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(Dr - Dc, mi), __fmul_rn(Sr - Sc, m));
+        vy[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(Dd - Dc, mi), __fmul_rn(Sd - Sc, m));
+    }
+}
+
+}  // namespace scb

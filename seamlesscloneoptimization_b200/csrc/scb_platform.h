@@ -1,0 +1,31 @@
+// Platform glue: the kernels and the host driver are written once and compile two ways.
+//
+//   nvcc (product)      : real CUDA for sm_100a.  This is the only thing the package ever loads.
+//   g++ -DSCB_EMU (CI)  : tests/emu/emu_cuda.h supplies a fiber-based SIMT interpreter (one fiber
+//                         per CUDA thread, __syncthreads/shuffles as fiber barriers) and a stub of
+//                         the few runtime calls the driver uses.  It exists so that the indexing
+//                         and host logic can be checked in the GPU-less authoring container; it is
+//                         built into tests/emu/_build/ only and is never importable from the package.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#ifdef SCB_EMU
+#include "emu_cuda.h"
+#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    ::emu::launch(kernel, grid, block, smem, __VA_ARGS__)
+#define SCB_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(::emu::dyn_smem())
+#define SCB_UNROLL
+#else
+#include <cuda_runtime.h>
+#define SCB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define SCB_DYN_SMEM(type, name)                                      \
+    extern __shared__ __align__(16) unsigned char name##_raw_[];     \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#define SCB_UNROLL _Pragma("unroll")
+#endif
+
+#define SCB_D __device__ __forceinline__
+#define SCB_HD __host__ __device__ __forceinline__

@@ -1,0 +1,125 @@
+// scb_tables.h -- host-side (plan-time) tables, all evaluated in double and rounded once.
+//
+//  * chirp / chirp spectrum / twiddles for the Bluestein DST-I engine (scb_fft.cuh)
+//  * sin rows for the exact low-frequency refinement
+//  * OpenCV's float32 eigenvalue filters, reproduced operation by operation:
+//      scale = CV_PI / (w - 1)  (double);  filter_X[i] = 2.0f * (float)cos(scale * (i + 1))
+//    (the reference's initDSTMatrix_kernel, /root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp:581-599,
+//     uses a float PI and deviates from OpenCV; OpenCV's recipe is the parity target)
+#pragma once
+
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <vector>
+
+namespace scb {
+
+static const int kLowK = 8;          // low-frequency corner refined exactly (kLowK x kLowK bins)
+static const int kMaxLog2M = 14;     // longest convolution: 16384  ->  n <= 8192 unknowns per line
+static const int kMinLog2M = 5;
+
+struct HostF2 { float x, y; };
+
+struct HostLenTab {
+    int n = 0, log2m = 0, lowk = 0;
+    std::vector<HostF2> chirp;   // n+1 : exp(+i pi j^2 / 2N)
+    std::vector<HostF2> bhat_t;  // M   : permuted spectrum of conj chirp, / M, operand-major
+    std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)
+    std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
+};
+
+inline int choose_log2m(int n) {
+    int need = 2 * n - 1;
+    int l = kMinLog2M;
+    while ((1 << l) < need) ++l;
+    return l;  // caller checks against kMaxLog2M
+}
+
+inline int first_radix(int log2m) { return (log2m % 4 == 0) ? 16 : (1 << (log2m % 4)); }
+
+typedef std::complex<double> cd;
+
+// The exact forward pass sequence of scb_fft.cuh (radix R0 at L = M, then radix 16 down to L = 16),
+// in double with directly evaluated DFT kernels.  Leaves the spectrum in the device's permuted order.
+inline void host_dif_forward(std::vector<cd>& a, int log2m) {
+    const int M = 1 << log2m;
+    const double PI = 3.14159265358979323846;
+    auto pass = [&](int R, int L) {
+        const int S = L / R;
+        std::vector<cd> wr(R * R), v(R), out(R);
+        for (int r = 0; r < R; ++r)
+            for (int q = 0; q < R; ++q) {
+                int e = (r * q) % R;
+                wr[r * R + q] = cd(std::cos(2 * PI * e / R), -std::sin(2 * PI * e / R));
+            }
+        for (int b = 0; b < M / R; ++b) {
+            const int i = b % S, base = (b / S) * L + i;
+            for (int r = 0; r < R; ++r) v[r] = a[base + r * S];
+            for (int q = 0; q < R; ++q) {
+                cd s(0, 0);
+                for (int r = 0; r < R; ++r) s += v[r] * wr[r * R + q];
+                long long e = (long long)i * q;  // < L
+                s *= cd(std::cos(2 * PI * e / L), -std::sin(2 * PI * e / L));
+                out[q] = s;
+            }
+            for (int q = 0; q < R; ++q) a[base + q * S] = out[q];
+        }
+    };
+    const int R0 = first_radix(log2m);
+    pass(R0, M);
+    for (int L = M / R0; L >= 16; L /= 16) pass(16, L);
+}
+
+inline HostLenTab build_len_tab(int n) {
+    HostLenTab t;
+    const double PI = 3.14159265358979323846;
+    t.n = n;
+    t.log2m = choose_log2m(n);
+    t.lowk = n < kLowK ? n : kLowK;
+    const int M = 1 << t.log2m;
+    const long long N = n + 1;
+    std::vector<cd> c(n + 1);
+    t.chirp.resize(n + 1);
+    for (long long j = 0; j <= n; ++j) {
+        long long ph = (j * j) % (4 * N);
+        double ang = PI * (double)ph / (2.0 * (double)N);
+        c[j] = cd(std::cos(ang), std::sin(ang));
+        t.chirp[j] = HostF2{(float)c[j].real(), (float)c[j].imag()};
+    }
+    std::vector<cd> b(M, cd(0, 0));
+    for (int m = 0; m <= n - 1; ++m) {
+        b[m] = std::conj(c[m]);
+        if (m) b[M - m] = std::conj(c[m]);
+    }
+    host_dif_forward(b, t.log2m);
+    t.bhat_t.resize(M);
+    for (int blk = 0; blk < M / 16; ++blk)
+        for (int q = 0; q < 16; ++q) {
+            cd v = b[16 * blk + q] / (double)M;
+            t.bhat_t[(size_t)q * (M / 16) + blk] = HostF2{(float)v.real(), (float)v.imag()};
+        }
+    t.tw.resize(M);
+    for (int k = 0; k < M; ++k) {
+        double ang = 2.0 * PI * (double)k / (double)M;
+        t.tw[k] = HostF2{(float)std::cos(ang), (float)(-std::sin(ang))};
+    }
+    t.sinlow.resize((size_t)t.lowk * n);
+    for (int k = 0; k < t.lowk; ++k)
+        for (int j = 0; j < n; ++j) {
+            long long e = ((long long)(j + 1) * (k + 1)) % (2 * N);
+            t.sinlow[(size_t)k * n + j] = std::sin(PI * (double)e / (double)N);
+        }
+    return t;
+}
+
+// filter_X / filter_Y of OpenCV's Cloning::initVariables; `extent` is the ROI width (or height).
+inline std::vector<float> build_filter(int extent) {
+    const double CV_PI_ = 3.1415926535897932384626433832795;
+    std::vector<float> f(extent - 2);
+    const double scale = CV_PI_ / (extent - 1);
+    for (int i = 0; i < extent - 2; ++i) f[i] = 2.0f * (float)std::cos(scale * (i + 1));
+    return f;
+}
+
+}  // namespace scb
