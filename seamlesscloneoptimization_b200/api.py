@@ -22,7 +22,7 @@ from ._capi import (EXEC_BLEND_PREFILLED, EXEC_DEFAULT, MEM_DEVICE, MEM_HOST, MI
 
 def _gray_mask(mask: np.ndarray | None, src_hw) -> np.ndarray:
     """cv::seamlessClone accepts an empty mask (= all 255) and 1/3/4-channel masks (colour masks go
-    through cvtColor BGR2GRAY: (1868 B + 9617 G + 4899 R + 8192) >> 14)."""
+    through cvtColor BGR2GRAY, 4.x fixed point: (3735 B + 19235 G + 9798 R + 16384) >> 15)."""
     if mask is None or getattr(mask, "size", 0) == 0:
         return np.full(tuple(src_hw), 255, np.uint8)
     m = np.asarray(mask)
@@ -32,7 +32,7 @@ def _gray_mask(mask: np.ndarray | None, src_hw) -> np.ndarray:
         m = m[:, :, 0]
     elif m.ndim == 3 and m.shape[2] in (3, 4):
         b, g, r = (m[:, :, k].astype(np.uint32) for k in range(3))
-        m = ((b * 1868 + g * 9617 + r * 4899 + 8192) >> 14).astype(np.uint8)
+        m = ((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15).astype(np.uint8)
     elif m.ndim != 2:
         raise ScbError(capi.SCB_ERR_INVALID_ARGUMENT, "mask must be HxW, HxWx1, HxWx3 or HxWx4")
     if m.strides[-1] != 1:
@@ -141,6 +141,18 @@ class Plan:
             vs, vd, vb = (x if isinstance(x, capi.ScbImage) else capi.tensor_view(x) for x in (src, dst, blend))
         self.ctx._check(self.lib.scb_plan_execute(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags))
         return blend
+
+    STAGES = ("copy_in", "lowfreq", "rows_fwd", "cols", "rows_inv", "copy_out")
+
+    def execute_timed(self, src, dst, blend, mem_kind: int = MEM_HOST, flags: int = EXEC_DEFAULT) -> dict:
+        """execute() with CUDA events between the stages; returns {stage: ms} (syncs the stream)."""
+        if mem_kind == MEM_HOST:
+            vs, vd, vb = capi.host_view(_bgr(src, "src")), capi.host_view(_bgr(dst, "dst")), capi.host_view(blend)
+        else:
+            vs, vd, vb = (x if isinstance(x, capi.ScbImage) else capi.tensor_view(x) for x in (src, dst, blend))
+        ms = (C.c_float * 6)()
+        self.ctx._check(self.lib.scb_plan_execute_timed(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags, ms))
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
 
     def set_debug(self, on: bool = True):
         self.ctx._check(self.lib.scb_plan_set_debug(self.handle, int(on)))

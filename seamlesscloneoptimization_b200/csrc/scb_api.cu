@@ -627,7 +627,19 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
     launch_rows_inv(p->ctx, p->g.log2m_x, y1 - y0, r);
 }
 
-extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags) {
+// stage boundaries recorded by scb_plan_execute_timed
+enum { ST_BEGIN = 0, ST_IN, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_COUNT };
+
+struct StageTimer {
+    cudaEvent_t ev[ST_COUNT];
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    void mark(int i) {
+        if (on) cudaEventRecord(ev[i], stream);
+    }
+};
+
+static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     int rc;
@@ -660,6 +672,7 @@ extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_ima
     StencilSrc st;
     unsigned char* out;
     long long out_pitch;
+    tm.mark(ST_BEGIN);
     if (host) {
         // ROI-only transfers (the reference uploads the whole dst every call: seamlessClone_imp.cpp:419-421)
         SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, c->stream));
@@ -677,21 +690,54 @@ extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_ima
         SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, c->stream, st, p->dbg_vx, p->dbg_vy);
         c->launches++;
     }
+    tm.mark(ST_IN);
     run_lowfreq_rows(p, st, w.R, 0, g.ny);
     run_lowfreq_cols(p, w.R, w.lowspec);
+    tm.mark(ST_LOW);
     run_rows_fwd(p, st, w.At, 0, g.ny);
+    tm.mark(ST_ROWS_FWD);
     run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
+    tm.mark(ST_COLS);
     run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+    tm.mark(ST_ROWS_INV);
     SCB_CUDA(c, cudaGetLastError());
     if (host) {
         // blend = dst.copy() on the host while the GPU works, then only the ROI interior comes back
         if (copy_dst)
             for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
         SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, c->stream));
+        tm.mark(ST_OUT);
         SCB_CUDA(c, cudaStreamSynchronize(c->stream));
         SCB_CUDA(c, cudaGetLastError());
+    } else {
+        tm.mark(ST_OUT);
     }
     return SCB_OK;
+}
+
+extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags) {
+    StageTimer tm;
+    return execute_impl(p, src, dst, blend, mem_kind, exec_flags, tm);
+}
+
+// Same as scb_plan_execute, with CUDA events between the stages on the context stream; returns after a
+// stream sync.  stage_ms[6] = { input copies, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
+extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms) {
+    if (!p || !stage_ms) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    StageTimer tm;
+    tm.on = true;
+    tm.stream = c->stream;
+    for (int i = 0; i < ST_COUNT; ++i) SCB_CUDA(c, cudaEventCreate(&tm.ev[i]));
+    for (int i = 0; i < ST_COUNT - 1; ++i) stage_ms[i] = 0.f;
+    int rc = execute_impl(p, src, dst, blend, mem_kind, exec_flags, tm);
+    if (rc == SCB_OK && !p->g.empty) {
+        cudaStreamSynchronize(c->stream);
+        for (int i = 0; i < ST_COUNT - 1; ++i) cudaEventElapsedTime(&stage_ms[i], tm.ev[i], tm.ev[i + 1]);
+    }
+    for (int i = 0; i < ST_COUNT; ++i) cudaEventDestroy(tm.ev[i]);
+    return rc;
 }
 
 extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const scb_image* dst, const scb_image* mask,

@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def emu_lib():
+    """The g++ -DSCB_EMU build of the kernel + driver sources (CI checker; tests/emu/README)."""
+    import __graft_entry__ as ge
+
+    return ge.build_emu()
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    import __graft_entry__ as ge
+
+    if not os.path.exists(ge.LIB):
+        ge.build_cuda()
+    return ge.LIB

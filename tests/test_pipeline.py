@@ -1,0 +1,395 @@
+"""Parity tests proper.  Every test runs twice through the SAME C ABI:
+  [cuda]  the sm_100a library on a real B200                      (-m gpu)
+  [emu]   the g++ -DSCB_EMU build of the same sources on the CPU  (-m "not gpu"; checks indexing/host logic)
+Bar (BASELINE.json north_star): integer work bit-exact; float intermediates within 1e-4 relative;
+final image within +-1 LSB with >= 99.9 % of the solved bytes exact."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import seamlesscloneoptimization_b200 as scb
+from oracle import seamless_oracle as so
+from seamlesscloneoptimization_b200 import _capi as capi
+from tests import common
+
+
+class Backend:
+    def __init__(self, name, lib_path):
+        self.name, self.lib_path = name, lib_path
+        self.is_cuda = name == "cuda"
+
+    def context(self):
+        return scb.Context(0, lib_path=self.lib_path)
+
+    def to_device(self, a: np.ndarray):
+        """Return (scb_image view, holder).  In the emulator 'device' memory is host memory."""
+        if self.is_cuda:
+            import torch
+
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            return capi.tensor_view(t), t
+        h = np.ascontiguousarray(a).copy()
+        return capi.host_view(h), h
+
+    def to_host(self, holder) -> np.ndarray:
+        return holder.cpu().numpy() if self.is_cuda else holder
+
+    def dev_buffer(self, n, dtype):
+        if self.is_cuda:
+            import torch
+
+            t = torch.full((n,), float("nan"), dtype={np.float32: torch.float32, np.float64: torch.float64}[dtype], device="cuda")
+            return t.data_ptr(), t
+        a = np.full(n, np.nan, dtype)
+        return a.ctypes.data, a
+
+
+@pytest.fixture(scope="module", params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def be(request):
+    if request.param == "emu":
+        return Backend("emu", request.getfixturevalue("emu_lib"))
+    return Backend("cuda", request.getfixturevalue("cuda_lib"))
+
+
+@pytest.fixture(scope="module")
+def ctx(be):
+    c = be.context()
+    yield c
+    c.close()
+
+
+def roi_interior(img, g):
+    return img[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
+
+
+def assert_matches(blend, ref_blend, g, what="", u_ref=None):
+    """+-1 LSB everywhere; >= 99.9 % exact.  Truncation makes a pixel whose exact value sits ON an
+    integer flip under any float noise (OpenCV's own included), so pixels whose oracle value lies
+    within the float tolerance of an integer are not counted as mismatches (they still must be +-1)."""
+    a, b = roi_interior(blend, g), roi_interior(ref_blend, g)
+    cmp = so.compare_u8(a, b)
+    assert cmp["max_abs"] <= common.U8_MAX_ABS, (what, cmp)
+    diff = a != b
+    if u_ref is not None:
+        on_boundary = np.abs(u_ref - np.rint(u_ref)) < common.FLOAT_REL_TOL * 255.0
+        diff = diff & ~on_boundary
+    assert int(diff.sum()) <= common.allowed_mismatches(a.size), (what, cmp)
+    outside = np.ones(blend.shape[:2], bool)
+    outside[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = False
+    assert np.array_equal(blend[outside], ref_blend[outside]), what
+    return cmp
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", common.golden_names())
+def test_golden_vectors(ctx, name):
+    common.check_against_golden(ctx, name)
+
+
+@pytest.mark.parametrize("cfg,seed", [("small", 1), ("small", 4), ("cfg1", 0)])
+def test_configs_vs_oracle(ctx, cfg, seed):
+    src, dst, mask, p = so.make_config(cfg, seed)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    plan.set_debug(True)
+    blend = plan.execute(src, dst)
+    g = plan.geometry
+    assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs)
+    assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_X).transpose(1, 2, 0), ref.vx)
+    assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_Y).transpose(1, 2, 0), ref.vy)
+    assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
+    assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
+    assert_matches(blend, ref.blend, g, cfg, ref.solved)
+    plan.close()
+
+
+# every convolution length class (LOG2M) and every first-radix variant, thin ROIs to stay cheap
+SIZES_EMU = [(3, 3), (4, 7), (10, 18), (19, 35), (66, 40), (131, 20), (20, 259), (515, 12), (12, 1027)]
+SIZES_GPU_ONLY = [(2051, 12), (12, 2052), (4099, 10), (8194, 9), (9, 8194), (8194, 3)]
+
+
+def _run_size(ctx, w, h, seed=0):
+    """Full-rect mask whose ring-zeroed bbox is exactly w x h, cloned into a slightly larger dst."""
+    rng = np.random.default_rng(1000 * w + h + seed)
+    ws, hs = w + 2, h + 2
+    src = so.smooth_rand(rng, hs, ws, 2.0)
+    dst = so.smooth_rand(rng, hs + 5, ws + 7, 2.0)
+    mask = np.full((hs, ws), 255, np.uint8)
+    p = (3 + w // 2 + 1, 2 + h // 2 + 1)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    assert (ref.geom.w, ref.geom.h) == (w, h)
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    plan.set_debug(True)
+    blend = plan.execute(src, dst)
+    g = plan.geometry
+    assert (g.w, g.h, g.rx, g.ry) == (w, h, ref.geom.rx, ref.geom.ry)
+    assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs)
+    assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
+    assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
+    assert_matches(blend, ref.blend, g, f"{w}x{h}", ref.solved)
+    plan.close()
+
+
+@pytest.mark.parametrize("w,h", SIZES_EMU)
+def test_every_transform_length_class(ctx, w, h):
+    _run_size(ctx, w, h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", SIZES_GPU_ONLY)
+def test_long_transform_lengths(cuda_lib, w, h):
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        _run_size(c, w, h)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_error_behaviour(ctx):
+    src, dst, mask, p = so.make_config("small", 2)
+    with pytest.raises(scb.ScbError) as e:  # OpenCV: -215 assertion on the ROI
+        ctx.seamless_clone(src, dst, mask, (2, 2))
+    assert e.value.code == capi.SCB_ERR_ROI_OUT_OF_BOUNDS
+    with pytest.raises(scb.ScbError) as e:  # no CPU fallback for the other flags
+        ctx.seamless_clone(src, dst, mask, p, scb.MIXED_CLONE)
+    assert e.value.code == capi.SCB_ERR_UNSUPPORTED
+    with pytest.raises(scb.ScbError) as e:
+        ctx.seamless_clone(src, dst, mask[:-1], p)
+    assert e.value.code == capi.SCB_ERR_INVALID_ARGUMENT
+    tiny = np.zeros_like(mask)
+    tiny[10:12, 10:12] = 255  # 2x2 bbox: OpenCV itself crashes; we report
+    with pytest.raises(scb.ScbError) as e:
+        ctx.seamless_clone(src, dst, tiny, p)
+    assert e.value.code == capi.SCB_ERR_UNSUPPORTED
+    with pytest.raises(scb.ScbError):
+        ctx.seamless_clone(src.astype(np.float32), dst, mask, p)
+    # the context stays usable after errors
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    blend = ctx.seamless_clone(src, dst, mask, p)
+    assert so.compare_u8(blend, ref.blend)["max_abs"] <= 1
+
+
+def test_empty_mask_returns_dst(ctx):
+    src, dst, mask, p = so.make_config("small", 2)
+    z = np.zeros_like(mask)
+    z[0, :] = 255  # only ring pixels set: still empty after ring-zero
+    blend = ctx.seamless_clone(src, dst, z, p)
+    assert np.array_equal(blend, dst) and blend is not dst
+
+
+def test_mask_and_src_variants(ctx):
+    src, dst, mask, p = so.make_config("small", 6)
+    base = ctx.seamless_clone(src, dst, mask, p)
+    assert np.array_equal(ctx.seamless_clone(src, dst, mask[:, :, None], p), base)
+    assert np.array_equal(ctx.seamless_clone(src, dst, np.repeat(mask[:, :, None], 3, axis=2), p), base)
+    # no mask == all 255
+    full = ctx.seamless_clone(src, dst, None, p)
+    assert np.array_equal(full, ctx.seamless_clone(src, dst, np.full(src.shape[:2], 255, np.uint8), p))
+    # non-contiguous rows (views into bigger arrays) are taken as they are
+    big_s = np.zeros((src.shape[0] + 4, src.shape[1] + 6, 3), np.uint8)
+    big_s[2:-2, 3:-3] = src
+    big_d = np.zeros((dst.shape[0] + 2, dst.shape[1] + 10, 3), np.uint8)
+    big_d[1:-1, 5:-5] = dst
+    big_m = np.zeros((mask.shape[0], mask.shape[1] + 3), np.uint8)
+    big_m[:, :-3] = mask
+    assert np.array_equal(ctx.seamless_clone(big_s[2:-2, 3:-3], big_d[1:-1, 5:-5], big_m[:, :-3], p), base)
+    # grey src is replicated like OpenCV does
+    grey = src[:, :, 1].copy()
+    ref = so.restate(grey, dst, mask, p, transform="f64")
+    assert so.compare_u8(ctx.seamless_clone(grey, dst, mask, p), ref.blend)["max_abs"] <= 1
+
+
+def test_colour_mask_grey_conversion_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    from seamlesscloneoptimization_b200.api import _gray_mask
+
+    rng = np.random.default_rng(0)
+    m3 = rng.integers(0, 256, size=(33, 47, 3), dtype=np.uint8)
+    assert np.array_equal(_gray_mask(m3, (33, 47)), cv2.cvtColor(m3, cv2.COLOR_BGR2GRAY))
+
+
+def test_plan_reuse_streaming(ctx):
+    """cfg5 semantics: fixed mask/offset, new src/dst every frame, one plan."""
+    src, dst, mask, p = so.make_config("small", 8)
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    for seed in range(3):
+        s, d, _, _ = so.make_config("small", 20 + seed)
+        ref = so.restate(s, d, mask, p, transform="f64")
+        blend = plan.execute(s, d)
+        assert_matches(blend, ref.blend, plan.geometry, f"frame {seed}")
+    plan.close()
+
+
+def test_device_resident_inplace_and_prefilled(be, ctx):
+    src, dst, mask, p = so.make_config("small", 9)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    host_blend = ctx.seamless_clone(src, dst, mask, p)
+    vs, hs = be.to_device(src)
+    vd, hd = be.to_device(dst)
+    vm, hm = be.to_device(mask)
+    vb, hb = be.to_device(np.zeros_like(dst))
+    plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    plan.execute(vs, vd, vb, scb.MEM_DEVICE)
+    ctx.sync()
+    out = be.to_host(hb)
+    assert np.array_equal(out, host_blend), "device-resident and host-resident paths must agree bit for bit"
+    assert np.array_equal(be.to_host(hd), dst), "dst must not be modified"
+    # in place: blend aliases dst
+    plan.execute(vs, vd, vd, scb.MEM_DEVICE)
+    ctx.sync()
+    assert np.array_equal(be.to_host(hd), host_blend)
+    # prefilled: only the ROI interior is written
+    vb2, hb2 = be.to_device(np.full_like(dst, 7))
+    vd2, hd2 = be.to_device(dst)
+    plan.execute(vs, vd2, vb2, scb.MEM_DEVICE, scb.EXEC_BLEND_PREFILLED)
+    ctx.sync()
+    out2 = be.to_host(hb2)
+    g = plan.geometry
+    assert np.array_equal(roi_interior(out2, g), roi_interior(host_blend, g))
+    out2[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = 7
+    assert (out2 == 7).all()
+    assert_matches(host_blend, ref.blend, g)
+    plan.close()
+
+
+def test_reference_entry_points(be):
+    """The reference's Python class and its four extern "C" names (seamlessclone_cuda.h:4-63)."""
+    src, dst, mask, p = so.make_config("small", 10)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    sc = scb.SeamlessClone(lib_path=be.lib_path)
+    sc.loadMatsInSeamlessClone(src, dst, mask[:, :, None], p[0], p[1], 1)  # gpu_id=1 like SeamlessClone_test.py
+    blended = sc.seamlessClone()
+    sc.sync()
+    sc.destroy()
+    assert so.compare_u8(blended, ref.blend)["max_abs"] <= 1
+    lib = capi.load(be.lib_path)
+    inst = lib.my_seamlessclone_api_imp_create_instance(0)
+    assert inst
+    out = np.zeros_like(dst)
+    vs, vd, vm, vb = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(out)
+    rc = lib.my_seamlessclone_api_imp_run(inst, C.byref(vs), C.byref(vd), C.byref(vm), p[0], p[1], 0, 1, C.byref(vb))
+    assert rc == 0
+    lib.my_seamlessclone_api_imp_sync(inst)
+    lib.my_seamlessclone_api_imp_destroy(inst)
+    assert np.array_equal(out, blended)
+
+
+def test_batch_of_independent_jobs(be, ctx):
+    """cfg3 semantics at toy size: varied patch sizes/offsets, full and elliptic masks."""
+    jobs = so.make_batch_jobs(4, seed=3, dst_hw=(140, 200), w_range=(12, 90), h_range=(12, 70))
+    arr = (capi.ScbJob * len(jobs))()
+    keep, refs = [], []
+    for k, j in enumerate(jobs):
+        src, dst, mask, p = so.materialise_job(j, dst_hw=(140, 200), sigma=2.0)
+        blend = np.zeros_like(dst)
+        keep.append((src, dst, mask, blend))
+        refs.append(so.restate(src, dst, mask, p, transform="f64"))
+        arr[k].src, arr[k].dst, arr[k].mask, arr[k].blend = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(blend)
+        arr[k].px, arr[k].py = p
+    rc = ctx.lib.scb_clone_batch(ctx.handle, arr, len(jobs), scb.MEM_HOST)
+    assert rc == 0
+    for k in range(len(jobs)):
+        assert arr[k].status == 0
+        g = refs[k].geom
+        cmp = so.compare_u8(keep[k][3], refs[k].blend)
+        assert cmp["max_abs"] <= 1 and cmp["n_diff"] <= common.allowed_mismatches(3 * g.nx * g.ny)
+
+
+def test_sharded_solve_equals_single_solve(be, ctx):
+    """cfg4 structure at toy size: rows split in two 'ranks', transpose exchange, columns split in two,
+    exchange back, rows again.  The exchange here is a no-op because both halves write one buffer;
+    tests/test_distributed.py runs the real all-to-all over gloo."""
+    src, dst, mask, p = so.make_config("small", 12)
+    vs, hs = be.to_device(src)
+    vd, hd = be.to_device(dst)
+    vm, hm = be.to_device(mask)
+    vb, hb = be.to_device(dst)       # sharded passes write the interior only: start from a copy of dst
+    vb1, hb1 = be.to_device(np.zeros_like(dst))
+    plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    plan.execute(vs, vd, vb1, scb.MEM_DEVICE)
+    ctx.sync()
+    single = be.to_host(hb1).copy()
+    g = plan.geometry
+    lkx, lky = C.c_int(), C.c_int()
+    assert ctx.lib.scb_plan_lowk(plan.handle, C.byref(lkx), C.byref(lky)) == 0
+    n = 3 * g.nx * g.ny
+    at_p, at_h = be.dev_buffer(n, np.float32)
+    ct_p, ct_h = be.dev_buffer(n, np.float32)
+    lr_p, lr_h = be.dev_buffer(3 * lkx.value * g.ny, np.float64)
+    ls_p, ls_h = be.dev_buffer(3 * lkx.value * lky.value, np.float32)
+    ymid, xmid = g.ny // 3, g.nx // 2
+    for y0, y1 in ((0, ymid), (ymid, g.ny)):
+        ctx._check(ctx.lib.scb_plan_rows_forward(plan.handle, C.byref(vs), C.byref(vd), scb.MEM_DEVICE, y0, y1, at_p, lr_p))
+    ctx._check(ctx.lib.scb_plan_lowfreq_finish(plan.handle, lr_p, ls_p))
+    for x0, x1 in ((0, xmid), (xmid, g.nx)):
+        ctx._check(ctx.lib.scb_plan_cols(plan.handle, x0, x1, at_p, ct_p, ls_p))
+    for y0, y1 in ((0, ymid), (ymid, g.ny)):
+        ctx._check(ctx.lib.scb_plan_rows_inverse(plan.handle, ct_p, C.byref(vb), scb.MEM_DEVICE, y0, y1))
+    ctx.sync()
+    assert np.array_equal(be.to_host(hb), single)
+    plan.close()
+
+
+def test_launch_counter(ctx):
+    src, dst, mask, p = so.make_config("small", 13)
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    before = ctx.kernel_launches
+    plan.execute(src, dst)
+    assert ctx.kernel_launches - before == 5  # lowfreq rows, lowfreq cols, rows fwd, cols, rows inv
+    plan.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size cases: GPU only, against cv2.seamlessClone itself (cv2 is part of the image)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg5", "cfg2"])
+def test_full_size_vs_opencv(cuda_lib, cfg):
+    pytest.importorskip("cv2")
+    src, dst, mask, p = so.make_config(cfg, 0)
+    ref = so.cv_reference(src, dst, mask, p)
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        blend = c.seamless_clone(src, dst, mask, p)
+        plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
+        g = plan.geometry
+        plan.close()
+    cmp = so.compare_u8(roi_interior(blend, g), roi_interior(ref, g))
+    print(cfg, cmp)
+    assert cmp["max_abs"] <= 1
+    # the oracle's own float32 FFT noise bounds %exact from above: the
+    # float64 solve with OpenCV's denominator reaches 99.97 / 99.99 / 99.89 % at these three shapes
+    floor = {"cfg1": 99.9, "cfg5": 99.9, "cfg2": 99.8}[cfg]
+    assert cmp["pct_exact"] >= floor
+    outside = np.ones(dst.shape[:2], bool)
+    outside[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = False
+    assert np.array_equal(blend[outside], dst[outside])
+
+
+@pytest.mark.gpu
+def test_full_size_properties_cfg4(cuda_lib):
+    """8K config: too slow for the CPU oracle in a unit test (12-18 s per cv2 call), so check
+    size-independent properties instead: the solved field satisfies the discrete Poisson equation
+    (Laplacian(u) == rhs up to float32 noise) with the dst ring as Dirichlet boundary, and a constant
+    offset added to dst shifts the result by exactly that offset."""
+    import torch
+
+    src, dst, mask, p = so.make_config("cfg4", 0)
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
+        plan.set_debug(True)
+        blend = plan.execute(src, dst)
+        g = plan.geometry
+        rhs = torch.from_numpy(plan.intermediate(capi.INT_RHS)).double()
+        u = torch.from_numpy(plan.intermediate(capi.INT_SOLVED)).double()
+        plan.close()
+    assert (g.w, g.h) == (4094, 4094)
+    up = torch.zeros(3, g.ny + 2, g.nx + 2, dtype=torch.float64)
+    up[:, 1:-1, 1:-1] = u
+    lap = up[:, :-2, 1:-1] + up[:, 2:, 1:-1] + up[:, 1:-1, :-2] + up[:, 1:-1, 2:] - 4 * up[:, 1:-1, 1:-1]
+    # rhs = div(v) - boundary terms, and the solve inverts the zero-boundary Laplacian: lap(u) == rhs
+    resid = (lap - rhs).abs().max().item()
+    assert resid < 5e-2, resid  # |rhs| ~ 1e2..1e3, u ~ 1e2, float32 second differences
+    out = torch.from_numpy(roi_interior(blend, g).copy()).permute(2, 0, 1).double()
+    ucl = u.clamp(0, 255).floor()
+    assert (out - ucl).abs().max().item() <= 1.0
+    assert ((out - ucl).abs() > 0).double().mean().item() < 1e-3
