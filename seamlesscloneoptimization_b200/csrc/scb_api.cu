@@ -16,6 +16,7 @@
 
 #include "../../include/scb.h"
 #include "scb_kernels.cuh"
+#include "scb_kernels2.cuh"
 #include "scb_platform.h"
 #include "scb_tables.h"
 
@@ -96,22 +97,50 @@ static int ensure_ws(scb_context* c, size_t bytes) {
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch over the convolution length
 // ------------------------------------------------------------------------------------------------
+// Engine selection per convolution length:
+//   packed (scb_kernels2.cuh): NP = 3 pairs per CTA up to M = 4096, NP = 1 at M = 8192
+//   scalar (scb_kernels.cuh) : M = 16384 (one 139 KB sequence per CTA), or everything when
+//                              SCB_ENGINE=scalar is set in the environment (A/B checks)
 template <int LOG2M>
 struct Nch {
-    static constexpr int value = (LOG2M <= 13) ? 3 : 1;  // 3 x 16384-point lines do not fit in 227 KB
+    static constexpr int value = (LOG2M <= 13) ? 3 : 1;  // scalar engine: 3 x 16384-point lines do not fit in 227 KB
+};
+template <int LOG2M>
+struct Npairs {
+    static constexpr int value = (LOG2M <= 12) ? 3 : 1;
 };
 template <int LOG2M>
 static constexpr size_t smem_bytes() { return (size_t)Nch<LOG2M>::value * FftCfg<LOG2M>::PADDED * sizeof(float2); }
+template <int LOG2M>
+static constexpr size_t smem2_bytes() { return (size_t)Npairs<LOG2M>::value * FftCfg<LOG2M>::PADDED * sizeof(float4); }
+
+static bool use_scalar_engine(int log2m) {
+    static const bool forced = [] {
+        const char* e = std::getenv("SCB_ENGINE");
+        return e && std::strcmp(e, "scalar") == 0;
+    }();
+    return forced || log2m >= 14;
+}
+
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
 
 template <int LOG2M>
 static cudaError_t configure_one() {
     cudaError_t e;
-    const int s = (int)smem_bytes<LOG2M>();
-    e = cudaFuncSetAttribute(rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(cols_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rows_inv_kernel<LOG2M, Nch<LOG2M>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize, s);
+    if ((e = set_smem(rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>, smem_bytes<LOG2M>())) != cudaSuccess) return e;
+    if ((e = set_smem(cols_kernel<LOG2M, Nch<LOG2M>::value>, smem_bytes<LOG2M>())) != cudaSuccess) return e;
+    if ((e = set_smem(rows_inv_kernel<LOG2M, Nch<LOG2M>::value>, smem_bytes<LOG2M>())) != cudaSuccess) return e;
+    if constexpr (LOG2M <= 13) {
+        if ((e = set_smem(rows_fwd2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
+        if ((e = set_smem(cols2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
+        if ((e = set_smem(rows_inv2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 #define SCB_FOR_LOG2M(X) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
@@ -124,18 +153,47 @@ static cudaError_t configure_all() {
     return e;
 }
 
+static int ctas_for(int nlines, int np) { return (3 * nlines + 2 * np - 1) / (2 * np); }
+
 template <int LOG2M>
 static void launch_rows_fwd_t(scb_context* c, int nlines, const RowsFwdParams& p) {
+    if constexpr (LOG2M <= 13) {
+        if (!use_scalar_engine(LOG2M)) {
+            constexpr int NP = Npairs<LOG2M>::value;
+            RowsFwd2Params pp{p, p.tx.ptw, p.y0 + nlines};
+            auto k = rows_fwd2_kernel<LOG2M, NP>;
+            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            return;
+        }
+    }
     auto k = rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>;
     SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
 }
 template <int LOG2M>
 static void launch_cols_t(scb_context* c, int nlines, const ColsParams& p) {
+    if constexpr (LOG2M <= 13) {
+        if (!use_scalar_engine(LOG2M)) {
+            constexpr int NP = Npairs<LOG2M>::value;
+            Cols2Params pp{p, p.ty.ptw, p.x0 + nlines};
+            auto k = cols2_kernel<LOG2M, NP>;
+            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            return;
+        }
+    }
     auto k = cols_kernel<LOG2M, Nch<LOG2M>::value>;
     SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
 }
 template <int LOG2M>
 static void launch_rows_inv_t(scb_context* c, int nlines, const RowsInvParams& p) {
+    if constexpr (LOG2M <= 13) {
+        if (!use_scalar_engine(LOG2M)) {
+            constexpr int NP = Npairs<LOG2M>::value;
+            RowsInv2Params pp{p, p.tx.ptw, p.y0 + nlines};
+            auto k = rows_inv2_kernel<LOG2M, NP>;
+            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            return;
+        }
+    }
     auto k = rows_inv_kernel<LOG2M, Nch<LOG2M>::value>;
     SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
 }
@@ -182,12 +240,14 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     const size_t off_chirp = 0;
     const size_t off_bhat = align_up(off_chirp + (n + 1) * sizeof(float2), 256);
     const size_t off_tw = align_up(off_bhat + M * sizeof(float2), 256);
-    const size_t off_sin = align_up(off_tw + M * sizeof(float2), 256);
+    const size_t off_ptw = align_up(off_tw + M * sizeof(float2), 256);
+    const size_t off_sin = align_up(off_ptw + h.ptw.size() * sizeof(float2), 256);
     const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
     std::vector<char> host(total, 0);
     std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
+    std::memcpy(host.data() + off_ptw, h.ptw.data(), h.ptw.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
@@ -200,6 +260,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.chirp = (const float2*)(b + off_chirp);
     d.dev.bhat_t = (const float2*)(b + off_bhat);
     d.dev.tw = (const float2*)(b + off_tw);
+    d.dev.ptw = (const float2*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);
     c->lentabs[n] = d;
     *out = d.dev;

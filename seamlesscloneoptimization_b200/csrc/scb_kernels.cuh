@@ -32,6 +32,7 @@ struct LenTabDev {
     const float2* chirp;
     const float2* bhat_t;
     const float2* tw;
+    const float2* ptw;  // per-pass tables of the packed engine
     const double* sinlow;
 };
 

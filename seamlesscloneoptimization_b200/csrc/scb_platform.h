@@ -29,3 +29,21 @@
 
 #define SCB_D __device__ __forceinline__
 #define SCB_HD __host__ __device__ __forceinline__
+
+// Packed fp32x2 arithmetic: FADD2 / FMUL2 / FFMA2 on sm_100a (one instruction, two lanes, operand
+// negation and broadcast immediates are free).  The emulator spells them out per lane.
+namespace scb {
+#ifdef SCB_EMU
+SCB_D float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+SCB_D float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+SCB_D float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+SCB_D float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+#else
+SCB_D float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SCB_D float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+SCB_D float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+SCB_D float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+SCB_D float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+SCB_D float2 f2dup(float s) { return make_float2(s, s); }
+}  // namespace scb

@@ -25,7 +25,8 @@ struct HostLenTab {
     int n = 0, log2m = 0, lowk = 0;
     std::vector<HostF2> chirp;   // n+1 : exp(+i pi j^2 / 2N)
     std::vector<HostF2> bhat_t;  // M   : permuted spectrum of conj chirp, / M, operand-major
-    std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)
+    std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)                       (scalar engine)
+    std::vector<HostF2> ptw;     // per-pass [q-1][i] twiddles W_L^{iq}, q <= 8     (packed engine, scb_pfft.cuh)
     std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
 };
 
@@ -103,6 +104,19 @@ inline HostLenTab build_len_tab(int n) {
     for (int k = 0; k < M; ++k) {
         double ang = 2.0 * PI * (double)k / (double)M;
         t.tw[k] = HostF2{(float)std::cos(ang), (float)(-std::sin(ang))};
+    }
+    {   // per-pass coalesced tables, same order as ptw_offset16() in scb_pfft.cuh
+        auto emit = [&](int R, int L) {
+            const int S = L / R, rows = (R - 1 < 8) ? (R - 1) : 8;
+            for (int q = 1; q <= rows; ++q)
+                for (int i = 0; i < S; ++i) {
+                    const double ang = 2.0 * PI * (double)((long long)i * q) / (double)L;
+                    t.ptw.push_back(HostF2{(float)std::cos(ang), (float)(-std::sin(ang))});
+                }
+        };
+        const int R0 = first_radix(t.log2m);
+        emit(R0, M);
+        for (int L = M / R0; L > 16; L /= 16) emit(16, L);
     }
     t.sinlow.resize((size_t)t.lowk * n);
     for (int k = 0; k < t.lowk; ++k)
