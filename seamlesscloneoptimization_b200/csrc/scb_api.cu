@@ -16,7 +16,7 @@
 
 #include "../../include/scb.h"
 #include "scb_kernels.cuh"
-#include "scb_kernels2.cuh"
+#include "scb_kernels3.cuh"
 #include "scb_platform.h"
 #include "scb_tables.h"
 
@@ -40,6 +40,8 @@ struct scb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;              // low-frequency refinement runs here, beside pass A
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     std::map<int, DevLenTab> lentabs;   // keyed by n
@@ -98,21 +100,15 @@ static int ensure_ws(scb_context* c, size_t bytes) {
 // kernel dispatch over the convolution length
 // ------------------------------------------------------------------------------------------------
 // Engine selection per convolution length:
-//   packed (scb_kernels2.cuh): NP = 3 pairs per CTA up to M = 4096, NP = 1 at M = 8192
-//   scalar (scb_kernels.cuh) : M = 16384 (one 139 KB sequence per CTA), or everything when
-//                              SCB_ENGINE=scalar is set in the environment (A/B checks)
+//   group engine  (scb_kernels3.cuh): M <= 8192; CTA = 2 lines x 3 channel groups (1 group at M = 8192)
+//   scalar engine (scb_kernels.cuh) : M = 16384 (one 139 KB sequence per CTA), or everything when
+//                                     SCB_ENGINE=scalar is set in the environment (A/B checks)
 template <int LOG2M>
 struct Nch {
     static constexpr int value = (LOG2M <= 13) ? 3 : 1;  // scalar engine: 3 x 16384-point lines do not fit in 227 KB
 };
 template <int LOG2M>
-struct Npairs {
-    static constexpr int value = (LOG2M <= 12) ? 3 : 1;
-};
-template <int LOG2M>
 static constexpr size_t smem_bytes() { return (size_t)Nch<LOG2M>::value * FftCfg<LOG2M>::PADDED * sizeof(float2); }
-template <int LOG2M>
-static constexpr size_t smem2_bytes() { return (size_t)Npairs<LOG2M>::value * FftCfg<LOG2M>::PADDED * sizeof(float4); }
 
 static bool use_scalar_engine(int log2m) {
     static const bool forced = [] {
@@ -136,9 +132,9 @@ static cudaError_t configure_one() {
     if ((e = set_smem(cols_kernel<LOG2M, Nch<LOG2M>::value>, smem_bytes<LOG2M>())) != cudaSuccess) return e;
     if ((e = set_smem(rows_inv_kernel<LOG2M, Nch<LOG2M>::value>, smem_bytes<LOG2M>())) != cudaSuccess) return e;
     if constexpr (LOG2M <= 13) {
-        if ((e = set_smem(rows_fwd2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
-        if ((e = set_smem(cols2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
-        if ((e = set_smem(rows_inv2_kernel<LOG2M, Npairs<LOG2M>::value>, smem2_bytes<LOG2M>())) != cudaSuccess) return e;
+        if ((e = set_smem(rows_fwd3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
+        if ((e = set_smem(cols3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
+        if ((e = set_smem(rows_inv3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
@@ -153,16 +149,15 @@ static cudaError_t configure_all() {
     return e;
 }
 
-static int ctas_for(int nlines, int np) { return (3 * nlines + 2 * np - 1) / (2 * np); }
+template <int LOG2M>
+static dim3 group_grid(int nlines) { return dim3((nlines + 1) / 2, GCfg<LOG2M>::NG == 1 ? 3 : 1); }
 
 template <int LOG2M>
 static void launch_rows_fwd_t(scb_context* c, int nlines, const RowsFwdParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
-            constexpr int NP = Npairs<LOG2M>::value;
-            RowsFwd2Params pp{p, p.tx.ptw, p.y0 + nlines};
-            auto k = rows_fwd2_kernel<LOG2M, NP>;
-            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            RowsFwd3Params pp{p, p.tx.gtw, p.y0 + nlines};
+            SCB_LAUNCH(rows_fwd3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
             return;
         }
     }
@@ -173,10 +168,8 @@ template <int LOG2M>
 static void launch_cols_t(scb_context* c, int nlines, const ColsParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
-            constexpr int NP = Npairs<LOG2M>::value;
-            Cols2Params pp{p, p.ty.ptw, p.x0 + nlines};
-            auto k = cols2_kernel<LOG2M, NP>;
-            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            Cols3Params pp{p, p.ty.gtw, p.x0 + nlines};
+            SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
             return;
         }
     }
@@ -187,10 +180,8 @@ template <int LOG2M>
 static void launch_rows_inv_t(scb_context* c, int nlines, const RowsInvParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
-            constexpr int NP = Npairs<LOG2M>::value;
-            RowsInv2Params pp{p, p.tx.ptw, p.y0 + nlines};
-            auto k = rows_inv2_kernel<LOG2M, NP>;
-            SCB_LAUNCH(k, dim3(ctas_for(nlines, NP)), dim3(FftCfg<LOG2M>::T), smem2_bytes<LOG2M>(), c->stream, pp);
+            RowsInv3Params pp{p, p.tx.gtw, p.y0 + nlines};
+            SCB_LAUNCH(rows_inv3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
             return;
         }
     }
@@ -241,13 +232,13 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     const size_t off_bhat = align_up(off_chirp + (n + 1) * sizeof(float2), 256);
     const size_t off_tw = align_up(off_bhat + M * sizeof(float2), 256);
     const size_t off_ptw = align_up(off_tw + M * sizeof(float2), 256);
-    const size_t off_sin = align_up(off_ptw + h.ptw.size() * sizeof(float2), 256);
+    const size_t off_sin = align_up(off_ptw + h.gtw.size() * sizeof(float), 256);
     const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
     std::vector<char> host(total, 0);
     std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
-    std::memcpy(host.data() + off_ptw, h.ptw.data(), h.ptw.size() * sizeof(HostF2));
+    std::memcpy(host.data() + off_ptw, h.gtw.data(), h.gtw.size() * sizeof(float));
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
@@ -260,7 +251,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.chirp = (const float2*)(b + off_chirp);
     d.dev.bhat_t = (const float2*)(b + off_bhat);
     d.dev.tw = (const float2*)(b + off_tw);
-    d.dev.ptw = (const float2*)(b + off_ptw);
+    d.dev.gtw = (const float4*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);
     c->lentabs[n] = d;
     *out = d.dev;
@@ -314,6 +305,9 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
         c->own_stream = true;
     }
+    if ((e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if ((e = configure_all()) != cudaSuccess) return bail("cudaFuncSetAttribute (is this an sm_100a device?)", e);
@@ -336,6 +330,12 @@ extern "C" int scb_destroy(scb_context* c) {
     if (c->ws) cudaFree(c->ws);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
+    if (c->side) {
+        cudaStreamSynchronize(c->side);
+        cudaStreamDestroy(c->side);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SCB_OK;
@@ -618,7 +618,7 @@ static StencilSrc make_stencil(const scb_plan* p, const unsigned char* D, long l
     return s;
 }
 
-static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y0, int y1) {
+static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y0, int y1, cudaStream_t stream) {
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
     LowRowsParams lp;
@@ -630,10 +630,10 @@ static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y
     lp.R = R;
     lp.rhs_in = nullptr;
     lp.y0 = y0;
-    SCB_LAUNCH(lowfreq_rows_kernel, dim3(y1 - y0), dim3(kLowThreads), 0, c->stream, lp);
+    SCB_LAUNCH(lowfreq_rows_kernel, dim3(y1 - y0), dim3(kLowThreads), 0, stream, lp);
     c->launches++;
 }
-static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec) {
+static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec, cudaStream_t stream) {
     scb_context* c = p->ctx;
     LowColsParams lc;
     lc.R = R;
@@ -642,7 +642,7 @@ static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec) {
     lc.lowkx = p->lowkx;
     lc.lowky = p->lowky;
     lc.lowspec = lowspec;
-    SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, c->stream, lc);
+    SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, stream, lc);
     c->launches++;
 }
 static void run_rows_fwd(scb_plan* p, const StencilSrc& st, float* At, int y0, int y1) {
@@ -752,10 +752,19 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         c->launches++;
     }
     tm.mark(ST_IN);
-    run_lowfreq_rows(p, st, w.R, 0, g.ny);
-    run_lowfreq_cols(p, w.R, w.lowspec);
+    if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
+        run_lowfreq_rows(p, st, w.R, 0, g.ny, c->stream);
+        run_lowfreq_cols(p, w.R, w.lowspec, c->stream);
+    } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
+        SCB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+        SCB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        run_lowfreq_rows(p, st, w.R, 0, g.ny, c->side);
+        run_lowfreq_cols(p, w.R, w.lowspec, c->side);
+        SCB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
+    }
     tm.mark(ST_LOW);
     run_rows_fwd(p, st, w.At, 0, g.ny);
+    if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     tm.mark(ST_ROWS_FWD);
     run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
     tm.mark(ST_COLS);
@@ -851,7 +860,7 @@ extern "C" int scb_plan_rows_forward(scb_plan* p, const scb_image* src, const sc
     const unsigned char* dROI = (const unsigned char*)dst->data + (size_t)g.ry * dst->stride + (size_t)3 * g.rx;
     const unsigned char* sROI = (const unsigned char*)src->data + (size_t)g.y * src->stride + (size_t)3 * g.x;
     StencilSrc st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
-    if (lowrows_dev) run_lowfreq_rows(p, st, lowrows_dev, y0, y1);
+    if (lowrows_dev) run_lowfreq_rows(p, st, lowrows_dev, y0, y1, c->stream);
     run_rows_fwd(p, st, at_dev, y0, y1);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
@@ -862,7 +871,7 @@ extern "C" int scb_plan_lowfreq_finish(scb_plan* p, const double* lowrows_dev, f
     scb_context* c = p->ctx;
     if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
     SCB_CUDA(c, cudaSetDevice(c->device));
-    run_lowfreq_cols(p, lowrows_dev, lowspec_dev);
+    run_lowfreq_cols(p, lowrows_dev, lowspec_dev, c->stream);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }

@@ -32,7 +32,7 @@ struct LenTabDev {
     const float2* chirp;
     const float2* bhat_t;
     const float2* tw;
-    const float2* ptw;  // per-pass tables of the packed engine
+    const float4* gtw;  // per-pass twiddle tables of the group engine (scb_gfft.cuh)
     const double* sinlow;
 };
 

@@ -26,7 +26,7 @@ struct HostLenTab {
     std::vector<HostF2> chirp;   // n+1 : exp(+i pi j^2 / 2N)
     std::vector<HostF2> bhat_t;  // M   : permuted spectrum of conj chirp, / M, operand-major
     std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)                       (scalar engine)
-    std::vector<HostF2> ptw;     // per-pass [q-1][i] twiddles W_L^{iq}, q <= 8     (packed engine, scb_pfft.cuh)
+    std::vector<float> gtw;      // per-pass [row][i] float4 (re_q, re_q+1, im_q, im_q+1), q = 1,3,5,7  (group engine, scb_gfft.cuh)
     std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
 };
 
@@ -105,13 +105,24 @@ inline HostLenTab build_len_tab(int n) {
         double ang = 2.0 * PI * (double)k / (double)M;
         t.tw[k] = HostF2{(float)std::cos(ang), (float)(-std::sin(ang))};
     }
-    {   // per-pass coalesced tables, same order as ptw_offset16() in scb_pfft.cuh
+    {   // per-pass coalesced tables, same order as gtw_offset16() in scb_gfft.cuh
         auto emit = [&](int R, int L) {
-            const int S = L / R, rows = (R - 1 < 8) ? (R - 1) : 8;
-            for (int q = 1; q <= rows; ++q)
+            const int S = L / R, rows = (R >= 16) ? 4 : R / 2;
+            for (int j = 0; j < rows; ++j)
                 for (int i = 0; i < S; ++i) {
-                    const double ang = 2.0 * PI * (double)((long long)i * q) / (double)L;
-                    t.ptw.push_back(HostF2{(float)std::cos(ang), (float)(-std::sin(ang))});
+                    float re[2] = {1.f, 1.f}, im[2] = {0.f, 0.f};
+                    for (int e = 0; e < 2; ++e) {
+                        const int q = 2 * j + 1 + e;
+                        if (q >= R && !(R == 16 && q == 8)) continue;
+                        if (q > 8) continue;
+                        const double ang = 2.0 * PI * (double)((long long)i * q) / (double)L;
+                        re[e] = (float)std::cos(ang);
+                        im[e] = (float)(-std::sin(ang));
+                    }
+                    t.gtw.push_back(re[0]);
+                    t.gtw.push_back(re[1]);
+                    t.gtw.push_back(im[0]);
+                    t.gtw.push_back(im[1]);
                 }
         };
         const int R0 = first_radix(t.log2m);

@@ -87,6 +87,8 @@ struct Block {
     Fiber* cur = nullptr;
     unsigned live = 0, bar_count = 0;
     unsigned long bar_gen = 0;
+    unsigned named_count[16] = {0};
+    unsigned long named_gen[16] = {0};
     std::function<void()> body;
     void* dyn = nullptr;
 };
@@ -105,6 +107,17 @@ inline void syncthreads() {
         return;
     }
     while (b->bar_gen == gen) yield();
+}
+// bar.sync id, nthreads : named barrier among a fixed number of threads
+inline void bar_sync(int id, unsigned nthreads) {
+    Block* b = g_blk;
+    unsigned long gen = b->named_gen[id];
+    if (++b->named_count[id] >= nthreads) {
+        b->named_count[id] = 0;
+        b->named_gen[id]++;
+        return;
+    }
+    while (b->named_gen[id] == gen) yield();
 }
 inline void syncwarp() {
     Block* b = g_blk;
@@ -153,6 +166,7 @@ inline void run_block(Block& b, unsigned nthreads, dim3 block) {
     b.live = nthreads;
     b.bar_count = 0;
     b.bar_gen = 0;
+    for (int k = 0; k < 16; ++k) b.named_count[k] = 0;
     for (unsigned t = 0; t < nthreads; ++t) {
         Fiber& f = b.fibers[t];
         f.done = false;
