@@ -111,7 +111,7 @@ int scb_plan_geometry(const scb_plan* plan, scb_geometry* out);
 /* Asynchronous on the context stream for SCB_MEM_DEVICE; for SCB_MEM_HOST returns when blend is complete. */
 int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags);
 /* Same call with CUDA events between the stages (on the context stream); returns after a stream sync.
- * stage_ms[6] = { input copies, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
+ * stage_ms[7] = { input copies, RHS stencil, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
  * (The reference times its whole run() with one event pair: seamlessClone_imp.cu:281-349.) */
 int scb_plan_execute_timed(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms);
 int scb_plan_set_debug(scb_plan* plan, int on);

@@ -142,7 +142,7 @@ class Plan:
         self.ctx._check(self.lib.scb_plan_execute(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags))
         return blend
 
-    STAGES = ("copy_in", "lowfreq", "rows_fwd", "cols", "rows_inv", "copy_out")
+    STAGES = ("copy_in", "rhs", "lowfreq", "rows_fwd", "cols", "rows_inv", "copy_out")
 
     def execute_timed(self, src, dst, blend, mem_kind: int = MEM_HOST, flags: int = EXEC_DEFAULT) -> dict:
         """execute() with CUDA events between the stages; returns {stage: ms} (syncs the stream)."""
@@ -150,7 +150,7 @@ class Plan:
             vs, vd, vb = capi.host_view(_bgr(src, "src")), capi.host_view(_bgr(dst, "dst")), capi.host_view(blend)
         else:
             vs, vd, vb = (x if isinstance(x, capi.ScbImage) else capi.tensor_view(x) for x in (src, dst, blend))
-        ms = (C.c_float * 6)()
+        ms = (C.c_float * 7)()
         self.ctx._check(self.lib.scb_plan_execute_timed(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags, ms))
         return dict(zip(self.STAGES, (float(v) for v in ms)))
 

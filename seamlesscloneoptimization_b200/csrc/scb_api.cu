@@ -566,7 +566,8 @@ static int check_image(scb_context* c, const scb_image* im, int rows, int cols, 
 struct Workspace {
     unsigned char *stD = nullptr, *stS = nullptr, *stO = nullptr;
     long long pD = 0, pS = 0, pO = 0;
-    float *At = nullptr, *Ct = nullptr, *lowspec = nullptr;
+    float *At = nullptr, *Ct = nullptr, *lowspec = nullptr, *G = nullptr;
+    int gp = 0;
     double* R = nullptr;
 };
 
@@ -582,7 +583,9 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     const size_t in = (size_t)3 * g.nx * g.ny;
     w->pD = w->pS = (long long)align_up((size_t)3 * g.w, 128);
     w->pO = (long long)align_up((size_t)3 * g.nx, 128);
+    w->gp = (int)align_up((size_t)g.nx, 4);
     const size_t oAt = take(in * sizeof(float)), oCt = take(in * sizeof(float));
+    const size_t oG = take((size_t)3 * g.ny * w->gp * sizeof(float));
     const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
     size_t oD = 0, oS = 0, oO = 0;
@@ -595,6 +598,7 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     if (rc) return rc;
     w->At = (float*)(c->ws + oAt);
     w->Ct = (float*)(c->ws + oCt);
+    w->G = (float*)(c->ws + oG);
     w->R = (double*)(c->ws + oR);
     w->lowspec = (float*)(c->ws + oLow);
     if (host) {
@@ -618,7 +622,26 @@ static StencilSrc make_stencil(const scb_plan* p, const unsigned char* D, long l
     return s;
 }
 
-static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y0, int y1, cudaStream_t stream) {
+static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0, int y1) {
+    scb_context* c = p->ctx;
+    if (y1 <= y0) return;
+    RhsParams rp;
+    rp.st = st;
+    rp.nx = p->g.nx;
+    rp.ny = p->g.ny;
+    rp.g = G;
+    rp.gp = gp;
+    rp.y0 = y0;
+    const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
+    SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, c->stream, rp);
+    c->launches++;
+    if (p->debug)  // dense [3][ny][nx] copy for scb_plan_get_intermediate
+        for (int ch = 0; ch < 3; ++ch)
+            cudaMemcpy2DAsync(p->dbg_rhs + ((size_t)ch * p->g.ny + y0) * p->g.nx, (size_t)p->g.nx * sizeof(float), G + ((size_t)ch * p->g.ny + y0) * gp,
+                              (size_t)gp * sizeof(float), (size_t)p->g.nx * sizeof(float), (size_t)(y1 - y0), cudaMemcpyDeviceToDevice, c->stream);
+}
+
+static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, const float* G, int gp, double* R, int y0, int y1, cudaStream_t stream) {
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
     LowRowsParams lp;
@@ -628,7 +651,8 @@ static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, double* R, int y
     lp.ny = p->g.ny;
     lp.lowkx = p->lowkx;
     lp.R = R;
-    lp.rhs_in = nullptr;
+    lp.rhs_in = G;
+    lp.rhs_pitch = gp;
     lp.y0 = y0;
     SCB_LAUNCH(lowfreq_rows_kernel, dim3(y1 - y0), dim3(kLowThreads), 0, stream, lp);
     c->launches++;
@@ -645,15 +669,16 @@ static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec, cudaS
     SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, stream, lc);
     c->launches++;
 }
-static void run_rows_fwd(scb_plan* p, const StencilSrc& st, float* At, int y0, int y1) {
+static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1) {
     RowsFwdParams a;
     a.st = st;
     a.tx = p->tx;
     a.nx = p->g.nx;
     a.ny = p->g.ny;
     a.At = At;
-    a.rhs_dump = p->debug ? p->dbg_rhs : nullptr;
-    a.rhs_in = nullptr;
+    a.rhs_dump = nullptr;
+    a.rhs_in = G;
+    a.rhs_pitch = gp;
     a.y0 = y0;
     launch_rows_fwd(p->ctx, p->g.log2m_x, y1 - y0, a);
 }
@@ -689,7 +714,7 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
 }
 
 // stage boundaries recorded by scb_plan_execute_timed
-enum { ST_BEGIN = 0, ST_IN, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_COUNT };
+enum { ST_BEGIN = 0, ST_IN, ST_RHS, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_COUNT };
 
 struct StageTimer {
     cudaEvent_t ev[ST_COUNT];
@@ -752,18 +777,20 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         c->launches++;
     }
     tm.mark(ST_IN);
+    run_rhs(p, st, w.G, w.gp, 0, g.ny);
+    tm.mark(ST_RHS);
     if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
-        run_lowfreq_rows(p, st, w.R, 0, g.ny, c->stream);
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, c->stream);
         run_lowfreq_cols(p, w.R, w.lowspec, c->stream);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
         SCB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
         SCB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-        run_lowfreq_rows(p, st, w.R, 0, g.ny, c->side);
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, c->side);
         run_lowfreq_cols(p, w.R, w.lowspec, c->side);
         SCB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
     }
     tm.mark(ST_LOW);
-    run_rows_fwd(p, st, w.At, 0, g.ny);
+    run_rows_fwd(p, st, w.G, w.gp, w.At, 0, g.ny);
     if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     tm.mark(ST_ROWS_FWD);
     run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
@@ -791,7 +818,7 @@ extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_ima
 }
 
 // Same as scb_plan_execute, with CUDA events between the stages on the context stream; returns after a
-// stream sync.  stage_ms[6] = { input copies, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
+// stream sync.  stage_ms[7] = { input copies, RHS stencil, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
 extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms) {
     if (!p || !stage_ms) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
@@ -860,8 +887,11 @@ extern "C" int scb_plan_rows_forward(scb_plan* p, const scb_image* src, const sc
     const unsigned char* dROI = (const unsigned char*)dst->data + (size_t)g.ry * dst->stride + (size_t)3 * g.rx;
     const unsigned char* sROI = (const unsigned char*)src->data + (size_t)g.y * src->stride + (size_t)3 * g.x;
     StencilSrc st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
-    if (lowrows_dev) run_lowfreq_rows(p, st, lowrows_dev, y0, y1, c->stream);
-    run_rows_fwd(p, st, at_dev, y0, y1);
+    Workspace w;
+    if ((rc = carve(p, false, &w))) return rc;
+    run_rhs(p, st, w.G, w.gp, y0, y1);
+    if (lowrows_dev) run_lowfreq_rows(p, st, w.G, w.gp, lowrows_dev, y0, y1, c->stream);
+    run_rows_fwd(p, st, w.G, w.gp, at_dev, y0, y1);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }

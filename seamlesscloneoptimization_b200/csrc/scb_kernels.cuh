@@ -85,6 +85,120 @@ SCB_D void rhs_pixel(const StencilSrc& s, int x, int y, float g[3]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stand-alone fused stencil: u8 dst/src/mask in, float RHS out, one HBM round trip per pixel
+// (7 B read + 12 B written).  Replaces pre_process_kernel_gradient + pre_process_kernel_lapXY
+// (imp.cpp:1920-2018), which move 24 + 24 B per pixel of float gradients through HBM in between.
+//
+// A thread owns 4 consecutive interior pixels of one row: it fetches the 3 x 20 bytes of dst, the
+// 3 x 20 bytes of src and the 2 x 8 bytes of mask it needs as aligned 32-bit words (funnel-shifted to
+// the pixel boundary -- rows of a caller's image start at any byte), and writes three float4.
+// Where all three mask taps are 0 or 255 -- everywhere except on grey masks -- the blend is a select
+// and the whole stencil runs in integer arithmetic (exact, hence bit-identical to the float path).
+// ---------------------------------------------------------------------------------------------
+struct RhsParams {
+    StencilSrc st;
+    int nx, ny;
+    float* g;  // [3][ny][gp]
+    int gp;    // row pitch of g in floats, multiple of 4
+    int y0;    // first interior row of this launch
+};
+
+template <int N>
+SCB_D void load_unaligned_words(const unsigned char* p, unsigned (&out)[N]) {
+    const unsigned a = (unsigned)((size_t)p & 3);
+    const unsigned* q = reinterpret_cast<const unsigned*>(p - a);
+    unsigned w[N + 1];
+    SCB_UNROLL
+    for (int k = 0; k < N; ++k) w[k] = __ldg(q + k);
+    w[N] = a ? __ldg(q + N) : 0u;  // an unaligned span of 4N bytes touches N+1 words; never reads a word without a needed byte
+    SCB_UNROLL
+    for (int k = 0; k < N; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], 8 * a);
+}
+template <int N>
+SCB_D int byte_of(const unsigned (&w)[N], int i) { return (int)((w[i >> 2] >> (8 * (i & 3))) & 255u); }
+
+static constexpr int kRhsThreads = 128;
+
+__global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
+    const int y = p.y0 + blockIdx.y;
+    const int x0 = 4 * (blockIdx.x * kRhsThreads + threadIdx.x);
+    if (x0 >= p.nx) return;
+    const StencilSrc& s = p.st;
+    float* g0 = p.g + ((size_t)0 * p.ny + y) * p.gp + x0;
+    const size_t plane = (size_t)p.ny * p.gp;
+    if (x0 + 8 > p.nx) {  // row tail (and the pad columns up to gp): per-pixel path with byte loads
+        for (int k = 0; k < 4; ++k) {
+            float g[3] = {0.f, 0.f, 0.f};
+            if (x0 + k < p.nx) rhs_pixel(s, x0 + k, y, g);
+            if (x0 + k < p.gp) {
+                g0[k] = g[0];
+                g0[plane + k] = g[1];
+                g0[2 * plane + k] = g[2];
+            }
+        }
+        return;
+    }
+    const int X = x0 + 1, Y = y + 1;
+    // row Y from column X-1 (20 bytes cover X-1 .. X+4), rows Y-1 / Y+1 from column X (12 bytes cover X .. X+3)
+    unsigned dm[5], du[3], dd[3], sm[5], su[3], sd[3], em[2], eu[1];
+    load_unaligned_words<5>(s.D + (long long)Y * s.d_pitch + 3 * (X - 1), dm);
+    load_unaligned_words<3>(s.D + (long long)(Y - 1) * s.d_pitch + 3 * X, du);
+    load_unaligned_words<3>(s.D + (long long)(Y + 1) * s.d_pitch + 3 * X, dd);
+    load_unaligned_words<5>(s.S + (long long)Y * s.s_pitch + 3 * (X - 1), sm);
+    load_unaligned_words<3>(s.S + (long long)(Y - 1) * s.s_pitch + 3 * X, su);
+    load_unaligned_words<3>(s.S + (long long)(Y + 1) * s.s_pitch + 3 * X, sd);
+    load_unaligned_words<2>(s.E + (long long)Y * s.e_pitch + (X - 1), em);
+    load_unaligned_words<1>(s.E + (long long)(Y - 1) * s.e_pitch + X, eu);
+    float out[3][4];
+    SCB_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const int el = byte_of(em, k), ec = byte_of(em, k + 1), eup = byte_of(eu, k);
+        const bool binary = ((el == 0) | (el == 255)) & ((ec == 0) | (ec == 255)) & ((eup == 0) | (eup == 255));
+        const int Xk = X + k;
+        if (binary) {
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const int Dl = byte_of(dm, 3 * k + c), Dc = byte_of(dm, 3 * k + 3 + c), Dr = byte_of(dm, 3 * k + 6 + c);
+                const int Du = byte_of(du, 3 * k + c), Dd = byte_of(dd, 3 * k + c);
+                const int Sl = byte_of(sm, 3 * k + c), Sc = byte_of(sm, 3 * k + 3 + c), Sr = byte_of(sm, 3 * k + 6 + c);
+                const int Su = byte_of(su, 3 * k + c), Sd = byte_of(sd, 3 * k + c);
+                int lap = (ec ? (Sr - Sc) + (Sd - Sc) : (Dr - Dc) + (Dd - Dc)) - (el ? (Sc - Sl) : (Dc - Dl)) - (eup ? (Sc - Su) : (Dc - Du));
+                if (Xk == 1) lap -= Dl;
+                if (Xk == s.w - 2) lap -= Dr;
+                if (Y == 1) lap -= Du;
+                if (Y == s.h - 2) lap -= Dd;
+                out[c][k] = (float)lap;
+            }
+        } else {  // grey mask values: OpenCV's float arithmetic, operation by operation
+            const float inv255 = 1.0f / 255.0f;
+            const float mc = __fmul_rn((float)ec, inv255), mic = __fmul_rn((float)(255 - ec), inv255);
+            const float ml = __fmul_rn((float)el, inv255), mil = __fmul_rn((float)(255 - el), inv255);
+            const float mu = __fmul_rn((float)eup, inv255), miu = __fmul_rn((float)(255 - eup), inv255);
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const float Dl = (float)byte_of(dm, 3 * k + c), Dc = (float)byte_of(dm, 3 * k + 3 + c), Dr = (float)byte_of(dm, 3 * k + 6 + c);
+                const float Du = (float)byte_of(du, 3 * k + c), Dd = (float)byte_of(dd, 3 * k + c);
+                const float Sl = (float)byte_of(sm, 3 * k + c), Sc = (float)byte_of(sm, 3 * k + 3 + c), Sr = (float)byte_of(sm, 3 * k + 6 + c);
+                const float Su = (float)byte_of(su, 3 * k + c), Sd = (float)byte_of(sd, 3 * k + c);
+                const float vxc = __fadd_rn(__fmul_rn(Dr - Dc, mic), __fmul_rn(Sr - Sc, mc));
+                const float vxl = __fadd_rn(__fmul_rn(Dc - Dl, mil), __fmul_rn(Sc - Sl, ml));
+                const float vyc = __fadd_rn(__fmul_rn(Dd - Dc, mic), __fmul_rn(Sd - Sc, mc));
+                const float vyu = __fadd_rn(__fmul_rn(Dc - Du, miu), __fmul_rn(Sc - Su, mu));
+                const float lap = __fadd_rn(__fsub_rn(vxc, vxl), __fsub_rn(vyc, vyu));
+                float bnd = 0.f;
+                if (Xk == 1) bnd += Dl;
+                if (Xk == s.w - 2) bnd += Dr;
+                if (Y == 1) bnd += Du;
+                if (Y == s.h - 2) bnd += Dd;
+                out[c][k] = __fsub_rn(lap, bnd);
+            }
+        }
+    }
+    SCB_UNROLL
+    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(g0 + c * plane) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass A: stencil -> forward DST-I along x.   grid = ny CTAs, block = FftCfg::T
 // ---------------------------------------------------------------------------------------------
 struct RowsFwdParams {
@@ -93,7 +207,8 @@ struct RowsFwdParams {
     int nx, ny;
     float* At;            // [3][nx][ny]
     float* rhs_dump;      // [3][ny][nx] or null
-    const float* rhs_in;  // [3][ny][nx] or null: bypass the stencil (sharded / test entry)
+    const float* rhs_in;  // [3][ny][rhs_pitch] from rhs_kernel, or null: evaluate the stencil in place
+    int rhs_pitch;
     int y0;               // first interior row handled by this launch (row-sharded solves)
 };
 
@@ -109,7 +224,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_fwd_kernel(RowsFwdParam
             if (j >= 1 && j <= n) {
                 if (p.rhs_in) {
                     SCB_UNROLL
-                    for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.nx + (j - 1)];
+                    for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.rhs_pitch + (j - 1)];
                 } else {
                     rhs_pixel(p.st, j - 1, y, g);
                 }
@@ -290,6 +405,7 @@ struct LowRowsParams {
     int nx, ny, lowkx;
     double* R;           // [3][lowkx][ny]   R = sum_x g[y][x] sin(pi (x+1)(k+1) / Nx)
     const float* rhs_in;
+    int rhs_pitch;
     int y0;
 };
 
@@ -303,7 +419,7 @@ __global__ void __launch_bounds__(kLowThreads) lowfreq_rows_kernel(LowRowsParams
         float g[3];
         if (p.rhs_in) {
             SCB_UNROLL
-            for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.nx + x];
+            for (int c = 0; c < 3; ++c) g[c] = p.rhs_in[((size_t)c * p.ny + y) * p.rhs_pitch + x];
         } else {
             rhs_pixel(p.st, x, y, g);
         }

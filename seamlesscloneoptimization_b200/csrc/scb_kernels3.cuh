@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_fwd3_kernel(RowsFwd3Param
         const float2 ch = __ldg(p.tx.chirp + j);
         float a, b = 0.f;
         if (p.rhs_in) {
-            a = p.rhs_in[((size_t)c * p.ny + y0) * p.nx + (j - 1)];
-            if (has1) b = p.rhs_in[((size_t)c * p.ny + y1) * p.nx + (j - 1)];
+            a = __ldg(p.rhs_in + ((size_t)c * p.ny + y0) * p.rhs_pitch + (j - 1));
+            if (has1) b = __ldg(p.rhs_in + ((size_t)c * p.ny + y1) * p.rhs_pitch + (j - 1));
         } else {
             a = rhs_pixel_c(p.st, j - 1, y0, c);
             if (has1) b = rhs_pixel_c(p.st, j - 1, y1, c);

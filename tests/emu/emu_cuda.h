@@ -265,6 +265,7 @@ inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (shift & 31)); }
 inline int __float2int_rz(float f) { return (int)f; }
 inline unsigned __float2uint_rz(float f) { return (unsigned)f; }
 inline float __int2float_rn(int i) { return (float)i; }

@@ -335,7 +335,7 @@ def test_launch_counter(ctx):
     plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
     before = ctx.kernel_launches
     plan.execute(src, dst)
-    assert ctx.kernel_launches - before == 5  # lowfreq rows, lowfreq cols, rows fwd, cols, rows inv
+    assert ctx.kernel_launches - before == 6  # rhs, lowfreq rows, lowfreq cols, rows fwd, cols, rows inv
     plan.close()
 
 
