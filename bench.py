@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- solved Mpix/s of seamlessClone(NORMAL_CLONE) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg5|cfg4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|cfg5] [--impl reference]
 
-One "step" = one whole NORMAL_CLONE of the workload (default cfg2: 3840x2160 dst, 2048x1536 irregular
-mask patch, ROI 1810x1341 -> 2.42 M solved RGB pixels).  With N > 1 (torchrun, one rank per GPU)
-every rank clones its own independent job of that shape (jobs shard with no collective): weak scaling,
-value = N * solved pixels / max-over-ranks time.
+Default workload cfg2 (the configuration BASELINE.json's metric is quoted on): 3840x2160 dst, 2048x1536
+irregular-mask patch, ROI 1810x1341 -> 2.42 M solved RGB pixels per clone.  One "step" = one whole
+NORMAL_CLONE of the workload (cfg3: one pass over the whole batch of jobs).
 
-  value   device-resident: src/dst/mask/blend already in HBM, plan (mask prep + tables) made once,
-          timed with CUDA events on the library's stream, L2 flushed between steps
-  e2e     the drop-in call: scb_seamless_clone on pinned HOST buffers -- mask upload, bbox, erosion,
-          ROI H2D, solve, ROI D2H, dst->blend host copy all inside the timed region (wall clock)
-  roofline  the dominant kernel (columns pass), algorithmic bytes / its CUDA-event time vs measured HBM peak
+  N > 1 (torchrun, one rank per GPU)
+    cfg1/2/5  every rank clones its own independent job of that shape, no collective: "weak"
+    cfg3      the 512 jobs are split over the ranks (LPT by solved pixels), no collective: "strong"
+    cfg4      ONE solve, rows/columns sharded over the ranks, NCCL all-to-all between the passes: "strong"
+
+  value     device-resident: images already in HBM, plan (mask prep + tables) made once, CUDA events on the
+            library's stream, L2 flushed (256 MiB write) between timed steps
+  e2e       the drop-in call on pinned HOST buffers: mask upload, bbox, erosion, ROI H2D, solve, ROI D2H,
+            dst->blend host copy all inside the timed region (wall clock, sync on return)
+  roofline  dominant kernel: algorithmic bytes / its CUDA-event time vs the measured HBM peak;
+            roofline_stencil: the same for the fused RHS stencil (the HBM-bound kernel of the path)
   cpu_baseline  cv2.seamlessClone (OpenCV 4.13 wheel = the reference arithmetic) on this box's host cores
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -34,6 +40,8 @@ from seamlesscloneoptimization_b200 import workloads  # noqa: E402
 
 METRIC = "solved_mpix_per_s"
 UNIT = "Mpix/s"
+ALG_BYTES = {"rhs": 19, "rows_fwd": 24, "cols": 24, "rows_inv": 15}  # per solved RGB pixel
+KERNEL_NAMES = {"rhs": "rhs_kernel", "rows_fwd": "rows_fwd", "cols": "cols", "rows_inv": "rows_inv"}
 
 
 def measured_peak_gbs():
@@ -42,6 +50,15 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def ncu_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -77,72 +94,462 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
+    def stop(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def solved_pixels(g) -> int:
-    return int(g.nx) * int(g.ny)
+def percentile(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = min(len(xs) - 1, max(0, int(round(q * (len(xs) - 1)))))
+    return xs[k]
 
 
-def cpu_reference_run(src, dst, mask, p, n_calls: int, threads: int | None):
-    """cv2.seamlessClone = OpenCV's own CPU implementation of the path (the reference arithmetic)."""
+WORKLOADS = {
+    "cfg1": "cfg1: 512x384 full-mask patch into 1920x1080 at ROI origin (800,150)",
+    "cfg2": "cfg2: 3840x2160 dst, 2048x1536 irregular-mask patch (ellipse+disc, ROI 1810x1341), p=(1920,1080)",
+    "cfg3": "cfg3: batch of 512 independent 1080p clone jobs, patch sizes U[64,1024]xU[64,768], varied offsets, full/elliptic masks",
+    "cfg4": "cfg4: 7680x4320 dst, 4096x4096 full-mask patch (ROI 4094x4094), one solve",
+    "cfg5": "cfg5: 1920x1080 dst stream, fixed 1280x720 elliptic mask (ROI 1201x661) and offset, plan + CUDA graph reused",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference (OpenCV's own implementation of the path)
+# ------------------------------------------------------------------------------------------------
+def cpu_clone_times(jobs, n_calls: int, threads: int | None):
+    """cv2.seamlessClone over `jobs` (list of (src,dst,mask,p)), n_calls passes after one warm-up call."""
     import cv2
 
     if threads:
         cv2.setNumThreads(threads)
-    cv2.seamlessClone(src, dst, mask.copy(), p, cv2.NORMAL_CLONE)  # warm-up
+    s, d, m, p = jobs[0]
+    cv2.seamlessClone(s, d, m.copy(), p, cv2.NORMAL_CLONE)
     ts = []
     for _ in range(n_calls):
-        m = mask.copy()
         t0 = time.perf_counter()
-        cv2.seamlessClone(src, dst, m, p, cv2.NORMAL_CLONE)
+        for s, d, m, p in jobs:
+            cv2.seamlessClone(s, d, m.copy(), p, cv2.NORMAL_CLONE)  # cv2 mutates the mask: always a copy
         ts.append(time.perf_counter() - t0)
     return ts, cv2.getNumThreads(), cv2.__version__
 
 
-def roi_of(mask):
+def roi_pixels(mask):
     ys, xs = np.nonzero(mask[1:-1, 1:-1])
     w, h = int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)
-    return w, h
+    return (w - 2) * (h - 2), (w, h)
 
 
-def run_reference(args, rank, world):
+def cpu_sample_jobs(workload: str):
+    """Bounded sample of the workload for the CPU legs (about 10-30 s of cv2 work)."""
+    if workload == "cfg3":
+        specs = workloads.make_batch_jobs(512, seed=0)[:16]
+        jobs = [workloads.materialise_job(j) for j in specs]
+        return jobs, "first 16 of the 512 cfg3 jobs"
+    src, dst, mask, p = workloads.make_config(workload, seed=0)
+    return [(src, dst, mask, p)], f"whole {workload} clones"
+
+
+def run_reference(args, rank):
     """--impl reference: OpenCV's CPU seamlessClone on the box's host cores, same config/metric/unit."""
     if rank != 0:
         return
-    src, dst, mask, p = workloads.make_config(args.workload, seed=0)
-    w, h = roi_of(mask)
-    px = (w - 2) * (h - 2)
-    ncores = os.cpu_count() or 1
     try:
         import cv2  # noqa: F401
     except Exception as e:
         print(json.dumps({"impl": "reference", "unavailable": f"cv2 not importable: {e}"}))
         return
-    cpu_reference_run(src, dst, mask, p, max(0, args.warmup - 1), ncores)
-    ts, nthreads, ver = cpu_reference_run(src, dst, mask, p, args.steps, ncores)
-    total = sum(ts)
-    value = px * len(ts) / total / 1e6
+    jobs, what = cpu_sample_jobs(args.workload)
+    px = sum(roi_pixels(m)[0] for _, _, m, _ in jobs)
+    ncores = os.cpu_count() or 1
+    steps = args.steps if args.workload != "cfg4" else min(args.steps, 2)  # 12-18 s per 8K clone
+    if args.warmup > 1 and args.workload != "cfg4":
+        cpu_clone_times(jobs, args.warmup - 1, ncores)
+    ts, nthreads, ver = cpu_clone_times(jobs, steps, ncores)
+    value = px * len(ts) / sum(ts) / 1e6
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "solved_pixels_per_step": px, "roi": [w, h]},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts), "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "solved_pixels_per_step": px},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "reference",
-                         "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} whole {args.workload} clones, {nthreads} threads of {ncores} host cores"},
+                         "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} passes over {what}, {nthreads} threads of {ncores} host cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "p50_ms": 1e3 * statistics.median(ts),
     }
     print(json.dumps(line))
 
 
-def workload_name(w):
-    return {
-        "cfg1": "cfg1: 512x384 full-mask patch into 1920x1080 at ROI origin (800,150)",
-        "cfg2": "cfg2: 3840x2160 dst, 2048x1536 irregular-mask patch (ellipse+disc, ROI 1810x1341), p=(1920,1080)",
-        "cfg4": "cfg4: 7680x4320 dst, 4096x4096 full-mask patch (ROI 4094x4094)",
-        "cfg5": "cfg5: 1920x1080 dst, 1280x720 elliptic-mask patch (ROI 1201x661), fixed mask/offset",
-    }[w]
+def cpu_baseline_leg(args, px_per_pass_hint=None):
+    try:
+        jobs, what = cpu_sample_jobs(args.workload)
+        px = sum(roi_pixels(m)[0] for _, _, m, _ in jobs)
+        ncores = os.cpu_count() or 1
+        calls = 1 if args.workload == "cfg4" else args.cpu_baseline_calls
+        ts, nthreads, ver = cpu_clone_times(jobs, calls, ncores)
+        return {"value": px * len(ts) / sum(ts) / 1e6, "unit": UNIT, "cores": nthreads, "kind": "reference", "p50_ms": 1e3 * statistics.median(ts),
+                "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} passes over {what} after 1 warm-up, {nthreads} threads of {ncores} host cores"}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 legs
+# ------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: seamlesscloneoptimization_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.warmup = max(3, args.warmup)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    def sum_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def pinned(self, a):
+        t = self.torch.empty(a.shape, dtype=self.torch.uint8, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+
+    def timed_steps(self, stream, step, steps):
+        """K steps, each bracketed by its own CUDA event pair on `stream`, L2 flushed before each."""
+        torch = self.torch
+        evs = []
+        for _ in range(steps):
+            self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step()
+            e1.record(stream)
+            evs.append((e0, e1))
+        return evs
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def roofline_objects(stages, px, workload):
+    peak, peak_kind = measured_peak_gbs()
+    dom = max(("rows_fwd", "cols", "rows_inv"), key=lambda k: stages.get(k, 0.0))
+
+    def obj(k):
+        alg = ALG_BYTES[k] * px
+        ach = alg / (stages[k] * 1e-3) / 1e9 if stages.get(k) else None
+        return {"bound": "hbm", "kernel": KERNEL_NAMES[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "algorithmic_bytes_per_launch": alg, "duration_ms": stages.get(k),
+                "traffic": ncu_traffic(workload, k)}
+
+    return obj(dom), obj("rhs")
+
+
+def single_job_leg(env: Env, args):
+    """cfg1 / cfg2 / cfg5 (and cfg4 on one GPU): one clone per step; every rank its own independent job."""
+    import seamlesscloneoptimization_b200 as scb
+    from seamlesscloneoptimization_b200 import _capi as capi
+
+    torch = env.torch
+    src, dst, mask, p = workloads.make_config(args.workload, seed=env.rank)
+    stream = torch.cuda.Stream(device=env.dev)
+    ctx = scb.Context(env.local_rank, stream=stream.cuda_stream)
+    d_src, d_dst, d_mask = (torch.from_numpy(a).to(env.dev) for a in (src, dst, mask))
+    d_blend = torch.empty_like(d_dst)
+    plan = scb.Plan(ctx, d_mask, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    g = plan.geometry
+    px = int(g.nx) * int(g.ny)
+    use_graph = args.workload == "cfg5" or args.graph
+
+    def device_step():
+        if use_graph:
+            plan.execute_graph(d_src, d_dst, d_blend)
+        else:
+            plan.execute(d_src, d_dst, d_blend, scb.MEM_DEVICE)
+
+    with torch.cuda.stream(stream):
+        for _ in range(env.warmup):
+            device_step()
+        env.barrier()
+        sampler = ClockSampler(env.local_rank)
+        sampler.start()
+        launches0 = ctx.kernel_launches
+        evs = env.timed_steps(stream, device_step, args.steps)
+        env.barrier()
+        launches = ctx.kernel_launches - launches0
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        stage_acc = {}
+        for _ in range(min(10, max(3, args.steps))):
+            env.flush.fill_(1)
+            for k, v in plan.execute_timed(d_src, d_dst, d_blend, scb.MEM_DEVICE).items():
+                stage_acc.setdefault(k, []).append(v)
+        sampler.stop()
+    stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
+
+    # ---- end to end through the drop-in call, pinned host buffers ----
+    h_src, h_dst, h_mask = env.pinned(src), env.pinned(dst), env.pinned(mask)
+    h_blend = torch.empty(dst.shape, dtype=torch.uint8, pin_memory=True)
+    vs, vd, vm, vb = (capi.host_view(t.numpy()) for t in (h_src, h_dst, h_mask, h_blend))
+    stream_plan = scb.Plan(ctx, mask, src.shape[:2], dst.shape[:2], p, scb.MEM_HOST) if args.workload == "cfg5" else None
+
+    def e2e_step():
+        if stream_plan is not None:  # cfg5: fixed mask/offset -> the plan is reused, frames come from the host
+            rc = ctx.lib.scb_plan_execute(stream_plan.handle, C.byref(vs), C.byref(vd), C.byref(vb), scb.MEM_HOST, scb.EXEC_DEFAULT)
+        else:
+            rc = ctx.lib.scb_seamless_clone(ctx.handle, C.byref(vs), C.byref(vd), C.byref(vm), p[0], p[1], C.byref(vb), scb.NORMAL_CLONE, scb.MEM_HOST)
+        if rc:
+            ctx._check(rc)
+
+    for _ in range(env.warmup):
+        e2e_step()
+    env.barrier()
+    e2e_ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        e2e_step()  # returns when blend is complete on the host
+        e2e_ts.append(time.perf_counter() - t0)
+    env.barrier()
+    assert np.array_equal(h_blend.numpy(), d_blend.cpu().numpy()), "host and device paths disagree"
+
+    total_ms_max, e2e_ms_max = env.max_over_ranks(sum(step_ms), sum(e2e_ts) * 1e3)
+    line = None
+    if env.rank == 0:
+        roof, roof_st = roofline_objects(stages, px, args.workload)
+        e2e_call = ("scb_plan_execute(HOST pinned frames, plan reused): ROI H2D + solve + ROI D2H + dst->blend host copy" if stream_plan is not None else
+                    "scb_seamless_clone(HOST pinned buffers): mask prep + ROI H2D + solve + ROI D2H + dst->blend host copy")
+        line = {
+            "metric": METRIC, "value": env.world * px * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+            "warmup": env.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
+                       "l2": "256 MiB flush write between timed steps", "jobs_per_step_per_gpu": 1, "cuda_graph": bool(use_graph)},
+            "clocks": sampler.summary(),
+            "e2e": {"value": env.world * px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
+                    "h2d_bytes_per_step": int((0 if stream_plan is not None else mask.size) + 2 * 3 * g.w * g.h), "d2h_bytes_per_step": int(3 * g.nx * g.ny),
+                    "ms_per_step": e2e_ms_max / args.steps, "p50_ms": 1e3 * statistics.median(e2e_ts), "p99_ms": 1e3 * percentile(e2e_ts, 0.99), "call": e2e_call},
+            "gpu_launches": int(launches),
+            "p50_ms_device": statistics.median(step_ms), "p99_ms_device": percentile(step_ms, 0.99),
+            "stages_ms": stages, "roofline": roof, "roofline_stencil": roof_st,
+        }
+    if stream_plan is not None:
+        stream_plan.close()
+    plan.close()
+    ctx.close()
+    return line
+
+
+def batch_leg(env: Env, args):
+    """cfg3: the batch of independent jobs, split over the ranks by LPT on solved pixels, no collective."""
+    import seamlesscloneoptimization_b200 as scb
+    from seamlesscloneoptimization_b200 import _capi as capi
+    from seamlesscloneoptimization_b200 import batch
+
+    torch = env.torch
+    specs = workloads.make_batch_jobs(args.jobs, seed=0)
+    costs = [(j["src_hw"][0] - 4) * (j["src_hw"][1] - 4) for j in specs]
+    mine = batch.shard_jobs(costs, env.world)[env.rank]
+    rng = np.random.default_rng(1234 + env.rank)
+    # synthetic pools (512 distinct 1080p frames would take minutes to generate): 4 textured dst frames,
+    # one 1024x768 textured src canvas cropped per job
+    dst_pool = [workloads.smooth_rand(rng, 1080, 1920, 6.0) for _ in range(4)]
+    canvas = workloads.smooth_rand(rng, 768, 1024, 6.0)
+    host_jobs = []
+    for i in mine:
+        j = specs[i]
+        hs, ws = j["src_hw"]
+        src = np.ascontiguousarray(canvas[:hs, :ws])
+        mask = np.full((hs, ws), 255, np.uint8) if j["mask_kind"] == "full" else workloads.ellipse_mask(hs, ws, ws / 2.0, hs / 2.0, ws * 0.45, hs * 0.45, 0.0)
+        host_jobs.append((src, dst_pool[i % len(dst_pool)], mask, j["p"]))
+    px = sum(roi_pixels(m)[0] for _, _, m, _ in host_jobs)
+
+    stream = torch.cuda.Stream(device=env.dev)
+    ctx = scb.Context(env.local_rank, stream=stream.cuda_stream)
+    d_dst_pool = [torch.from_numpy(d).to(env.dev) for d in dst_pool]
+    keep, views = [], []
+    for k, (src, dst, mask, p) in enumerate(host_jobs):
+        ts, tm = torch.from_numpy(src).to(env.dev), torch.from_numpy(mask).to(env.dev)
+        td = d_dst_pool[mine[k] % len(dst_pool)]
+        tb = torch.empty_like(td)
+        keep.append((ts, tm, tb))
+        views.append((capi.tensor_view(ts), capi.tensor_view(td), capi.tensor_view(tm), capi.tensor_view(tb), p))
+    job_arr = batch.make_device_jobs(views)
+
+    def device_step():
+        batch.clone_batch_device(ctx, job_arr)  # mask prep + solve of every job; returns after the lanes drained
+
+    with torch.cuda.stream(stream):
+        for _ in range(env.warmup):
+            device_step()
+        env.barrier()
+        sampler = ClockSampler(env.local_rank)
+        sampler.start()
+        launches0 = ctx.kernel_launches
+        step_ms = []
+        for _ in range(args.steps):
+            env.flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            device_step()  # work runs on the context's lanes; the call returns after they drained
+            e1.record(stream)
+            torch.cuda.synchronize()
+            # the lanes are other streams than `stream`: take the wall clock of the synchronous call as well
+            step_ms.append(e0.elapsed_time(e1))
+        env.barrier()
+        launches = ctx.kernel_launches - launches0
+        sampler.stop()
+
+    # e2e: pinned host images through scb_clone_batch(HOST)
+    h_jobs = (capi.ScbJob * len(host_jobs))()
+    pins = []
+    pin_dst = [env.pinned(d) for d in dst_pool]
+    for k, (src, dst, mask, p) in enumerate(host_jobs):
+        a, m = env.pinned(src), env.pinned(mask)
+        d = pin_dst[mine[k] % len(dst_pool)]
+        b = torch.empty(dst.shape, dtype=torch.uint8, pin_memory=True)
+        pins.append((a, m, b))
+        h_jobs[k].src, h_jobs[k].dst, h_jobs[k].mask, h_jobs[k].blend = (capi.host_view(t.numpy()) for t in (a, d, m, b))
+        h_jobs[k].px, h_jobs[k].py = p
+
+    def e2e_step():
+        ctx._check(ctx.lib.scb_clone_batch(ctx.handle, h_jobs, len(host_jobs), scb.MEM_HOST))
+
+    for _ in range(env.warmup):
+        e2e_step()
+    env.barrier()
+    e2e_ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        e2e_step()
+        e2e_ts.append(time.perf_counter() - t0)
+    env.barrier()
+    for k in range(0, len(host_jobs), max(1, len(host_jobs) // 8)):
+        assert np.array_equal(pins[k][2].numpy(), keep[k][2].cpu().numpy()), "host and device batch paths disagree"
+
+    total_ms_max, e2e_ms_max = env.max_over_ranks(sum(step_ms), sum(e2e_ts) * 1e3)
+    px_all, jobs_all, h2d, d2h = env.sum_over_ranks(px, len(host_jobs), sum(m.size + 2 * 3 * m.size for _, _, m, _ in host_jobs), 3 * px)
+    line = None
+    if env.rank == 0:
+        line = {
+            "metric": METRIC, "value": px_all * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+            "warmup": env.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["cfg3"], "jobs": int(jobs_all), "solved_pixels_per_step": int(px_all), "l2": "256 MiB flush write between timed steps",
+                       "partition": "LPT by solved pixels, no collective", "images": "4 dst frames + 1 src canvas per rank, cropped per job"},
+            "jobs_per_s": jobs_all * args.steps / (total_ms_max * 1e-3),
+            "clocks": sampler.summary(),
+            "e2e": {"value": px_all * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_max / args.steps, "jobs_per_s": jobs_all * args.steps / (e2e_ms_max * 1e-3),
+                    "call": "scb_clone_batch(HOST pinned buffers): per job mask prep + ROI H2D + solve + ROI D2H + dst->blend host copy"},
+            "gpu_launches": int(launches),
+        }
+    ctx.close()
+    return line
+
+
+def sharded_leg(env: Env, args):
+    """cfg4 on N > 1 GPUs: ONE solve, row/column sharded, all-to-all between the passes."""
+    import seamlesscloneoptimization_b200 as scb
+    from seamlesscloneoptimization_b200 import _capi as capi
+    from seamlesscloneoptimization_b200 import sharded
+
+    torch = env.torch
+    src, dst, mask, p = workloads.make_config("cfg4", seed=0)  # every rank holds the same u8 inputs (no halo exchange)
+    stream = torch.cuda.Stream(device=env.dev)  # the library, torch's pack/unpack copies and NCCL all order on this stream
+    ctx = scb.Context(env.local_rank, stream=stream.cuda_stream)
+    d_src, d_dst, d_mask = (torch.from_numpy(a).to(env.dev) for a in (src, dst, mask))
+    d_blend = d_dst.clone()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        plan = scb.Plan(ctx, d_mask, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+        g = plan.geometry
+        px = int(g.nx) * int(g.ny)
+        solve = sharded.ShardedSolve(ctx, plan, env.dev)
+        vs, vd, vb = capi.tensor_view(d_src), capi.tensor_view(d_dst), capi.tensor_view(d_blend)
+
+        def device_step():
+            solve.run(vs, vd, vb)
+
+        for _ in range(env.warmup):
+            device_step()
+        env.barrier()
+        sampler = ClockSampler(env.local_rank)
+        sampler.start()
+        launches0 = ctx.kernel_launches
+        evs = env.timed_steps(stream, device_step, args.steps)
+        env.barrier()
+        launches = ctx.kernel_launches - launches0
+        sampler.stop()
+        step_ms = [a.elapsed_time(b) for a, b in evs]
+        total_ms_max, = env.max_over_ranks(sum(step_ms))
+        # e2e: pinned host inputs -> device -> sharded solve -> own row slab back to the host
+        h_src, h_dst = env.pinned(src), env.pinned(dst)
+        y0, y1 = solve.ys[env.rank], solve.ys[env.rank + 1]
+        h_rows = torch.empty((y1 - y0, g.nx, 3), dtype=torch.uint8, pin_memory=True)
+
+        def e2e_step():
+            d_src.copy_(h_src, non_blocking=True)
+            d_dst.copy_(h_dst, non_blocking=True)
+            d_blend.copy_(d_dst, non_blocking=True)
+            solve.run(vs, vd, vb)
+            h_rows.copy_(d_blend[g.ry + 1 + y0 : g.ry + 1 + y1, g.rx + 1 : g.rx + 1 + g.nx], non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        env.barrier()
+        e2e_ts = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            e2e_step()
+            e2e_ts.append(time.perf_counter() - t0)
+        env.barrier()
+        e2e_ms_max, = env.max_over_ranks(sum(e2e_ts) * 1e3)
+    line = None
+    if env.rank == 0:
+        a2a_bytes = 2 * 4 * 3 * px * (env.world - 1) // (env.world * env.world)  # sent per rank per solve, both exchanges
+        line = {
+            "metric": METRIC, "value": px * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+            "warmup": env.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS["cfg4"], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
+                       "l2": "256 MiB flush write between timed steps", "parallelism": f"rows/cols sharded x{env.world}, 2 all-to-all (NCCL grouped send/recv)",
+                       "a2a_bytes_sent_per_rank_per_step": int(a2a_bytes)},
+            "clocks": sampler.summary(),
+            "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(src.size + dst.size), "d2h_bytes_per_step": int(h_rows.numel()),
+                    "ms_per_step": e2e_ms_max / args.steps, "call": "pinned src+dst H2D per rank, ShardedSolve.run, own row slab D2H"},
+            "gpu_launches": int(launches), "p50_ms_device": statistics.median(step_ms),
+        }
+    plan.close()
+    ctx.close()
+    return line
 
 
 def main():
@@ -151,153 +558,28 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--jobs", type=int, default=512, help="cfg3: jobs in the batch")
+    ap.add_argument("--graph", action="store_true", help="replay the device-resident step as a CUDA graph (default for cfg5)")
     ap.add_argument("--cpu-baseline-calls", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
-
-    import torch
-    import torch.distributed as dist
-
-    import seamlesscloneoptimization_b200 as scb
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: seamlesscloneoptimization_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # every rank clones its own independent job of the same shape (different seed per rank)
-    src, dst, mask, p = workloads.make_config(args.workload, seed=rank)
-    stream = torch.cuda.Stream(device=dev)
-    ctx = scb.Context(local_rank, stream=stream.cuda_stream)
-    d_src, d_dst, d_mask = (torch.from_numpy(a).to(dev) for a in (src, dst, mask))
-    d_blend = torch.empty_like(d_dst)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    plan = scb.Plan(ctx, d_mask, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
-    g = plan.geometry
-    px = solved_pixels(g)
-
-    def device_step():
-        plan.execute(d_src, d_dst, d_blend, scb.MEM_DEVICE)
-
-    with torch.cuda.stream(stream):
-        for _ in range(max(3, args.warmup)):
-            device_step()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = ctx.kernel_launches
-        evs = []
-        for _ in range(args.steps):
-            flush.fill_(1)  # evict L2 between timed steps (outside the event pair)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            device_step()
-            e1.record(stream)
-            evs.append((e0, e1))
-        barrier()
-        launches = ctx.kernel_launches - launches0
-        step_ms = [a.elapsed_time(b) for a, b in evs]
-        total_ms = sum(step_ms)
-
-        # per-stage CUDA-event times of the same call (dominant kernel for the roofline)
-        stage_acc = {}
-        n_prof = min(10, max(3, args.steps))
-        for _ in range(n_prof):
-            flush.fill_(1)
-            st = plan.execute_timed(d_src, d_dst, d_blend, scb.MEM_DEVICE)
-            for k, v in st.items():
-                stage_acc.setdefault(k, []).append(v)
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
-    stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
-
-    # ---- end to end through the drop-in call, host buffers ----
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
-        t.numpy()[...] = a
-        return t
-
-    h_src, h_dst, h_mask = pinned(src), pinned(dst), pinned(mask)
-    h_blend = torch.empty(dst.shape, dtype=torch.uint8, pin_memory=True)
-    from seamlesscloneoptimization_b200 import _capi as capi
-    import ctypes as C
-
-    vs, vd, vm, vb = (capi.host_view(t.numpy()) for t in (h_src, h_dst, h_mask, h_blend))
-
-    def e2e_step():
-        rc = ctx.lib.scb_seamless_clone(ctx.handle, C.byref(vs), C.byref(vd), C.byref(vm), p[0], p[1], C.byref(vb), scb.NORMAL_CLONE, scb.MEM_HOST)
-        if rc:
-            ctx._check(rc)
-
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    barrier()
-    e2e_ts = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        e2e_step()  # returns when blend is complete on the host
-        e2e_ts.append(time.perf_counter() - t0)
-    barrier()
-    e2e_total = sum(e2e_ts)
-    # sanity: host path and device path agree bit for bit
-    assert np.array_equal(h_blend.numpy(), d_blend.cpu().numpy()), "host and device paths disagree"
-
-    t_dev = torch.tensor([total_ms, e2e_total * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_ms_max = (float(x) for x in t_dev.cpu())
-
-    if rank == 0:
-        peak, peak_kind = measured_peak_gbs()
-        value = world * px * args.steps / (total_ms_max * 1e-3) / 1e6
-        e2e_value = world * px * args.steps / (e2e_ms_max * 1e-3) / 1e6
-        dom = max(("rows_fwd", "cols", "rows_inv"), key=lambda k: stages.get(k, 0.0))
-        alg_bytes = {"rows_fwd": 19, "cols": 24, "rows_inv": 15}[dom] * px
-        achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
-                       "l2": "256 MiB flush write between timed steps", "jobs_per_step_per_gpu": 1},
-            "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(mask.size + 2 * 3 * g.w * g.h), "d2h_bytes_per_step": int(3 * g.nx * g.ny),
-                    "ms_per_step": e2e_ms_max / args.steps, "p50_ms": 1e3 * statistics.median(e2e_ts), "call": "scb_seamless_clone(HOST pinned buffers): mask prep + ROI H2D + solve + ROI D2H + dst->blend host copy"},
-            "gpu_launches": int(launches),
-            "p50_ms_device": statistics.median(step_ms),
-            "stages_ms": stages,
-            "roofline": {"bound": "hbm", "kernel": {"rows_fwd": "rows_fwd_kernel", "cols": "cols_kernel", "rows_inv": "rows_inv_kernel"}[dom],
-                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_per_launch": alg_bytes, "traffic": None},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                ncores = os.cpu_count() or 1
-                ts, nthreads, ver = cpu_reference_run(src, dst, mask, p, args.cpu_baseline_calls, ncores)
-                line["cpu_baseline"] = {"value": px * len(ts) / sum(ts) / 1e6, "unit": UNIT, "cores": nthreads, "kind": "reference",
-                                        "p50_ms": 1e3 * statistics.median(ts),
-                                        "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} whole {args.workload} clones after 1 warm-up, {nthreads} threads of {ncores} host cores"}
-            except Exception as e:  # pragma: no cover
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    env = Env(args)
+    if args.workload == "cfg3":
+        line = batch_leg(env, args)
+    elif args.workload == "cfg4" and env.world > 1:
+        line = sharded_leg(env, args)
+    else:
+        line = single_job_leg(env, args)
+    if env.rank == 0 and line is not None:
+        if env.world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line))
-    plan.close()
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
 
 
 if __name__ == "__main__":

@@ -22,6 +22,11 @@
  *   my_seamlessclone_api_imp_*
  *       the four extern "C" names of seamlessclone_cuda.h:4-63 (which return cv::Mat by value and
  *       so are not a C ABI); same names and argument meaning, POD image views instead of cv::Mat*
+ *   scb_plan_execute_graph
+ *       the same run() captured once and replayed as a single CUDA graph launch (no reference counterpart;
+ *       the reference re-launches ~47 kernels and syncs twice per call)
+ *   scb_clone_batch
+ *       a loop over seamlessClone_imp_run (seamlessClone_imp.cu:265-352), pipelined over streams
  *   scb_plan_get_intermediate
  *       the SCDEBUG YAML dumps compared by compare/vs.py:12-34 (g*.yml vs OpenCV's mod_diff*.yml)
  */
@@ -114,6 +119,10 @@ int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst,
  * stage_ms[7] = { input copies, RHS stencil, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
  * (The reference times its whole run() with one event pair: seamlessClone_imp.cu:281-349.) */
 int scb_plan_execute_timed(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms);
+/* DEVICE-resident execute replayed as one CUDA graph launch (captured on first use; re-captured when a
+ * pointer, stride or the workspace changes): the per-frame call of a fixed-mask stream (BASELINE cfg5).
+ * Replaces the reference's ~47 launches and 2 host syncs per frame (seamlessClone_imp.cpp:2105-2135). */
+int scb_plan_execute_graph(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int exec_flags);
 int scb_plan_set_debug(scb_plan* plan, int on);
 int scb_plan_get_intermediate(scb_plan* plan, int which, float* out_host, size_t capacity_floats, size_t* written);
 

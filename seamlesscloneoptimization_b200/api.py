@@ -142,6 +142,12 @@ class Plan:
         self.ctx._check(self.lib.scb_plan_execute(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags))
         return blend
 
+    def execute_graph(self, src, dst, blend, flags: int = EXEC_DEFAULT):
+        """Device-resident execute replayed as one CUDA graph launch (fixed-mask streams)."""
+        vs, vd, vb = (x if isinstance(x, capi.ScbImage) else capi.tensor_view(x) for x in (src, dst, blend))
+        self.ctx._check(self.lib.scb_plan_execute_graph(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), flags))
+        return blend
+
     STAGES = ("copy_in", "rhs", "lowfreq", "rows_fwd", "cols", "rows_inv", "copy_out")
 
     def execute_timed(self, src, dst, blend, mem_kind: int = MEM_HOST, flags: int = EXEC_DEFAULT) -> dict:

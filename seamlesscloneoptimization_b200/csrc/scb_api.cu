@@ -36,26 +36,57 @@ struct DevLenTab {
     void* block = nullptr;
 };
 
-struct scb_context {
-    int device = 0;
+// A lane is one in-order pipeline of the context: a stream, the side stream of the low-frequency
+// refinement, and a grow-only workspace arena.  Lane 0 is the context's main stream (the only one the
+// single-job entry points use); scb_clone_batch spreads independent jobs over all lanes so that one
+// job's transfers overlap another's kernels and small jobs share the 148 SMs.
+struct Lane {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;              // low-frequency refinement runs here, beside pass A
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    char* ws = nullptr;
+    size_t ws_cap = 0;
+    uint64_t ws_epoch = 0;                    // bumps when the arena moves (captured graphs hold its addresses)
+};
+static const int kMaxLanes = 4;
+
+struct scb_context {
+    int device = 0;
+    Lane lanes[kMaxLanes];
+    int n_lanes = 0;
+    cudaStream_t prep = nullptr;  // scb_clone_batch: mask uploads + bounding boxes of the next chunk
     std::string err;
     uint64_t launches = 0;
     std::map<int, DevLenTab> lentabs;   // keyed by n
     std::map<int, float*> filters;      // keyed by ROI extent
-    char* ws = nullptr;
-    size_t ws_cap = 0;
-    int* bbox_dev = nullptr;
-    int* bbox_pinned = nullptr;  // [0..3] init pattern, [4..7] result
+    int* bbox_dev = nullptr;     // [slots][4]
+    int* bbox_pinned = nullptr;  // [0..3] init pattern, then [slots][4] results
+    int bbox_slots = 0;
     int sm_count = 148;
     int max_smem = 232448;
 };
 
+struct GraphKey {
+    const void *src = nullptr, *dst = nullptr, *blend = nullptr;
+    int64_t s_stride = 0, d_stride = 0, b_stride = 0;
+    int flags = 0;
+    uint64_t ws_epoch = 0;
+    bool operator==(const GraphKey& o) const {
+        return src == o.src && dst == o.dst && blend == o.blend && s_stride == o.s_stride && d_stride == o.d_stride && b_stride == o.b_stride &&
+               flags == o.flags && ws_epoch == o.ws_epoch;
+    }
+};
+
 struct scb_plan {
     scb_context* ctx = nullptr;
+    Lane* lane = nullptr;
+#ifndef SCB_EMU
+    cudaGraphExec_t graph_exec = nullptr;
+#endif
+    GraphKey graph_key;
+    uint64_t graph_kernels = 0;
+    unsigned char* mask_stage = nullptr;  // batch: staged host mask between plan_begin and plan_finish
     scb_geometry g{};
     int src_rows = 0, src_cols = 0, dst_rows = 0, dst_cols = 0;
     unsigned char* E = nullptr;
@@ -84,15 +115,71 @@ static int fail(scb_context* c, int code, const std::string& msg) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int ensure_ws(scb_context* c, size_t bytes) {
-    if (bytes <= c->ws_cap) return SCB_OK;
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->ws) SCB_CUDA(c, cudaFree(c->ws));
-    c->ws = nullptr;
-    c->ws_cap = 0;
+static int ensure_ws(scb_context* c, Lane* l, size_t bytes) {
+    if (bytes <= l->ws_cap) return SCB_OK;
+    SCB_CUDA(c, cudaStreamSynchronize(l->stream));
+    if (l->ws) SCB_CUDA(c, cudaFree(l->ws));
+    l->ws = nullptr;
+    l->ws_cap = 0;
+    l->ws_epoch++;
     size_t want = align_up(bytes + bytes / 4, 1 << 20);
-    SCB_CUDA(c, cudaMalloc(&c->ws, want));
-    c->ws_cap = want;
+    SCB_CUDA(c, cudaMalloc(&l->ws, want));
+    l->ws_cap = want;
+    return SCB_OK;
+}
+
+static cudaError_t lane_create(Lane* l, cudaStream_t adopt) {
+    cudaError_t e;
+    if (adopt) {
+        l->stream = adopt;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        l->own_stream = true;
+    }
+    if ((e = cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+static void lane_destroy(Lane* l) {
+    if (l->stream) cudaStreamSynchronize(l->stream);
+    if (l->side) {
+        cudaStreamSynchronize(l->side);
+        cudaStreamDestroy(l->side);
+    }
+    if (l->ws) cudaFree(l->ws);
+    if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+    if (l->ev_join) cudaEventDestroy(l->ev_join);
+    if (l->own_stream && l->stream) cudaStreamDestroy(l->stream);
+    *l = Lane();
+}
+
+// lanes 1.. are created on first use (scb_clone_batch)
+static int ensure_lanes(scb_context* c, int n) {
+    if (n > kMaxLanes) n = kMaxLanes;
+    while (c->n_lanes < n) {
+        SCB_CUDA(c, lane_create(&c->lanes[c->n_lanes], nullptr));
+        c->n_lanes++;
+    }
+    return SCB_OK;
+}
+
+static int ensure_bbox_slots(scb_context* c, int slots) {
+    if (slots <= c->bbox_slots) return SCB_OK;
+    for (int i = 0; i < c->n_lanes; ++i) SCB_CUDA(c, cudaStreamSynchronize(c->lanes[i].stream));
+    if (c->bbox_dev) cudaFree(c->bbox_dev);
+    if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
+    c->bbox_dev = nullptr;
+    c->bbox_pinned = nullptr;
+    c->bbox_slots = 0;
+    SCB_CUDA(c, cudaMalloc(&c->bbox_dev, (size_t)slots * 4 * sizeof(int)));
+    SCB_CUDA(c, cudaMallocHost(&c->bbox_pinned, (size_t)(slots + 1) * 4 * sizeof(int)));
+    c->bbox_pinned[0] = INT_MAX;
+    c->bbox_pinned[1] = INT_MAX;
+    c->bbox_pinned[2] = -1;
+    c->bbox_pinned[3] = -1;
+    c->bbox_slots = slots;
     return SCB_OK;
 }
 
@@ -153,64 +240,64 @@ template <int LOG2M>
 static dim3 group_grid(int nlines) { return dim3((nlines + 1) / 2, GCfg<LOG2M>::NG == 1 ? 3 : 1); }
 
 template <int LOG2M>
-static void launch_rows_fwd_t(scb_context* c, int nlines, const RowsFwdParams& p) {
+static void launch_rows_fwd_t(cudaStream_t stream, int nlines, const RowsFwdParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             RowsFwd3Params pp{p, p.tx.gtw, p.y0 + nlines};
-            SCB_LAUNCH(rows_fwd3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
+            SCB_LAUNCH(rows_fwd3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
     auto k = rows_fwd_kernel<LOG2M, Nch<LOG2M>::value>;
-    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), stream, p);
 }
 template <int LOG2M>
-static void launch_cols_t(scb_context* c, int nlines, const ColsParams& p) {
+static void launch_cols_t(cudaStream_t stream, int nlines, const ColsParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             Cols3Params pp{p, p.ty.gtw, p.x0 + nlines};
-            SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
+            SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
     auto k = cols_kernel<LOG2M, Nch<LOG2M>::value>;
-    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), stream, p);
 }
 template <int LOG2M>
-static void launch_rows_inv_t(scb_context* c, int nlines, const RowsInvParams& p) {
+static void launch_rows_inv_t(cudaStream_t stream, int nlines, const RowsInvParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             RowsInv3Params pp{p, p.tx.gtw, p.y0 + nlines};
-            SCB_LAUNCH(rows_inv3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, c->stream, pp);
+            SCB_LAUNCH(rows_inv3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
     auto k = rows_inv_kernel<LOG2M, Nch<LOG2M>::value>;
-    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), c->stream, p);
+    SCB_LAUNCH(k, dim3(nlines), dim3(FftCfg<LOG2M>::T), smem_bytes<LOG2M>(), stream, p);
 }
 
-static void launch_rows_fwd(scb_context* c, int log2m, int nlines, const RowsFwdParams& p) {
+static void launch_rows_fwd(scb_context* c, cudaStream_t stream, int log2m, int nlines, const RowsFwdParams& p) {
     if (nlines <= 0) return;
     switch (log2m) {
-#define X(L) case L: launch_rows_fwd_t<L>(c, nlines, p); break;
+#define X(L) case L: launch_rows_fwd_t<L>(stream, nlines, p); break;
         SCB_FOR_LOG2M(X)
 #undef X
     }
     c->launches++;
 }
-static void launch_cols(scb_context* c, int log2m, int nlines, const ColsParams& p) {
+static void launch_cols(scb_context* c, cudaStream_t stream, int log2m, int nlines, const ColsParams& p) {
     if (nlines <= 0) return;
     switch (log2m) {
-#define X(L) case L: launch_cols_t<L>(c, nlines, p); break;
+#define X(L) case L: launch_cols_t<L>(stream, nlines, p); break;
         SCB_FOR_LOG2M(X)
 #undef X
     }
     c->launches++;
 }
-static void launch_rows_inv(scb_context* c, int log2m, int nlines, const RowsInvParams& p) {
+static void launch_rows_inv(scb_context* c, cudaStream_t stream, int log2m, int nlines, const RowsInvParams& p) {
     if (nlines <= 0) return;
     switch (log2m) {
-#define X(L) case L: launch_rows_inv_t<L>(c, nlines, p); break;
+#define X(L) case L: launch_rows_inv_t<L>(stream, nlines, p); break;
         SCB_FOR_LOG2M(X)
 #undef X
     }
@@ -242,8 +329,8 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
-    SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));  // `host` dies at scope exit
+    SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->lanes[0].stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));  // `host` dies at scope exit; a blocking sync also publishes the table to every lane
     char* b = (char*)d.block;
     d.dev.n = n;
     d.dev.log2m = h.log2m;
@@ -267,8 +354,8 @@ static int get_filter(scb_context* c, int extent, const float** out) {
     std::vector<float> f = build_filter(extent);
     float* d = nullptr;
     SCB_CUDA(c, cudaMalloc(&d, f.size() * sizeof(float)));
-    SCB_CUDA(c, cudaMemcpyAsync(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCB_CUDA(c, cudaMemcpyAsync(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c->lanes[0].stream));
+    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));
     c->filters[extent] = d;
     *out = d;
     return SCB_OK;
@@ -299,24 +386,17 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
     };
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-    if (external_stream) {
-        c->stream = (cudaStream_t)external_stream;
-    } else {
-        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-        c->own_stream = true;
-    }
-    if ((e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = lane_create(&c->lanes[0], (cudaStream_t)external_stream)) != cudaSuccess) return bail("stream/event creation", e);
+    c->n_lanes = 1;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if ((e = configure_all()) != cudaSuccess) return bail("cudaFuncSetAttribute (is this an sm_100a device?)", e);
-    if ((e = cudaMalloc(&c->bbox_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMallocHost(&c->bbox_pinned, 8 * sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
-    c->bbox_pinned[0] = INT_MAX;
-    c->bbox_pinned[1] = INT_MAX;
-    c->bbox_pinned[2] = -1;
-    c->bbox_pinned[3] = -1;
+    if (ensure_bbox_slots(c, 1) != SCB_OK) {
+        g_create_error = c->err;
+        for (int i = 0; i < c->n_lanes; ++i) lane_destroy(&c->lanes[i]);
+        delete c;
+        return SCB_ERR_CUDA;
+    }
     *out = c;
     return SCB_OK;
 }
@@ -324,19 +404,15 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
 extern "C" int scb_destroy(scb_context* c) {
     if (!c) return SCB_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < c->n_lanes; ++i) lane_destroy(&c->lanes[i]);
+    if (c->prep) {
+        cudaStreamSynchronize(c->prep);
+        cudaStreamDestroy(c->prep);
+    }
     for (auto& kv : c->lentabs) cudaFree(kv.second.block);
     for (auto& kv : c->filters) cudaFree(kv.second);
-    if (c->ws) cudaFree(c->ws);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
-    if (c->side) {
-        cudaStreamSynchronize(c->side);
-        cudaStreamDestroy(c->side);
-    }
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return SCB_OK;
 }
@@ -344,12 +420,12 @@ extern "C" int scb_destroy(scb_context* c) {
 extern "C" int scb_sync(scb_context* c) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
     SCB_CUDA(c, cudaSetDevice(c->device));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < c->n_lanes; ++i) SCB_CUDA(c, cudaStreamSynchronize(c->lanes[i].stream));
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }
 
-extern "C" void* scb_stream(scb_context* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" void* scb_stream(scb_context* c) { return c ? (void*)c->lanes[0].stream : nullptr; }
 extern "C" const char* scb_last_error(const scb_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" uint64_t scb_kernel_launches(const scb_context* c) { return c ? c->launches : 0; }
 extern "C" const char* scb_status_string(int s) {
@@ -382,82 +458,122 @@ static void plan_free_debug(scb_plan* p) {
     p->dbg_vx = p->dbg_vy = p->dbg_rhs = p->dbg_spec = p->dbg_u = nullptr;
 }
 
+static void plan_drop_graph(scb_plan* p) {
+#ifndef SCB_EMU
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+#endif
+    p->graph_key = GraphKey();
+}
+
 extern "C" int scb_plan_destroy(scb_plan* p) {
     if (!p) return SCB_OK;
     cudaSetDevice(p->ctx->device);
-    if (p->E) scbFreeAsync(p->E, p->ctx->stream);
+    if (p->E) scbFreeAsync(p->E, p->lane->stream);
+    if (p->mask_stage) scbFreeAsync(p->mask_stage, p->lane->stream);
+    plan_drop_graph(p);
     plan_free_debug(p);
     delete p;
     return SCB_OK;
 }
 
-extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
-                               int dst_rows, int dst_cols, int px, int py, scb_plan** out) {
-    if (!c) return SCB_ERR_INVALID_ARGUMENT;
-    if (!out) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: out is null");
+// Plan creation in two halves so that a batch can put every job's bounding-box reduction in flight
+// before the first host sync (the reference's initMask blocks on a D2H per call: imp.cpp:1012).
+//   plan_begin : validate, stage the mask (HOST), launch the bbox reduction into slot `slot`
+//   plan_finish: (after a sync of the lane) geometry, erosion, tables
+struct PlanInput {
+    MaskView mv;
+    int px, py;
+    int slot;
+    bool staged;
+};
+
+static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                      int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in) {
     *out = nullptr;
     if (!mask || !mask->data) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask is null (pass an all-255 mask for 'no mask')");
     if (mask->channels != 1) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask must be single channel 8-bit (convert colour masks to grey first)");
     if (mask->rows != src_rows || mask->cols != src_cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask and src sizes differ");
     if (src_rows < 3 || src_cols < 3 || dst_rows < 3 || dst_cols < 3) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: images must be at least 3x3");
     if (mask->stride < mask->cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask stride smaller than a row");
-    SCB_CUDA(c, cudaSetDevice(c->device));
-
-    MaskView mv;
-    mv.rows = mask->rows;
-    mv.cols = mask->cols;
-    if (mask_mem_kind == SCB_MEM_HOST) {
-        const size_t pitch = align_up((size_t)mask->cols, 16);
-        int rc = ensure_ws(c, pitch * mask->rows);
-        if (rc) return rc;
-        SCB_CUDA(c, cudaMemcpy2DAsync(c->ws, pitch, mask->data, (size_t)mask->stride, (size_t)mask->cols, (size_t)mask->rows, cudaMemcpyHostToDevice, c->stream));
-        mv.data = (const unsigned char*)c->ws;
-        mv.pitch = (long long)pitch;
-    } else if (mask_mem_kind == SCB_MEM_DEVICE) {
-        mv.data = (const unsigned char*)mask->data;
-        mv.pitch = mask->stride;
-    } else {
-        return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: bad mem kind");
-    }
-    // bbox of the ring-zeroed mask (OpenCV: copyMakeBorder + boundingRect)
-    SCB_CUDA(c, cudaMemcpyAsync(c->bbox_dev, c->bbox_pinned, 4 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    {
-        const long long total = (long long)mv.rows * mv.cols;
-        long long blocks = (total + 255) / 256;
-        if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
-        SCB_LAUNCH(mask_bbox_kernel, dim3((unsigned)blocks), dim3(256), 0, c->stream, mv, c->bbox_dev);
-        c->launches++;
-    }
-    SCB_CUDA(c, cudaMemcpyAsync(c->bbox_pinned + 4, c->bbox_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
-    SCB_CUDA(c, cudaGetLastError());
-    const int minx = c->bbox_pinned[4], miny = c->bbox_pinned[5], maxx = c->bbox_pinned[6], maxy = c->bbox_pinned[7];
-
+    if (mask_mem_kind != SCB_MEM_HOST && mask_mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: bad mem kind");
     scb_plan* p = new scb_plan();
     p->ctx = c;
+    p->lane = lane;
     p->src_rows = src_rows;
     p->src_cols = src_cols;
     p->dst_rows = dst_rows;
     p->dst_cols = dst_cols;
+    MaskView& mv = in->mv;
+    mv.rows = mask->rows;
+    mv.cols = mask->cols;
+    in->px = px;
+    in->py = py;
+    in->slot = slot;
+    in->staged = false;
+    auto bad = [&](int code, const std::string& msg) {
+        scb_plan_destroy(p);
+        return fail(c, code, msg);
+    };
+    if (mask_mem_kind == SCB_MEM_HOST) {
+        const size_t pitch = align_up((size_t)mask->cols, 16);
+        void* m = nullptr;
+        if (scbMallocAsync(&m, pitch * mask->rows, prep) != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
+        p->mask_stage = (unsigned char*)m;
+        cudaError_t e = cudaMemcpy2DAsync(m, pitch, mask->data, (size_t)mask->stride, (size_t)mask->cols, (size_t)mask->rows, cudaMemcpyHostToDevice, prep);
+        if (e != cudaSuccess) return bad(SCB_ERR_CUDA, std::string("mask upload: ") + cudaGetErrorString(e));
+        mv.data = p->mask_stage;
+        mv.pitch = (long long)pitch;
+        in->staged = true;
+    } else {
+        mv.data = (const unsigned char*)mask->data;
+        mv.pitch = mask->stride;
+    }
+    // bbox of the ring-zeroed mask (OpenCV: copyMakeBorder + boundingRect)
+    int* slot_dev = c->bbox_dev + 4 * slot;
+    cudaMemcpyAsync(slot_dev, c->bbox_pinned, 4 * sizeof(int), cudaMemcpyHostToDevice, prep);
+    {
+        const long long total = (long long)mv.rows * mv.cols;
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
+        SCB_LAUNCH(mask_bbox_kernel, dim3((unsigned)blocks), dim3(256), 0, prep, mv, slot_dev);
+        c->launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(c->bbox_pinned + 4 * (slot + 1), slot_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, prep);
+    if (e != cudaSuccess) return bad(SCB_ERR_CUDA, std::string("bbox download: ") + cudaGetErrorString(e));
+    *out = p;
+    return SCB_OK;
+}
+
+// Call after the prep stream has been synchronised past plan_begin.  On failure the plan is destroyed.
+static int plan_finish(scb_plan* p, const PlanInput& in) {
+    scb_context* c = p->ctx;
+    Lane* lane = p->lane;
+    const int* r = c->bbox_pinned + 4 * (in.slot + 1);
+    const int minx = r[0], miny = r[1], maxx = r[2], maxy = r[3];
+    auto release_stage = [&]() {
+        if (p->mask_stage) scbFreeAsync(p->mask_stage, lane->stream);
+        p->mask_stage = nullptr;
+    };
     scb_geometry& g = p->g;
     if (maxx < 0) {  // nothing inside the ring: OpenCV returns dst unchanged
         g.empty = 1;
-        *out = p;
+        release_stage();
         return SCB_OK;
     }
     g.x = minx;
     g.y = miny;
     g.w = maxx - minx + 1;
     g.h = maxy - miny + 1;
-    g.rx = px - g.w / 2;  // truncating division on the BBOX size, like cv::seamlessClone
-    g.ry = py - g.h / 2;
+    g.rx = in.px - g.w / 2;  // truncating division on the BBOX size, like cv::seamlessClone
+    g.ry = in.py - g.h / 2;
     g.nx = g.w - 2;
     g.ny = g.h - 2;
     auto bad = [&](int code, const char* msg) {
-        delete p;
+        scb_plan_destroy(p);
         return fail(c, code, msg);
     };
-    if (g.rx < 0 || g.ry < 0 || g.rx + g.w > dst_cols || g.ry + g.h > dst_rows)
+    if (g.rx < 0 || g.ry < 0 || g.rx + g.w > p->dst_cols || g.ry + g.h > p->dst_rows)
         return bad(SCB_ERR_ROI_OUT_OF_BOUNDS, "seamlessClone: ROI (mask bounding box centred at p) does not fit inside dst");
     if (g.w < 3 || g.h < 3) return bad(SCB_ERR_UNSUPPORTED, "seamlessClone: mask bounding box must be at least 3x3 (OpenCV itself crashes on such masks)");
     g.log2m_x = choose_log2m(g.nx);
@@ -468,12 +584,13 @@ extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_m
     p->e_pitch = (long long)align_up((size_t)g.w, 16);
     {
         void* e = nullptr;
-        cudaError_t ce = scbMallocAsync(&e, (size_t)p->e_pitch * g.h, c->stream);
+        cudaError_t ce = scbMallocAsync(&e, (size_t)p->e_pitch * g.h, lane->stream);
         if (ce != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
         p->E = (unsigned char*)e;
     }
-    SCB_LAUNCH(mask_erode_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, c->stream, mv, g.x, g.y, g.w, g.h, p->E, p->e_pitch);
+    SCB_LAUNCH(mask_erode_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, lane->stream, in.mv, g.x, g.y, g.w, g.h, p->E, p->e_pitch);
     c->launches++;
+    release_stage();  // stream-ordered: freed after the erosion has read it
     int rc;
     if ((rc = get_lentab(c, g.nx, &p->tx)) || (rc = get_lentab(c, g.ny, &p->ty)) || (rc = get_filter(c, g.w, &p->fx)) || (rc = get_filter(c, g.h, &p->fy))) {
         scb_plan_destroy(p);
@@ -481,7 +598,27 @@ extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_m
     }
     p->lowkx = p->tx.lowk;
     p->lowky = p->ty.lowk;
-    if (mask_mem_kind == SCB_MEM_HOST) SCB_CUDA(c, cudaStreamSynchronize(c->stream));  // the staged mask lives in the shared workspace
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                               int dst_rows, int dst_cols, int px, int py, scb_plan** out) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (!out) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: out is null");
+    *out = nullptr;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    Lane* lane = &c->lanes[0];
+    scb_plan* p = nullptr;
+    PlanInput in;
+    int rc = plan_begin(c, lane, lane->stream, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, 0, &p, &in);
+    if (rc) return rc;
+    cudaError_t e = cudaStreamSynchronize(lane->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        scb_plan_destroy(p);
+        return fail(c, SCB_ERR_CUDA, std::string("scb_plan_create: ") + cudaGetErrorString(e));
+    }
+    if ((rc = plan_finish(p, in))) return rc;
     *out = p;
     return SCB_OK;
 }
@@ -502,7 +639,7 @@ extern "C" int scb_plan_set_debug(scb_plan* p, int on) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     SCB_CUDA(c, cudaSetDevice(c->device));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
     plan_free_debug(p);
     p->debug = false;
     if (on && !p->g.empty) {
@@ -535,8 +672,8 @@ extern "C" int scb_plan_get_intermediate(scb_plan* p, int which, float* out_host
             n = (size_t)p->g.w * p->g.h;
             if (capacity < n) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: buffer too small");
             std::vector<unsigned char> tmp((size_t)p->e_pitch * p->g.h);
-            SCB_CUDA(c, cudaMemcpyAsync(tmp.data(), p->E, tmp.size(), cudaMemcpyDeviceToHost, c->stream));
-            SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+            SCB_CUDA(c, cudaMemcpyAsync(tmp.data(), p->E, tmp.size(), cudaMemcpyDeviceToHost, p->lane->stream));
+            SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
             for (int y = 0; y < p->g.h; ++y)
                 for (int x = 0; x < p->g.w; ++x) out_host[(size_t)y * p->g.w + x] = (float)tmp[(size_t)y * p->e_pitch + x];
             if (written) *written = n;
@@ -546,8 +683,8 @@ extern "C" int scb_plan_get_intermediate(scb_plan* p, int which, float* out_host
     }
     if (!p->debug || !src) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: call scb_plan_set_debug(plan, 1) and execute first");
     if (capacity < n) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_get_intermediate: buffer too small");
-    SCB_CUDA(c, cudaMemcpyAsync(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->stream));
+    SCB_CUDA(c, cudaMemcpyAsync(out_host, src, n * sizeof(float), cudaMemcpyDeviceToHost, p->lane->stream));
+    SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
     if (written) *written = n;
     return SCB_OK;
 }
@@ -594,17 +731,17 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
         oS = take((size_t)w->pS * g.h);
         oO = take((size_t)w->pO * g.ny);
     }
-    int rc = ensure_ws(c, off);
+    int rc = ensure_ws(c, p->lane, off);
     if (rc) return rc;
-    w->At = (float*)(c->ws + oAt);
-    w->Ct = (float*)(c->ws + oCt);
-    w->G = (float*)(c->ws + oG);
-    w->R = (double*)(c->ws + oR);
-    w->lowspec = (float*)(c->ws + oLow);
+    w->At = (float*)(p->lane->ws + oAt);
+    w->Ct = (float*)(p->lane->ws + oCt);
+    w->G = (float*)(p->lane->ws + oG);
+    w->R = (double*)(p->lane->ws + oR);
+    w->lowspec = (float*)(p->lane->ws + oLow);
     if (host) {
-        w->stD = (unsigned char*)(c->ws + oD);
-        w->stS = (unsigned char*)(c->ws + oS);
-        w->stO = (unsigned char*)(c->ws + oO);
+        w->stD = (unsigned char*)(p->lane->ws + oD);
+        w->stS = (unsigned char*)(p->lane->ws + oS);
+        w->stO = (unsigned char*)(p->lane->ws + oO);
     }
     return SCB_OK;
 }
@@ -633,12 +770,12 @@ static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0,
     rp.gp = gp;
     rp.y0 = y0;
     const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
-    SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, c->stream, rp);
+    SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
     c->launches++;
     if (p->debug)  // dense [3][ny][nx] copy for scb_plan_get_intermediate
         for (int ch = 0; ch < 3; ++ch)
             cudaMemcpy2DAsync(p->dbg_rhs + ((size_t)ch * p->g.ny + y0) * p->g.nx, (size_t)p->g.nx * sizeof(float), G + ((size_t)ch * p->g.ny + y0) * gp,
-                              (size_t)gp * sizeof(float), (size_t)p->g.nx * sizeof(float), (size_t)(y1 - y0), cudaMemcpyDeviceToDevice, c->stream);
+                              (size_t)gp * sizeof(float), (size_t)p->g.nx * sizeof(float), (size_t)(y1 - y0), cudaMemcpyDeviceToDevice, p->lane->stream);
 }
 
 static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, const float* G, int gp, double* R, int y0, int y1, cudaStream_t stream) {
@@ -680,7 +817,7 @@ static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int 
     a.rhs_in = G;
     a.rhs_pitch = gp;
     a.y0 = y0;
-    launch_rows_fwd(p->ctx, p->g.log2m_x, y1 - y0, a);
+    launch_rows_fwd(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, a);
 }
 static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
     ColsParams b;
@@ -697,7 +834,7 @@ static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowsp
     b.spec_dump = p->debug ? p->dbg_spec : nullptr;
     b.inv_scale = (float)(1.0 / (double)(p->g.ny + 1));
     b.x0 = x0;
-    launch_cols(p->ctx, p->g.log2m_y, x1 - x0, b);
+    launch_cols(p->ctx, p->lane->stream, p->g.log2m_y, x1 - x0, b);
 }
 static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1) {
     RowsInvParams r;
@@ -710,7 +847,7 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
     r.u_dump = p->debug ? p->dbg_u : nullptr;
     r.inv_scale = (float)(1.0 / (double)(p->g.nx + 1));
     r.y0 = y0;
-    launch_rows_inv(p->ctx, p->g.log2m_x, y1 - y0, r);
+    launch_rows_inv(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, r);
 }
 
 // stage boundaries recorded by scb_plan_execute_timed
@@ -725,7 +862,7 @@ struct StageTimer {
     }
 };
 
-static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm) {
+static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm, bool defer_host_sync = false) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     int rc;
@@ -744,7 +881,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
             if (host) {
                 for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
             } else {
-                SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, c->stream));
+                SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, p->lane->stream));
             }
         }
         return SCB_OK;
@@ -761,37 +898,37 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     tm.mark(ST_BEGIN);
     if (host) {
         // ROI-only transfers (the reference uploads the whole dst every call: seamlessClone_imp.cpp:419-421)
-        SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, c->stream));
-        SCB_CUDA(c, cudaMemcpy2DAsync(w.stS, (size_t)w.pS, sROI, (size_t)src->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, c->stream));
+        SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, p->lane->stream));
+        SCB_CUDA(c, cudaMemcpy2DAsync(w.stS, (size_t)w.pS, sROI, (size_t)src->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, p->lane->stream));
         st = make_stencil(p, w.stD, w.pD, w.stS, w.pS);
         out = w.stO;
         out_pitch = w.pO;
     } else {
-        if (copy_dst) SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, c->stream));
+        if (copy_dst) SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, p->lane->stream));
         st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
         out = bInt;
         out_pitch = blend->stride;
     }
     if (p->debug) {
-        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, c->stream, st, p->dbg_vx, p->dbg_vy);
+        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, p->lane->stream, st, p->dbg_vx, p->dbg_vy);
         c->launches++;
     }
     tm.mark(ST_IN);
     run_rhs(p, st, w.G, w.gp, 0, g.ny);
     tm.mark(ST_RHS);
     if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, c->stream);
-        run_lowfreq_cols(p, w.R, w.lowspec, c->stream);
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, p->lane->stream);
+        run_lowfreq_cols(p, w.R, w.lowspec, p->lane->stream);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
-        SCB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-        SCB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, c->side);
-        run_lowfreq_cols(p, w.R, w.lowspec, c->side);
-        SCB_CUDA(c, cudaEventRecord(c->ev_join, c->side));
+        SCB_CUDA(c, cudaEventRecord(p->lane->ev_fork, p->lane->stream));
+        SCB_CUDA(c, cudaStreamWaitEvent(p->lane->side, p->lane->ev_fork, 0));
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, p->lane->side);
+        run_lowfreq_cols(p, w.R, w.lowspec, p->lane->side);
+        SCB_CUDA(c, cudaEventRecord(p->lane->ev_join, p->lane->side));
     }
     tm.mark(ST_LOW);
     run_rows_fwd(p, st, w.G, w.gp, w.At, 0, g.ny);
-    if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(p->lane->stream, p->lane->ev_join, 0));
     tm.mark(ST_ROWS_FWD);
     run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
     tm.mark(ST_COLS);
@@ -802,10 +939,12 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         // blend = dst.copy() on the host while the GPU works, then only the ROI interior comes back
         if (copy_dst)
             for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
-        SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, c->stream));
+        SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, p->lane->stream));
         tm.mark(ST_OUT);
-        SCB_CUDA(c, cudaStreamSynchronize(c->stream));
-        SCB_CUDA(c, cudaGetLastError());
+        if (!defer_host_sync) {
+            SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
+            SCB_CUDA(c, cudaGetLastError());
+        }
     } else {
         tm.mark(ST_OUT);
     }
@@ -825,12 +964,12 @@ extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const s
     SCB_CUDA(c, cudaSetDevice(c->device));
     StageTimer tm;
     tm.on = true;
-    tm.stream = c->stream;
+    tm.stream = p->lane->stream;
     for (int i = 0; i < ST_COUNT; ++i) SCB_CUDA(c, cudaEventCreate(&tm.ev[i]));
     for (int i = 0; i < ST_COUNT - 1; ++i) stage_ms[i] = 0.f;
     int rc = execute_impl(p, src, dst, blend, mem_kind, exec_flags, tm);
     if (rc == SCB_OK && !p->g.empty) {
-        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(p->lane->stream);
         for (int i = 0; i < ST_COUNT - 1; ++i) cudaEventElapsedTime(&stage_ms[i], tm.ev[i], tm.ev[i + 1]);
     }
     for (int i = 0; i < ST_COUNT; ++i) cudaEventDestroy(tm.ev[i]);
@@ -850,18 +989,116 @@ extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const sc
     return rc;
 }
 
+// Replays the plan's device-resident launches (D2D copy of dst, stencil, refinement on the side stream,
+// three transform passes) as ONE CUDA graph launch -- the per-frame call of a fixed-mask video stream
+// (BASELINE cfg5).  The graph is captured on first use and re-captured when a pointer, stride or the
+// workspace arena changes.  The reference has no counterpart (47 launches + 2 host syncs per frame).
+extern "C" int scb_plan_execute_graph(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int exec_flags) {
+    if (!p) return SCB_ERR_INVALID_ARGUMENT;
+    StageTimer tm;
+#ifdef SCB_EMU
+    return execute_impl(p, src, dst, blend, SCB_MEM_DEVICE, exec_flags, tm);
+#else
+    scb_context* c = p->ctx;
+    int rc;
+    if ((rc = check_image(c, src, p->src_rows, p->src_cols, "src"))) return rc;
+    if ((rc = check_image(c, dst, p->dst_rows, p->dst_cols, "dst"))) return rc;
+    if ((rc = check_image(c, blend, p->dst_rows, p->dst_cols, "blend"))) return rc;
+    if (p->g.empty) return execute_impl(p, src, dst, blend, SCB_MEM_DEVICE, exec_flags, tm);
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    Workspace w;
+    if ((rc = carve(p, false, &w))) return rc;  // grows the arena (sync + cudaMalloc) outside the capture
+    GraphKey k;
+    k.src = src->data;
+    k.dst = dst->data;
+    k.blend = blend->data;
+    k.s_stride = src->stride;
+    k.d_stride = dst->stride;
+    k.b_stride = blend->stride;
+    k.flags = exec_flags;
+    k.ws_epoch = p->lane->ws_epoch;
+    if (!p->graph_exec || !(k == p->graph_key)) {
+        plan_drop_graph(p);
+        const uint64_t before = c->launches;
+        SCB_CUDA(c, cudaStreamBeginCapture(p->lane->stream, cudaStreamCaptureModeThreadLocal));
+        rc = execute_impl(p, src, dst, blend, SCB_MEM_DEVICE, exec_flags, tm);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(p->lane->stream, &graph);
+        p->graph_kernels = c->launches - before;
+        c->launches = before;  // captured, not run
+        if (rc != SCB_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc != SCB_OK ? rc : fail(c, SCB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            p->graph_exec = nullptr;
+            return fail(c, SCB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        p->graph_key = k;
+    }
+    SCB_CUDA(c, cudaGraphLaunch(p->graph_exec, p->lane->stream));
+    c->launches += p->graph_kernels;
+    return SCB_OK;
+#endif
+}
+
+// Independent jobs (BASELINE cfg3).  Jobs are taken in chunks: the mask uploads and bounding-box
+// reductions of a whole chunk go onto a dedicated prep stream while the lanes still run the previous
+// chunk, ONE host sync fetches every bounding box, then each job (erosion, ROI upload, solve, ROI
+// download) is queued on lane i mod L without further syncs.  HOST results are complete on return;
+// DEVICE results after the trailing sync (also done here).
 extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int mem_kind) {
     if (!c || (!jobs && n_jobs > 0)) return SCB_ERR_INVALID_ARGUMENT;
+    if (n_jobs <= 0) return SCB_OK;
+    if (mem_kind != SCB_MEM_HOST && mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_clone_batch: bad mem kind");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    static const int kChunk = 64;
+    int rc;
+    if ((rc = ensure_lanes(c, n_jobs < kMaxLanes ? n_jobs : kMaxLanes))) return rc;
+    if ((rc = ensure_bbox_slots(c, kChunk))) return rc;
+    const int L = c->n_lanes;
+    if (!c->prep) SCB_CUDA(c, cudaStreamCreateWithFlags(&c->prep, cudaStreamNonBlocking));
     int worst = SCB_OK;
-    for (int i = 0; i < n_jobs; ++i) {
-        scb_job& j = jobs[i];
-        j.status = scb_seamless_clone(c, &j.src, &j.dst, &j.mask, j.px, j.py, &j.blend, SCB_NORMAL_CLONE, mem_kind);
-        if (j.status != SCB_OK) worst = j.status;
+    std::string first_error;
+    auto note = [&](scb_job& j, int status) {
+        j.status = status;
+        if (status != SCB_OK && worst == SCB_OK) {
+            worst = status;
+            first_error = c->err;
+        }
+    };
+    std::vector<scb_plan*> plans(kChunk);
+    std::vector<PlanInput> inputs(kChunk);
+    for (int base = 0; base < n_jobs; base += kChunk) {
+        const int m = (n_jobs - base < kChunk) ? n_jobs - base : kChunk;
+        for (int i = 0; i < m; ++i) {
+            scb_job& j = jobs[base + i];
+            plans[i] = nullptr;
+            if (!j.src.data || !j.dst.data || !j.blend.data) {
+                note(j, fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_clone_batch: null image"));
+                continue;
+            }
+            note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, i, &plans[i], &inputs[i]));
+        }
+        SCB_CUDA(c, cudaStreamSynchronize(c->prep));
+        SCB_CUDA(c, cudaGetLastError());
+        for (int i = 0; i < m; ++i) {
+            if (!plans[i]) continue;
+            scb_job& j = jobs[base + i];
+            int st = plan_finish(plans[i], inputs[i]);  // destroys the plan on failure
+            if (st == SCB_OK) {
+                StageTimer tm;
+                st = execute_impl(plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host_sync=*/true);
+                scb_plan_destroy(plans[i]);  // stream-ordered frees: the queued kernels finish first
+            }
+            plans[i] = nullptr;
+            note(j, st);
+        }
     }
-    if (mem_kind == SCB_MEM_DEVICE) {
-        int rc = scb_sync(c);
-        if (rc) return rc;
-    }
+    if ((rc = scb_sync(c))) return rc;
+    if (worst != SCB_OK) c->err = first_error;
     return worst;
 }
 
@@ -890,7 +1127,7 @@ extern "C" int scb_plan_rows_forward(scb_plan* p, const scb_image* src, const sc
     Workspace w;
     if ((rc = carve(p, false, &w))) return rc;
     run_rhs(p, st, w.G, w.gp, y0, y1);
-    if (lowrows_dev) run_lowfreq_rows(p, st, w.G, w.gp, lowrows_dev, y0, y1, c->stream);
+    if (lowrows_dev) run_lowfreq_rows(p, st, w.G, w.gp, lowrows_dev, y0, y1, p->lane->stream);
     run_rows_fwd(p, st, w.G, w.gp, at_dev, y0, y1);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
@@ -901,7 +1138,7 @@ extern "C" int scb_plan_lowfreq_finish(scb_plan* p, const double* lowrows_dev, f
     scb_context* c = p->ctx;
     if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
     SCB_CUDA(c, cudaSetDevice(c->device));
-    run_lowfreq_cols(p, lowrows_dev, lowspec_dev, c->stream);
+    run_lowfreq_cols(p, lowrows_dev, lowspec_dev, p->lane->stream);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }

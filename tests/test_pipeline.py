@@ -393,3 +393,69 @@ def test_full_size_properties_cfg4(cuda_lib):
     ucl = u.clamp(0, 255).floor()
     assert (out - ucl).abs().max().item() <= 1.0
     assert ((out - ucl).abs() > 0).double().mean().item() < 1e-3
+
+
+def test_graph_replay_equals_plain_execute(be, ctx):
+    """cfg5 structure: fixed mask/offset, new frames; the CUDA-graph replay must equal the plain launches
+    bit for bit, also after the frame pointers change (re-capture).  (The emulator has no graphs: there
+    the entry point runs the plain launches, which still checks the call path.)"""
+    src, dst, mask, p = so.make_config("small", 31)
+    vm, hm = be.to_device(mask)
+    plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    for seed in (31, 32):
+        s2, d2, _, _ = so.make_config("small", seed)
+        vs, hs = be.to_device(s2)
+        vd, hd = be.to_device(d2)
+        vb0, hb0 = be.to_device(np.zeros_like(d2))
+        vb1, hb1 = be.to_device(np.zeros_like(d2))
+        plan.execute(vs, vd, vb0, scb.MEM_DEVICE)
+        before = ctx.kernel_launches
+        for _ in range(3):  # first call captures, the next two replay
+            plan.execute_graph(vs, vd, vb1)
+        ctx.sync()
+        assert ctx.kernel_launches - before == 3 * 6
+        assert np.array_equal(be.to_host(hb0), be.to_host(hb1))
+    plan.close()
+
+
+def test_batch_pipelined_over_lanes_with_a_bad_job(be, ctx):
+    """More jobs than lanes, one job whose ROI falls outside dst: its status is reported, the others complete."""
+    jobs = so.make_batch_jobs(9, seed=5, dst_hw=(120, 170), w_range=(10, 60), h_range=(10, 50))
+    arr = (capi.ScbJob * len(jobs))()
+    keep, refs = [], []
+    for k, j in enumerate(jobs):
+        src, dst, mask, p = so.materialise_job(j, dst_hw=(120, 170), sigma=2.0)
+        if k == 4:
+            p = (2, 2)  # ROI outside dst
+        blend = np.zeros_like(dst)
+        keep.append((src, dst, mask, blend))
+        refs.append(None if k == 4 else so.restate(src, dst, mask, p, transform="f64"))
+        arr[k].src, arr[k].dst, arr[k].mask, arr[k].blend = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(blend)
+        arr[k].px, arr[k].py = p
+    rc = ctx.lib.scb_clone_batch(ctx.handle, arr, len(jobs), scb.MEM_HOST)
+    assert rc == capi.SCB_ERR_ROI_OUT_OF_BOUNDS
+    for k in range(len(jobs)):
+        if k == 4:
+            assert arr[k].status == capi.SCB_ERR_ROI_OUT_OF_BOUNDS
+            continue
+        assert arr[k].status == 0
+        g = refs[k].geom
+        cmp = so.compare_u8(keep[k][3], refs[k].blend)
+        assert cmp["max_abs"] <= 1 and cmp["n_diff"] <= common.allowed_mismatches(3 * g.nx * g.ny), (k, cmp)
+    # the context stays usable after a failed batch
+    src, dst, mask, p = so.make_config("small", 2)
+    assert ctx.seamless_clone(src, dst, mask, p).shape == dst.shape
+
+
+def test_reference_module_name_shim(be):
+    """`from SeamlessClone import SeamlessClone` (SeamlessClone_test.py:2) resolves through compat/."""
+    import importlib
+    import sys
+
+    compat = os.path.join(os.path.dirname(scb.__file__), "compat")
+    sys.path.insert(0, compat)
+    try:
+        mod = importlib.import_module("SeamlessClone")
+        assert mod.SeamlessClone is scb.SeamlessClone
+    finally:
+        sys.path.remove(compat)
