@@ -7,11 +7,14 @@
 // with the differences SURVEY.md 8b asks for: POD-only ABI, status codes instead of assert/exit,
 // cudaSetDevice on every entry, ROI-only transfers, no host sync inside the hot path other than the
 // one that reports a HOST-resident result, dst never modified, mask never modified.
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/scb.h"
@@ -49,7 +52,8 @@ struct Lane {
     size_t ws_cap = 0;
     uint64_t ws_epoch = 0;                    // bumps when the arena moves (captured graphs hold its addresses)
 };
-static const int kMaxLanes = 4;
+static const int kMaxLanes = 8;
+static const int kDefaultLanes = 4;  // SCB_LANES=1..8 overrides (tuning)
 
 struct scb_context {
     int device = 0;
@@ -386,6 +390,16 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
     };
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+#ifndef SCB_EMU
+    {   // plans allocate their eroded mask with cudaMallocAsync: keep freed blocks in the pool across syncs
+        // (the default release threshold of 0 hands them back to the OS at every synchronisation)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+#endif
     if ((e = lane_create(&c->lanes[0], (cudaStream_t)external_stream)) != cudaSuccess) return bail("stream/event creation", e);
     c->n_lanes = 1;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -700,6 +714,52 @@ static int check_image(scb_context* c, const scb_image* im, int rows, int cols, 
     return SCB_OK;
 }
 
+// blend = dst everywhere EXCEPT the ROI interior (which the device result overwrites): disjoint from the
+// D2H target, so it needs no ordering against the download and can run on several host threads while the
+// GPU works.  (OpenCV: dst.copyTo(blend) of the whole frame, then the ROI is overwritten.)
+static void host_copy_rows(const scb_image* dst, scb_image* blend, const scb_geometry& g, int y0, int y1) {
+    const size_t row_bytes = (size_t)3 * dst->cols;
+    const int iy0 = g.empty ? dst->rows : g.ry + 1, iy1 = g.empty ? dst->rows : g.ry + g.h - 1;
+    const size_t left = (size_t)3 * (g.rx + 1), right0 = (size_t)3 * (g.rx + g.w - 1);
+    for (int y = y0; y < y1; ++y) {
+        char* o = (char*)blend->data + (size_t)y * blend->stride;
+        const char* i = (const char*)dst->data + (size_t)y * dst->stride;
+        if (y < iy0 || y >= iy1) {
+            std::memcpy(o, i, row_bytes);
+        } else {
+            std::memcpy(o, i, left);
+            std::memcpy(o + right0, i + right0, row_bytes - right0);
+        }
+    }
+}
+
+static void host_copy_outside(const scb_image* dst, scb_image* blend, const scb_geometry& g, int max_threads) {
+    const size_t bytes = (size_t)3 * dst->cols * dst->rows;
+    int T = (int)(bytes >> 21);  // one thread per 2 MiB
+    if (T > max_threads) T = max_threads;
+    if (T <= 1) {
+        host_copy_rows(dst, blend, g, 0, dst->rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int per = (dst->rows + T - 1) / T;
+    for (int t = 1; t < T; ++t) {
+        const int a = t * per, b = (a + per < dst->rows) ? a + per : dst->rows;
+        if (a < b) th.emplace_back(host_copy_rows, dst, blend, std::cref(g), a, b);
+    }
+    host_copy_rows(dst, blend, g, 0, per < dst->rows ? per : dst->rows);
+    for (auto& t : th) t.join();
+}
+
+static int host_threads() {
+    static const int n = [] {
+        unsigned h = std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("SCB_HOST_THREADS")) h = (unsigned)std::atoi(e);
+        return (int)(h < 1 ? 1 : (h > 8 ? 8 : h));
+    }();
+    return n;
+}
+
 struct Workspace {
     unsigned char *stD = nullptr, *stS = nullptr, *stO = nullptr;
     long long pD = 0, pS = 0, pO = 0;
@@ -862,7 +922,8 @@ struct StageTimer {
     }
 };
 
-static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm, bool defer_host_sync = false) {
+// defer_host: batch mode -- leave the trailing stream sync AND the host-side dst->blend copy to the caller
+static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm, bool defer_host = false) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     int rc;
@@ -879,7 +940,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     if (g.empty) {  // OpenCV: blend = dst
         if (copy_dst) {
             if (host) {
-                for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
+                if (!defer_host) host_copy_outside(dst, blend, g, host_threads());
             } else {
                 SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, p->lane->stream));
             }
@@ -936,12 +997,11 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     tm.mark(ST_ROWS_INV);
     SCB_CUDA(c, cudaGetLastError());
     if (host) {
-        // blend = dst.copy() on the host while the GPU works, then only the ROI interior comes back
-        if (copy_dst)
-            for (int y = 0; y < p->dst_rows; ++y) std::memcpy((char*)blend->data + (size_t)y * blend->stride, (const char*)dst->data + (size_t)y * dst->stride, row_bytes);
+        // only the ROI interior comes back; everything else of blend is copied from dst on the host while the GPU works
         SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, p->lane->stream));
         tm.mark(ST_OUT);
-        if (!defer_host_sync) {
+        if (!defer_host) {
+            if (copy_dst) host_copy_outside(dst, blend, g, host_threads());
             SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
             SCB_CUDA(c, cudaGetLastError());
         }
@@ -1056,10 +1116,22 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
     SCB_CUDA(c, cudaSetDevice(c->device));
     static const int kChunk = 64;
     int rc;
-    if ((rc = ensure_lanes(c, n_jobs < kMaxLanes ? n_jobs : kMaxLanes))) return rc;
+    int want_lanes = kDefaultLanes;
+    if (const char* e = std::getenv("SCB_LANES")) want_lanes = std::atoi(e) > 0 ? std::atoi(e) : kDefaultLanes;
+    if (want_lanes > n_jobs) want_lanes = n_jobs;
+    if (want_lanes < c->n_lanes) want_lanes = c->n_lanes;
+    if ((rc = ensure_lanes(c, want_lanes))) return rc;
     if ((rc = ensure_bbox_slots(c, kChunk))) return rc;
     const int L = c->n_lanes;
-    if (!c->prep) SCB_CUDA(c, cudaStreamCreateWithFlags(&c->prep, cudaStreamNonBlocking));
+    if (!c->prep) {  // high priority: the next chunk's bounding boxes must not queue behind the lanes' transform kernels
+#ifdef SCB_EMU
+        SCB_CUDA(c, cudaStreamCreateWithFlags(&c->prep, cudaStreamNonBlocking));
+#else
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        SCB_CUDA(c, cudaStreamCreateWithPriority(&c->prep, cudaStreamNonBlocking, hi));
+#endif
+    }
     int worst = SCB_OK;
     std::string first_error;
     auto note = [&](scb_job& j, int status) {
@@ -1071,8 +1143,15 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
     };
     std::vector<scb_plan*> plans(kChunk);
     std::vector<PlanInput> inputs(kChunk);
+    std::vector<scb_geometry> geoms(kChunk);
+    std::vector<char> copy_ok(kChunk);
+    // SCB_BATCH_TRACE=1: host wall time of each phase of the batch (stderr), for tuning
+    static const bool trace = std::getenv("SCB_BATCH_TRACE") != nullptr;
+    double t_phase[5] = {0, 0, 0, 0, 0};
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int base = 0; base < n_jobs; base += kChunk) {
         const int m = (n_jobs - base < kChunk) ? n_jobs - base : kChunk;
+        double t0 = now();
         for (int i = 0; i < m; ++i) {
             scb_job& j = jobs[base + i];
             plans[i] = nullptr;
@@ -1082,22 +1161,56 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
             }
             note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, i, &plans[i], &inputs[i]));
         }
+        double t1 = now();
         SCB_CUDA(c, cudaStreamSynchronize(c->prep));
         SCB_CUDA(c, cudaGetLastError());
+        double t2 = now();
+        t_phase[0] += t1 - t0;
+        t_phase[1] += t2 - t1;
         for (int i = 0; i < m; ++i) {
             if (!plans[i]) continue;
             scb_job& j = jobs[base + i];
+            double a = now();
             int st = plan_finish(plans[i], inputs[i]);  // destroys the plan on failure
+            double b = now();
+            t_phase[2] += b - a;
+            scb_geometry gtmp{};
             if (st == SCB_OK) {
                 StageTimer tm;
-                st = execute_impl(plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host_sync=*/true);
+                gtmp = plans[i]->g;
+                st = execute_impl(plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host=*/true);
                 scb_plan_destroy(plans[i]);  // stream-ordered frees: the queued kernels finish first
             }
+            t_phase[3] += now() - b;
             plans[i] = nullptr;
+            geoms[i] = st == SCB_OK ? gtmp : scb_geometry();
+            copy_ok[i] = (st == SCB_OK);
             note(j, st);
         }
+        if (mem_kind == SCB_MEM_HOST) {  // blend = dst outside each ROI interior: a parallel-for over the chunk's jobs
+            double a = now();
+            const int T = host_threads();
+            std::vector<std::thread> th;
+            auto work = [&](int t) {
+                for (int i = t; i < m; i += T) {
+                    scb_job& j = jobs[base + i];
+                    if (copy_ok[i] && j.blend.data != j.dst.data) host_copy_rows(&j.dst, &j.blend, geoms[i], 0, j.dst.rows);
+                }
+            };
+            for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto& t : th) t.join();
+            t_phase[3] += now() - a;
+        }
     }
-    if ((rc = scb_sync(c))) return rc;
+    {
+        double a = now();
+        if ((rc = scb_sync(c))) return rc;
+        t_phase[4] = now() - a;
+    }
+    if (trace)
+        std::fprintf(stderr, "scb_clone_batch: %d jobs, %d lanes: plan_begin %.2f ms, prep syncs %.2f ms, plan_finish %.2f ms, execute+destroy %.2f ms, final sync %.2f ms\n",
+                     n_jobs, L, t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4]);
     if (worst != SCB_OK) c->err = first_error;
     return worst;
 }

@@ -141,14 +141,51 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
     const int X = x0 + 1, Y = y + 1;
     // row Y from column X-1 (20 bytes cover X-1 .. X+4), rows Y-1 / Y+1 from column X (12 bytes cover X .. X+3)
     unsigned dm[5], du[3], dd[3], sm[5], su[3], sd[3], em[2], eu[1];
+    load_unaligned_words<2>(s.E + (long long)Y * s.e_pitch + (X - 1), em);
+    load_unaligned_words<1>(s.E + (long long)(Y - 1) * s.e_pitch + X, eu);
+    {
+        // Fast path (almost every thread): the nine mask taps of the four pixels are all 0 or all 255 and no
+        // pixel touches the ROI border, so g is the 5-point Laplacian of ONE image, a 1-D stencil over its
+        // interleaved bytes (taps at -3, +3, -pitch, +pitch bytes).  Only that image is read, and the twelve
+        // values are formed two at a time in packed 16-bit lanes (biased by 2048 so that no borrow crosses a
+        // lane) and converted with the 2^23 trick: ~35 instructions per pixel instead of ~140, which is what
+        // lets the kernel run at HBM speed.  The results are small exact integers, hence bit-identical to
+        // the float path below.
+        const unsigned m_and = em[0] & eu[0] & (em[1] | 0xffffff00u), m_or = em[0] | eu[0] | (em[1] & 0xffu);
+        const bool all_src = (m_and == 0xffffffffu), all_dst = (m_or == 0u);
+        if ((all_src || all_dst) && x0 > 0 && Y > 1 && Y < s.h - 2) {
+            const unsigned char* img = all_src ? s.S : s.D;
+            const long long pitch = all_src ? s.s_pitch : s.d_pitch;
+            unsigned m[5], u[3], d[3];
+            load_unaligned_words<5>(img + (long long)Y * pitch + 3 * (X - 1), m);
+            load_unaligned_words<3>(img + (long long)(Y - 1) * pitch + 3 * X, u);
+            load_unaligned_words<3>(img + (long long)(Y + 1) * pitch + 3 * X, d);
+            float o[12];
+            SCB_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                const unsigned l = m[j];                                        // bytes e-3
+                const unsigned c = __funnelshift_r(m[j], m[j + 1], 24);         // bytes e
+                const unsigned r = __funnelshift_r(m[j + 1], m[j + 2], 16);     // bytes e+3
+                SCB_UNROLL
+                for (int half = 0; half < 2; ++half) {
+                    const unsigned sel = half ? 0x4342u : 0x4140u;  // two bytes -> two 16-bit lanes
+                    unsigned t = 0x08000800u + __byte_perm(l, 0u, sel) + __byte_perm(r, 0u, sel) + __byte_perm(u[j], 0u, sel) + __byte_perm(d[j], 0u, sel);
+                    t -= 4u * __byte_perm(c, 0u, sel);
+                    o[4 * j + 2 * half + 0] = __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7610u)) - 8390656.0f;  // (2^23 + 2048 + v) - (2^23 + 2048)
+                    o[4 * j + 2 * half + 1] = __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7632u)) - 8390656.0f;
+                }
+            }
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(g0 + c * plane) = make_float4(o[c], o[3 + c], o[6 + c], o[9 + c]);
+            return;
+        }
+    }
     load_unaligned_words<5>(s.D + (long long)Y * s.d_pitch + 3 * (X - 1), dm);
     load_unaligned_words<3>(s.D + (long long)(Y - 1) * s.d_pitch + 3 * X, du);
     load_unaligned_words<3>(s.D + (long long)(Y + 1) * s.d_pitch + 3 * X, dd);
     load_unaligned_words<5>(s.S + (long long)Y * s.s_pitch + 3 * (X - 1), sm);
     load_unaligned_words<3>(s.S + (long long)(Y - 1) * s.s_pitch + 3 * X, su);
     load_unaligned_words<3>(s.S + (long long)(Y + 1) * s.s_pitch + 3 * X, sd);
-    load_unaligned_words<2>(s.E + (long long)Y * s.e_pitch + (X - 1), em);
-    load_unaligned_words<1>(s.E + (long long)(Y - 1) * s.e_pitch + X, eu);
     float out[3][4];
     SCB_UNROLL
     for (int k = 0; k < 4; ++k) {

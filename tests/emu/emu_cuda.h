@@ -266,6 +266,14 @@ inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { return (unsigned)((((uint64_t)hi << 32) | lo) >> (shift & 31)); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, default mode (selector nibbles 0..7, no sign replication)
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline int __float2int_rz(float f) { return (int)f; }
 inline unsigned __float2uint_rz(float f) { return (unsigned)f; }
 inline float __int2float_rn(int i) { return (float)i; }
