@@ -484,6 +484,7 @@ def sharded_leg(env: Env, args):
     src, dst, mask, p = workloads.make_config("cfg4", seed=0)  # every rank holds the same u8 inputs (no halo exchange)
     stream = torch.cuda.Stream(device=env.dev)  # the library, torch's pack/unpack copies and NCCL all order on this stream
     ctx = scb.Context(env.local_rank, stream=stream.cuda_stream)
+    ctx.set_engine(capi.ENGINE_FFT)  # row/column-sharded passes exist for the FFT engine
     d_src, d_dst, d_mask = (torch.from_numpy(a).to(env.dev) for a in (src, dst, mask))
     d_blend = d_dst.clone()
     torch.cuda.synchronize()

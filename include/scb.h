@@ -65,6 +65,10 @@ enum {
     SCB_EXEC_BLEND_PREFILLED = 1 /* blend already holds a copy of dst (or aliases it): write the ROI interior only */
 };
 
+/* transform engines.  AUTO: tensor cores (tcgen05 dense sine-basis contraction, 3xTF32) for line lengths 16..4096,
+ * the Bluestein FFT engine otherwise.  The environment variable SCB_ENGINE=tc|fft sets the default. */
+enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2 };
+
 /* scb_plan_get_intermediate selectors; all float32, planar [3][rows][cols] */
 enum {
     SCB_INT_GRADIENT_X = 0, /* [3][h][w]    blended forward-difference gradient                  */
@@ -103,6 +107,12 @@ const char* scb_last_error(const scb_context* ctx); /* ctx may be NULL: error of
 const char* scb_status_string(int status);
 uint64_t scb_kernel_launches(const scb_context* ctx); /* kernels this library has launched on ctx so far */
 int scb_device_count(void);
+/* Chooses the DST engine of plans created afterwards (SCB_ENGINE_*).  The reference makes the same choice at
+ * compile time: SC_FFT_ENABLE, seamlessClone_imp.h:15 (cuFFT solver vs cuBLAS sine-basis solver). */
+int scb_set_engine(scb_context* ctx, int engine);
+/* Unit check of one tensor-core pass: random lines of length n against float64 direct sums; max error relative
+ * to the largest output of the line.  (No reference counterpart: SC_Test, seamlessClone_imp.cpp:532-554, is dead code.) */
+int scb_tc_selftest(scb_context* ctx, int n, int lines, int transposed, double* max_rel_err);
 
 /* pinned host memory helpers (cudaMallocHost / cudaFreeHost) */
 int scb_host_alloc(void** out, size_t bytes);
@@ -113,6 +123,7 @@ int scb_plan_create(scb_context* ctx, const scb_image* mask, int mask_mem_kind, 
                     int dst_rows, int dst_cols, int px, int py, scb_plan** out);
 int scb_plan_destroy(scb_plan* plan);
 int scb_plan_geometry(const scb_plan* plan, scb_geometry* out);
+int scb_plan_engine(const scb_plan* plan); /* SCB_ENGINE_FFT or SCB_ENGINE_TC */
 /* Asynchronous on the context stream for SCB_MEM_DEVICE; for SCB_MEM_HOST returns when blend is complete. */
 int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags);
 /* Same call with CUDA events between the stages (on the context stream); returns after a stream sync.

@@ -72,6 +72,15 @@ class Context:
     def sync(self):
         self._check(self.lib.scb_sync(self.handle))
 
+    def set_engine(self, engine: int):
+        """DST engine of plans created from now on: capi.ENGINE_AUTO / ENGINE_FFT / ENGINE_TC."""
+        self._check(self.lib.scb_set_engine(self.handle, int(engine)))
+
+    def tc_selftest(self, n: int, lines: int, transposed: bool = False) -> float:
+        err = C.c_double()
+        self._check(self.lib.scb_tc_selftest(self.handle, int(n), int(lines), int(bool(transposed)), C.byref(err)))
+        return float(err.value)
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.scb_kernel_launches(self.handle))
@@ -128,6 +137,7 @@ class Plan:
         g = capi.ScbGeometry()
         ctx._check(self.lib.scb_plan_geometry(self.handle, C.byref(g)))
         self.geometry = g
+        self.engine = int(self.lib.scb_plan_engine(self.handle))
 
     def execute(self, src, dst, blend=None, mem_kind: int = MEM_HOST, flags: int = EXEC_DEFAULT):
         if mem_kind == MEM_HOST:

@@ -9,6 +9,7 @@
 // one that reports a HOST-resident result, dst never modified, mask never modified.
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -22,6 +23,7 @@
 #include "scb_kernels3.cuh"
 #include "scb_platform.h"
 #include "scb_tables.h"
+#include "scb_tc.cuh"
 
 using namespace scb;
 
@@ -55,8 +57,18 @@ struct Lane {
 static const int kMaxLanes = 8;
 static const int kDefaultLanes = 4;  // SCB_LANES=1..8 overrides (tuning)
 
+struct DevTcTab {
+    TcTabDev dev{};
+    void* block = nullptr;
+#ifndef SCB_EMU
+    CUtensorMap map;
+#endif
+};
+
 struct scb_context {
     int device = 0;
+    int engine = SCB_ENGINE_AUTO;
+    std::map<int, DevTcTab> tctabs;     // keyed by n (tensor-core engine: split sine bases + tensor maps)
     Lane lanes[kMaxLanes];
     int n_lanes = 0;
     cudaStream_t prep = nullptr;  // scb_clone_batch: mask uploads + bounding boxes of the next chunk
@@ -96,6 +108,8 @@ struct scb_plan {
     unsigned char* E = nullptr;
     long long e_pitch = 0;
     LenTabDev tx{}, ty{};
+    bool use_tc = false;                // tensor-core dense engine (scb_tc.cuh) instead of the FFT engine
+    const DevTcTab *ttx = nullptr, *tty = nullptr;
     const float* fx = nullptr;
     const float* fy = nullptr;
     int lowkx = 0, lowky = 0;
@@ -349,6 +363,76 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     return SCB_OK;
 }
 
+#ifndef SCB_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+#endif
+
+// split sine basis of one line length for the tensor-core engine, built on the device at plan time
+static int get_tctab(scb_context* c, int n, const DevTcTab** out) {
+    auto it = c->tctabs.find(n);
+    if (it != c->tctabs.end()) {
+        *out = &it->second;
+        return SCB_OK;
+    }
+    DevTcTab d;
+    tc_geometry(n, &d.dev);
+    const size_t floats = (size_t)4 * d.dev.rows * d.dev.kpad;
+    SCB_CUDA(c, cudaMalloc(&d.block, floats * sizeof(float)));
+    d.dev.basis = (const float*)d.block;
+    {
+        const long long total = 2LL * d.dev.rows * d.dev.kpad;
+        long long blocks = (total + 255) / 256;
+        if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+        SCB_LAUNCH(tc_basis_kernel, dim3((unsigned)blocks), dim3(256), 0, c->lanes[0].stream, d.dev, (float*)d.block);
+        c->launches++;
+    }
+    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));  // publishes the table to every lane
+    SCB_CUDA(c, cudaGetLastError());
+#ifndef SCB_EMU
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        cudaFree(d.block);
+        return fail(c, SCB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)d.dev.kpad, (cuuint64_t)4 * d.dev.rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d.dev.kpad * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcKB, (cuuint32_t)d.dev.nt};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&d.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.block, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cudaFree(d.block);
+        return fail(c, SCB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    }
+#endif
+    auto ins = c->tctabs.emplace(n, d);
+    *out = &ins.first->second;
+    return SCB_OK;
+}
+
+static bool tc_eligible(const scb_context* c, int nx, int ny) {
+    static const int env_engine = [] {
+        const char* e = std::getenv("SCB_ENGINE");
+        if (!e) return (int)SCB_ENGINE_AUTO;
+        if (std::strcmp(e, "tc") == 0) return (int)SCB_ENGINE_TC;
+        if (std::strcmp(e, "fft") == 0 || std::strcmp(e, "scalar") == 0) return (int)SCB_ENGINE_FFT;
+        return (int)SCB_ENGINE_AUTO;
+    }();
+    const int want = c->engine != SCB_ENGINE_AUTO ? c->engine : env_engine;
+    if (want == SCB_ENGINE_FFT) return false;
+    return nx >= kTcMinN && ny >= kTcMinN && nx <= kTcMaxN && ny <= kTcMaxN;
+}
+
 static int get_filter(scb_context* c, int extent, const float** out) {
     auto it = c->filters.find(extent);
     if (it != c->filters.end()) {
@@ -425,6 +509,7 @@ extern "C" int scb_destroy(scb_context* c) {
     }
     for (auto& kv : c->lentabs) cudaFree(kv.second.block);
     for (auto& kv : c->filters) cudaFree(kv.second);
+    for (auto& kv : c->tctabs) cudaFree(kv.second.block);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
     delete c;
@@ -436,6 +521,13 @@ extern "C" int scb_sync(scb_context* c) {
     SCB_CUDA(c, cudaSetDevice(c->device));
     for (int i = 0; i < c->n_lanes; ++i) SCB_CUDA(c, cudaStreamSynchronize(c->lanes[i].stream));
     SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" int scb_set_engine(scb_context* c, int engine) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (engine != SCB_ENGINE_AUTO && engine != SCB_ENGINE_FFT && engine != SCB_ENGINE_TC) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_engine: unknown engine");
+    c->engine = engine;
     return SCB_OK;
 }
 
@@ -612,6 +704,11 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
     }
     p->lowkx = p->tx.lowk;
     p->lowky = p->ty.lowk;
+    p->use_tc = tc_eligible(c, g.nx, g.ny);
+    if (p->use_tc && ((rc = get_tctab(c, g.nx, &p->ttx)) || (rc = get_tctab(c, g.ny, &p->tty)))) {
+        scb_plan_destroy(p);
+        return rc;
+    }
     return SCB_OK;
 }
 
@@ -641,6 +738,10 @@ extern "C" int scb_plan_geometry(const scb_plan* p, scb_geometry* out) {
     if (!p || !out) return SCB_ERR_INVALID_ARGUMENT;
     *out = p->g;
     return SCB_OK;
+}
+extern "C" int scb_plan_engine(const scb_plan* p) {
+    if (!p) return -1;
+    return p->use_tc ? SCB_ENGINE_TC : SCB_ENGINE_FFT;
 }
 extern "C" int scb_plan_lowk(const scb_plan* p, int* lowkx, int* lowky) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
@@ -765,6 +866,7 @@ struct Workspace {
     long long pD = 0, pS = 0, pO = 0;
     float *At = nullptr, *Ct = nullptr, *lowspec = nullptr, *G = nullptr;
     int gp = 0;
+    int tpx = 0, tpy = 0;  // tensor-core engine: line pitches of the [..][nx] and [..][ny] orientations
     double* R = nullptr;
 };
 
@@ -781,7 +883,14 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     w->pD = w->pS = (long long)align_up((size_t)3 * g.w, 128);
     w->pO = (long long)align_up((size_t)3 * g.nx, 128);
     w->gp = (int)align_up((size_t)g.nx, 4);
-    const size_t oAt = take(in * sizeof(float)), oCt = take(in * sizeof(float));
+    size_t buf = in;
+    if (p->use_tc) {  // tensor-core engine: lines padded to 16 bytes, each buffer holds either orientation
+        w->tpx = (int)align_up((size_t)g.nx, 4);
+        w->tpy = (int)align_up((size_t)g.ny, 4);
+        const size_t a = (size_t)3 * g.nx * w->tpy, b = (size_t)3 * g.ny * w->tpx;
+        buf = a > b ? a : b;
+    }
+    const size_t oAt = take(buf * sizeof(float)), oCt = take(buf * sizeof(float));
     const size_t oG = take((size_t)3 * g.ny * w->gp * sizeof(float));
     const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
@@ -910,6 +1019,33 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
     launch_rows_inv(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, r);
 }
 
+// ---- tensor-core engine: the four passes + compose (scb_tc.cuh) ----
+static int tc_configure_once(scb_context* c) {
+#ifndef SCB_EMU
+    static bool done = false;
+    if (!done) {
+        SCB_CUDA(c, cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+        done = true;
+    }
+#endif
+    return SCB_OK;
+}
+
+static void launch_tc_pass(scb_plan* p, const DevTcTab* tab, const TcPassParams& pp) {
+    const int lines = pp.line_end - pp.line0;
+    if (lines <= 0) return;
+    const dim3 grid((lines + kTcM - 1) / kTcM, 2 * tab->dev.ntiles);
+#ifdef SCB_EMU
+    SCB_LAUNCH(tc_pass_kernel, grid, dim3(kTcM), 0, p->lane->stream, pp);
+#else
+    tc_pass_kernel<<<grid, kTcThreads, kTcSmemBytes, p->lane->stream>>>(tab->map, pp);
+#endif
+    p->ctx->launches++;
+}
+
+struct StageTimer;
+static int tc_solve(scb_plan* p, const Workspace& w, unsigned char* out, long long out_pitch, StageTimer& tm);
+
 // stage boundaries recorded by scb_plan_execute_timed
 enum { ST_BEGIN = 0, ST_IN, ST_RHS, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_COUNT };
 
@@ -923,6 +1059,98 @@ struct StageTimer {
 };
 
 // defer_host: batch mode -- leave the trailing stream sync AND the host-side dst->blend copy to the caller
+static int tc_solve(scb_plan* p, const Workspace& w, unsigned char* out, long long out_pitch, StageTimer& tm) {
+    scb_context* c = p->ctx;
+    const scb_geometry& g = p->g;
+    int rc = tc_configure_once(c);
+    if (rc) return rc;
+    float* bufA = w.At;
+    float* bufB = w.Ct;
+    TcPassParams a{};
+    // rows forward: G [c][y][x] -> At [c][kx][y]
+    a.tab = p->ttx->dev;
+    a.in = w.G;
+    a.in_plane = (long long)g.ny * w.gp;
+    a.in_pitch = w.gp;
+    a.lpc = g.ny;
+    a.line0 = 0;
+    a.line_end = 3 * g.ny;
+    a.out = bufA;
+    a.out_plane = (long long)g.nx * w.tpy;
+    a.out_pitch = w.tpy;
+    a.transposed = 1;
+    a.scale = -2.0f;  // OpenCV: Im of the odd-extension FFT = -2 sum x sin
+    launch_tc_pass(p, p->ttx, a);
+    if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(p->lane->stream, p->lane->ev_join, 0));  // the refinement corner is needed from here on
+    tm.mark(ST_ROWS_FWD);
+    // columns forward + refinement + eigenvalue division: At [c][kx][y] -> Q [c][kx][ky]
+    TcPassParams b{};
+    b.tab = p->tty->dev;
+    b.in = bufA;
+    b.in_plane = (long long)g.nx * w.tpy;
+    b.in_pitch = w.tpy;
+    b.lpc = g.nx;
+    b.line0 = 0;
+    b.line_end = 3 * g.nx;
+    b.out = bufB;
+    b.out_plane = (long long)g.nx * w.tpy;
+    b.out_pitch = w.tpy;
+    b.transposed = 0;
+    b.scale = -2.0f;
+    b.f_line = p->fx;
+    b.f_out = p->fy;
+    b.lowspec = w.lowspec;
+    b.lowk_line = p->lowkx;
+    b.lowk_out = p->lowky;
+    b.spec_dump = p->debug ? p->dbg_spec : nullptr;
+    launch_tc_pass(p, p->tty, b);
+    // columns inverse: Q [c][kx][ky] -> Ct [c][y][kx]
+    TcPassParams d{};
+    d.tab = p->tty->dev;
+    d.in = bufB;
+    d.in_plane = (long long)g.nx * w.tpy;
+    d.in_pitch = w.tpy;
+    d.lpc = g.nx;
+    d.line0 = 0;
+    d.line_end = 3 * g.nx;
+    d.out = bufA;
+    d.out_plane = (long long)g.ny * w.tpx;
+    d.out_pitch = w.tpx;
+    d.transposed = 1;
+    d.scale = (float)(1.0 / (double)(g.ny + 1));
+    launch_tc_pass(p, p->tty, d);
+    tm.mark(ST_COLS);
+    // rows inverse: Ct [c][y][kx] -> U [c][y][x]
+    TcPassParams e{};
+    e.tab = p->ttx->dev;
+    e.in = bufA;
+    e.in_plane = (long long)g.ny * w.tpx;
+    e.in_pitch = w.tpx;
+    e.lpc = g.ny;
+    e.line0 = 0;
+    e.line_end = 3 * g.ny;
+    e.out = bufB;
+    e.out_plane = (long long)g.ny * w.tpx;
+    e.out_pitch = w.tpx;
+    e.transposed = 0;
+    e.scale = (float)(1.0 / (double)(g.nx + 1));
+    launch_tc_pass(p, p->ttx, e);
+    // compose: U planar float -> interleaved u8
+    TcComposeParams cp;
+    cp.u = bufB;
+    cp.plane = (long long)g.ny * w.tpx;
+    cp.pitch = w.tpx;
+    cp.nx = g.nx;
+    cp.ny = g.ny;
+    cp.out = out;
+    cp.out_pitch = out_pitch;
+    cp.u_dump = p->debug ? p->dbg_u : nullptr;
+    SCB_LAUNCH(tc_compose_kernel, dim3((g.nx + 511) / 512, g.ny), dim3(128), 0, p->lane->stream, cp);
+    c->launches++;
+    tm.mark(ST_ROWS_INV);
+    return SCB_OK;
+}
+
 static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm, bool defer_host = false) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
@@ -988,13 +1216,17 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         SCB_CUDA(c, cudaEventRecord(p->lane->ev_join, p->lane->side));
     }
     tm.mark(ST_LOW);
-    run_rows_fwd(p, st, w.G, w.gp, w.At, 0, g.ny);
-    if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(p->lane->stream, p->lane->ev_join, 0));
-    tm.mark(ST_ROWS_FWD);
-    run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
-    tm.mark(ST_COLS);
-    run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
-    tm.mark(ST_ROWS_INV);
+    if (p->use_tc) {
+        if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
+    } else {
+        run_rows_fwd(p, st, w.G, w.gp, w.At, 0, g.ny);
+        if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(p->lane->stream, p->lane->ev_join, 0));
+        tm.mark(ST_ROWS_FWD);
+        run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
+        tm.mark(ST_COLS);
+        run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+        tm.mark(ST_ROWS_INV);
+    }
     SCB_CUDA(c, cudaGetLastError());
     if (host) {
         // only the ROI interior comes back; everything else of blend is copied from dst on the host while the GPU works
@@ -1281,6 +1513,85 @@ extern "C" int scb_plan_rows_inverse(scb_plan* p, const float* ct_dev, scb_image
     unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
     run_rows_inv(p, ct_dev, bInt, blend->stride, y0, y1);
     SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-test of one tensor-core pass against float64 direct sums (unit check of the tcgen05/TMA plumbing)
+// ------------------------------------------------------------------------------------------------
+extern "C" int scb_tc_selftest(scb_context* c, int n, int lines, int transposed, double* max_rel_err) {
+    if (!c || !max_rel_err) return SCB_ERR_INVALID_ARGUMENT;
+    if (n < kTcMinN || n > kTcMaxN || lines < 1) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_tc_selftest: n or lines out of range");
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    int rc = tc_configure_once(c);
+    if (rc) return rc;
+    const DevTcTab* tab = nullptr;
+    if ((rc = get_tctab(c, n, &tab))) return rc;
+    const int pin = (int)align_up((size_t)n, 4), pl = (int)align_up((size_t)lines, 4);
+    std::vector<float> hin((size_t)lines * pin, 0.f);
+    unsigned long long seed = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)n << 20) ^ (unsigned long long)lines;
+    auto rnd = [&]() {
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        return (double)(seed >> 11) / (double)(1ull << 53);
+    };
+    for (int l = 0; l < lines; ++l)
+        for (int j = 0; j < n; ++j) hin[(size_t)l * pin + j] = (float)((rnd() - 0.5) * 2000.0);
+    const size_t out_floats = transposed ? (size_t)n * pl : (size_t)lines * pin;
+    float *din = nullptr, *dout = nullptr;
+    SCB_CUDA(c, cudaMalloc(&din, hin.size() * sizeof(float)));
+    SCB_CUDA(c, cudaMalloc(&dout, out_floats * sizeof(float)));
+    cudaStream_t st = c->lanes[0].stream;
+    SCB_CUDA(c, cudaMemcpyAsync(din, hin.data(), hin.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    SCB_CUDA(c, cudaMemsetAsync(dout, 0xff, out_floats * sizeof(float), st));  // NaN pattern: unwritten outputs show up
+    TcPassParams a{};
+    a.tab = tab->dev;
+    a.in = din;
+    a.in_plane = 0;
+    a.in_pitch = pin;
+    a.lpc = lines;
+    a.line0 = 0;
+    a.line_end = lines;
+    a.out = dout;
+    a.out_plane = 0;
+    a.out_pitch = transposed ? pl : pin;
+    a.transposed = transposed;
+    a.scale = 1.0f;
+    {
+        scb_plan fake;
+        fake.ctx = c;
+        fake.lane = &c->lanes[0];
+        launch_tc_pass(&fake, tab, a);
+    }
+    std::vector<float> hout(out_floats);
+    SCB_CUDA(c, cudaMemcpyAsync(hout.data(), dout, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(c, SCB_ERR_CUDA, std::string("scb_tc_selftest: ") + cudaGetErrorString(e));
+    const double PI = 3.14159265358979323846;
+    double worst = 0.0;
+    const int step = lines > 24 ? lines / 24 : 1;
+    std::vector<double> ref(n);
+    for (int l = 0; l < lines; l += step) {
+        double mx = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double sum = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const long long ph = ((long long)(j + 1) * (k + 1)) % (2LL * (n + 1));
+                sum += (double)hin[(size_t)l * pin + j] * std::sin(PI * (double)ph / (double)(n + 1));
+            }
+            ref[k] = sum;
+            if (std::fabs(sum) > mx) mx = std::fabs(sum);
+        }
+        for (int k = 0; k < n; ++k) {
+            const float got = transposed ? hout[(size_t)k * pl + l] : hout[(size_t)l * pin + k];
+            double err = std::fabs((double)got - ref[k]) / (mx > 0 ? mx : 1.0);
+            if (!(err == err)) err = 1e30;  // NaN
+            if (err > worst) worst = err;
+        }
+    }
+    *max_rel_err = worst;
     return SCB_OK;
 }
 

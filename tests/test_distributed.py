@@ -32,6 +32,7 @@ def _worker(rank, world, port, lib_path, out_dir):
     try:
         src, dst, mask, p = so.make_config("small", 12)
         ctx = scb.Context(0, lib_path=lib_path)
+        ctx.set_engine(capi.ENGINE_FFT)  # the sharded passes are the FFT engine's
         hm, hs, hd = (np.ascontiguousarray(a) for a in (mask, src, dst))
         plan = scb.Plan(ctx, capi.host_view(hm), src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
         blend = torch.from_numpy(dst.copy())
@@ -52,6 +53,7 @@ def test_sharded_solve_over_gloo(tmp_path, emu_lib, world):
     mp.spawn(_worker, args=(world, port, emu_lib, str(tmp_path)), nprocs=world, join=True)
     src, dst, mask, p = so.make_config("small", 12)
     with scb.Context(0, lib_path=emu_lib) as ctx:
+        ctx.set_engine(capi.ENGINE_FFT)
         single = ctx.seamless_clone(src, dst, mask, p)
     for r in range(world):
         got = np.load(tmp_path / f"blend_{r}.npy")

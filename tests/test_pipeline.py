@@ -53,9 +53,13 @@ def be(request):
     return Backend("cuda", request.getfixturevalue("cuda_lib"))
 
 
-@pytest.fixture(scope="module")
-def ctx(be):
+@pytest.fixture(scope="module", params=["tc", "fft"])
+def ctx(be, request):
+    """Every test runs on both DST engines: 'tc' = tensor-core dense contraction where eligible (line
+    lengths 16..4096; shorter lines fall back to the FFT engine), 'fft' = the Bluestein FFT engine."""
     c = be.context()
+    c.set_engine(capi.ENGINE_AUTO if request.param == "tc" else capi.ENGINE_FFT)
+    c.engine_name = request.param
     yield c
     c.close()
 
@@ -305,7 +309,9 @@ def test_sharded_solve_equals_single_solve(be, ctx):
     vm, hm = be.to_device(mask)
     vb, hb = be.to_device(dst)       # sharded passes write the interior only: start from a copy of dst
     vb1, hb1 = be.to_device(np.zeros_like(dst))
+    ctx.set_engine(capi.ENGINE_FFT)  # the sharded entry points run the FFT engine's passes
     plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    ctx.set_engine(capi.ENGINE_AUTO if ctx.engine_name == "tc" else capi.ENGINE_FFT)
     plan.execute(vs, vd, vb1, scb.MEM_DEVICE)
     ctx.sync()
     single = be.to_host(hb1).copy()
@@ -335,7 +341,8 @@ def test_launch_counter(ctx):
     plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
     before = ctx.kernel_launches
     plan.execute(src, dst)
-    assert ctx.kernel_launches - before == 6  # rhs, lowfreq rows, lowfreq cols, rows fwd, cols, rows inv
+    # FFT engine: rhs, lowfreq rows, lowfreq cols, rows fwd, cols, rows inv; tensor-core engine: 4 passes + compose instead of 3
+    assert ctx.kernel_launches - before == (8 if plan.engine == capi.ENGINE_TC else 6)
     plan.close()
 
 
@@ -413,7 +420,7 @@ def test_graph_replay_equals_plain_execute(be, ctx):
         for _ in range(3):  # first call captures, the next two replay
             plan.execute_graph(vs, vd, vb1)
         ctx.sync()
-        assert ctx.kernel_launches - before == 3 * 6
+        assert ctx.kernel_launches - before == 3 * (8 if plan.engine == capi.ENGINE_TC else 6)
         assert np.array_equal(be.to_host(hb0), be.to_host(hb1))
     plan.close()
 

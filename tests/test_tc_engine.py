@@ -1,0 +1,73 @@
+"""The tensor-core DST engine (csrc/scb_tc.cuh): one pass against float64 direct sums, and whole clones on
+both engines.  On the B200 (-m gpu) this exercises the tcgen05 / TMA / TMEM kernel; on CPU the emulator build
+runs the stand-in kernel with the same tables, fold, 3xTF32 split and epilogue (host logic + indexing)."""
+import numpy as np
+import pytest
+
+import seamlesscloneoptimization_b200 as scb
+from oracle import seamless_oracle as so
+from seamlesscloneoptimization_b200 import _capi as capi
+from tests import common
+
+# 3xTF32 with FP32 accumulation: error relative to the largest output of a line
+TC_PASS_TOL = 3e-6
+
+
+@pytest.mark.parametrize("n,lines", [(16, 1), (17, 5), (33, 40), (100, 130)])
+def test_pass_selftest_emulator(emu_lib, n, lines):
+    with scb.Context(0, lib_path=emu_lib) as c:
+        for tr in (False, True):
+            assert c.tc_selftest(n, lines, tr) < TC_PASS_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [16, 17, 31, 32, 33, 63, 64, 65, 100, 255, 256, 257, 511, 512, 513, 1000, 1339, 1808, 2049, 4092])
+def test_pass_selftest_b200(cuda_lib, n):
+    """Odd/even lengths, lengths around the 32-element k-block and the 256-bin N tile, partial line tiles."""
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        for lines in (1, 128, 129, 300):
+            if n > 2048 and lines > 129:
+                continue
+            for tr in (False, True):
+                err = c.tc_selftest(n, lines, tr)
+                assert err < TC_PASS_TOL, (n, lines, tr, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", [capi.ENGINE_TC, capi.ENGINE_FFT])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg5", "cfg2"])
+def test_full_size_vs_opencv_both_engines(cuda_lib, cfg, engine):
+    pytest.importorskip("cv2")
+    src, dst, mask, p = so.make_config(cfg, 0)
+    ref = so.cv_reference(src, dst, mask, p)
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        c.set_engine(engine)
+        plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
+        assert plan.engine == engine
+        blend = plan.execute(src, dst)
+        g = plan.geometry
+        plan.close()
+    a = blend[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
+    b = ref[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
+    cmp = so.compare_u8(a, b)
+    print(cfg, engine, cmp)
+    assert cmp["max_abs"] <= 1
+    assert cmp["pct_exact"] >= {"cfg1": 99.9, "cfg5": 99.9, "cfg2": 99.8}[cfg]  # cfg2: the oracle's own FFT noise floor is 99.85 %
+
+
+def test_engines_agree_on_float_intermediates(emu_lib):
+    src, dst, mask, p = so.make_config("small", 41)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    with scb.Context(0, lib_path=emu_lib) as c:
+        outs = {}
+        for eng in (capi.ENGINE_TC, capi.ENGINE_FFT):
+            c.set_engine(eng)
+            plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
+            assert plan.engine == eng
+            plan.set_debug(True)
+            plan.execute(src, dst)
+            outs[eng] = (plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0))
+            plan.close()
+    for eng, (spec, u) in outs.items():
+        assert so.rel_linf(spec, ref.spectrum) < common.FLOAT_REL_TOL
+        assert so.rel_linf(u, ref.solved) < common.FLOAT_REL_TOL

@@ -34,6 +34,7 @@ def main():
     p = ((S + 300) // 2, (S + 200) // 2)
     stream = torch.cuda.Stream(device=dev)
     ctx = scb.Context(local, stream=stream.cuda_stream)
+    ctx.set_engine(capi.ENGINE_FFT)  # the sharded passes are the FFT engine's: compare like with like
     d_src, d_dst, d_mask = (torch.from_numpy(a).to(dev) for a in (src, dst, mask))
     torch.cuda.synchronize()
     with torch.cuda.stream(stream):
