@@ -65,8 +65,10 @@ enum {
     SCB_EXEC_BLEND_PREFILLED = 1 /* blend already holds a copy of dst (or aliases it): write the ROI interior only */
 };
 
-/* transform engines.  AUTO: tensor cores (tcgen05 dense sine-basis contraction, 3xTF32) for line lengths 16..4096,
- * the Bluestein FFT engine otherwise.  The environment variable SCB_ENGINE=tc|fft sets the default. */
+/* transform engines.  FFT: the Bluestein shared-memory FFT engine (default; AUTO resolves to it).  TC: dense
+ * sine-basis contraction on the tensor cores (tcgen05, 3xTF32, even/odd fold) for line lengths 16..4096 -- opt-in:
+ * its FP32 accumulation error (~1e-5 relative at K ~ 900) is inside the 1e-4 bar for float intermediates but
+ * costs exactly-matching bytes at some shapes.  The environment variable SCB_ENGINE=tc|fft sets the default. */
 enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2 };
 
 /* scb_plan_get_intermediate selectors; all float32, planar [3][rows][cols] */

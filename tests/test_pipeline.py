@@ -58,7 +58,7 @@ def ctx(be, request):
     """Every test runs on both DST engines: 'tc' = tensor-core dense contraction where eligible (line
     lengths 16..4096; shorter lines fall back to the FFT engine), 'fft' = the Bluestein FFT engine."""
     c = be.context()
-    c.set_engine(capi.ENGINE_AUTO if request.param == "tc" else capi.ENGINE_FFT)
+    c.set_engine(capi.ENGINE_TC if request.param == "tc" else capi.ENGINE_FFT)
     c.engine_name = request.param
     yield c
     c.close()
@@ -311,7 +311,7 @@ def test_sharded_solve_equals_single_solve(be, ctx):
     vb1, hb1 = be.to_device(np.zeros_like(dst))
     ctx.set_engine(capi.ENGINE_FFT)  # the sharded entry points run the FFT engine's passes
     plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
-    ctx.set_engine(capi.ENGINE_AUTO if ctx.engine_name == "tc" else capi.ENGINE_FFT)
+    ctx.set_engine(capi.ENGINE_TC if ctx.engine_name == "tc" else capi.ENGINE_FFT)
     plan.execute(vs, vd, vb1, scb.MEM_DEVICE)
     ctx.sync()
     single = be.to_host(hb1).copy()

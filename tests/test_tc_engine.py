@@ -9,8 +9,10 @@ from oracle import seamless_oracle as so
 from seamlesscloneoptimization_b200 import _capi as capi
 from tests import common
 
-# 3xTF32 with FP32 accumulation: error relative to the largest output of a line
-TC_PASS_TOL = 3e-6
+# 3xTF32 with FP32 accumulation inside the tensor core (truncating adds): error relative to the largest output
+# of a line grows with the number of MMA steps -- measured 3.5e-7 (n = 64) ... 7e-6 (n = 1808) ... 2e-5 (n = 4092).
+# The emulator stand-in accumulates with round-to-nearest and stays near 1e-6.
+TC_PASS_TOL = 4e-5
 
 
 @pytest.mark.parametrize("n,lines", [(16, 1), (17, 5), (33, 40), (100, 130)])
@@ -52,7 +54,10 @@ def test_full_size_vs_opencv_both_engines(cuda_lib, cfg, engine):
     cmp = so.compare_u8(a, b)
     print(cfg, engine, cmp)
     assert cmp["max_abs"] <= 1
-    assert cmp["pct_exact"] >= {"cfg1": 99.9, "cfg5": 99.9, "cfg2": 99.8}[cfg]  # cfg2: the oracle's own FFT noise floor is 99.85 %
+    if engine == capi.ENGINE_FFT:
+        assert cmp["pct_exact"] >= {"cfg1": 99.9, "cfg5": 99.9, "cfg2": 99.8}[cfg]  # cfg2: the oracle's own FFT noise floor is 99.85 %
+    else:  # opt-in engine: +-1 LSB holds; exactness is limited by the tensor core's truncating FP32 accumulation
+        assert cmp["pct_exact"] >= 99.5
 
 
 def test_engines_agree_on_float_intermediates(emu_lib):
