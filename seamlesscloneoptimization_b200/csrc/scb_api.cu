@@ -240,6 +240,9 @@ static cudaError_t configure_one() {
         if ((e = set_smem(rows_fwd3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
         if ((e = set_smem(cols3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
         if ((e = set_smem(rows_inv3_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
+        if ((e = set_smem(rows_fwd4_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
+        if ((e = set_smem(cols4_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
+        if ((e = set_smem(rows_inv4_kernel<LOG2M>, GCfg<LOG2M>::SMEM)) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
@@ -256,13 +259,27 @@ static cudaError_t configure_all() {
 
 template <int LOG2M>
 static dim3 group_grid(int nlines) { return dim3((nlines + 1) / 2, GCfg<LOG2M>::NG == 1 ? 3 : 1); }
+template <int LOG2M>
+static dim3 quad_grid(int nlines) { return dim3((nlines + 3) / 4, GCfg<LOG2M>::NG == 1 ? 3 : 1); }
+// quad mode (two real lines per complex sequence) whenever the length's table carries the extended chirp spectrum;
+// SCB_QUAD=0 disables it (A/B checks)
+static bool use_quad(const LenTabDev& t) {
+    static const bool off = [] {
+        const char* e = std::getenv("SCB_QUAD");
+        return e && std::strcmp(e, "0") == 0;
+    }();
+    return t.bhat_q != nullptr && !off;
+}
 
 template <int LOG2M>
 static void launch_rows_fwd_t(cudaStream_t stream, int nlines, const RowsFwdParams& p) {
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             RowsFwd3Params pp{p, p.tx.gtw, p.y0 + nlines};
-            SCB_LAUNCH(rows_fwd3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            if (use_quad(p.tx) && p.rhs_in && !p.rhs_dump)
+                SCB_LAUNCH(rows_fwd4_kernel<LOG2M>, quad_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            else
+                SCB_LAUNCH(rows_fwd3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
@@ -274,7 +291,10 @@ static void launch_cols_t(cudaStream_t stream, int nlines, const ColsParams& p) 
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             Cols3Params pp{p, p.ty.gtw, p.x0 + nlines};
-            SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            if (use_quad(p.ty))
+                SCB_LAUNCH(cols4_kernel<LOG2M>, quad_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            else
+                SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
@@ -286,7 +306,10 @@ static void launch_rows_inv_t(cudaStream_t stream, int nlines, const RowsInvPara
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             RowsInv3Params pp{p, p.tx.gtw, p.y0 + nlines};
-            SCB_LAUNCH(rows_inv3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            if (use_quad(p.tx))
+                SCB_LAUNCH(rows_inv4_kernel<LOG2M>, quad_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
+            else
+                SCB_LAUNCH(rows_inv3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             return;
         }
     }
@@ -335,13 +358,15 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     const size_t M = (size_t)1 << h.log2m;
     const size_t off_chirp = 0;
     const size_t off_bhat = align_up(off_chirp + (n + 1) * sizeof(float2), 256);
-    const size_t off_tw = align_up(off_bhat + M * sizeof(float2), 256);
+    const size_t off_bhq = align_up(off_bhat + M * sizeof(float2), 256);
+    const size_t off_tw = align_up(off_bhq + h.bhat_q.size() * sizeof(float2), 256);
     const size_t off_ptw = align_up(off_tw + M * sizeof(float2), 256);
     const size_t off_sin = align_up(off_ptw + h.gtw.size() * sizeof(float), 256);
     const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
     std::vector<char> host(total, 0);
     std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
+    if (!h.bhat_q.empty()) std::memcpy(host.data() + off_bhq, h.bhat_q.data(), h.bhat_q.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_ptw, h.gtw.data(), h.gtw.size() * sizeof(float));
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
@@ -355,6 +380,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.lowk = h.lowk;
     d.dev.chirp = (const float2*)(b + off_chirp);
     d.dev.bhat_t = (const float2*)(b + off_bhat);
+    d.dev.bhat_q = h.bhat_q.empty() ? nullptr : (const float2*)(b + off_bhq);
     d.dev.tw = (const float2*)(b + off_tw);
     d.dev.gtw = (const float4*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);

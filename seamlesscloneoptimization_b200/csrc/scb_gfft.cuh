@@ -310,4 +310,13 @@ __device__ __noinline__ void gconv_core(const float4* __restrict__ gtw, const fl
     GInv16<LOG2M, C::M / C::R0>::run(gtw, gtid, group, pl);
 }
 
+// First forward pass of a convolution whose operand is already in shared memory (written by other
+// threads of the group: hence the barrier first).  In place: a butterfly rewrites exactly what it read.
+template <int LOG2M>
+SCB_D void gpass_first_from_smem(const float4* __restrict__ gtw, int gtid, int group, const Planes& pl) {
+    using C = GCfg<LOG2M>;
+    group_sync<C::NG>(group, C::G);
+    gpass<LOG2M, C::R0, C::M, false>(gtw, gtid, SmemIn{pl}, SmemOut{pl});
+}
+
 }  // namespace scb

@@ -31,6 +31,7 @@ struct LenTabDev {
     int n, log2m, lowk;
     const float2* chirp;
     const float2* bhat_t;
+    const float2* bhat_q;  // quad mode (two real lines per sequence): spectrum of conj chirp over [-2n, n-1]; null when 3n > M
     const float2* tw;
     const float4* gtw;  // per-pass twiddle tables of the group engine (scb_gfft.cuh)
     const double* sinlow;

@@ -222,4 +222,187 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_inv3_kernel(RowsInv3Param
     gpass<LOG2M, C::R0, C::M, true>(g.gtw, g.gtid, SmemIn{g.pl}, store);
 }
 
+
+// =============================================================================================
+// Quad variants: TWO real lines per complex sequence (so four lines per packed pair, twelve per CTA).
+//
+// With z = x_a + i x_b the chirp-z sum  T[k] = sum_j z[j] e^{i pi j k / N}  holds both sine transforms:
+//     S_a[k] = (Im T[k] - Im T[-k]) / 2,      S_b[k] = (Re T[-k] - Re T[k]) / 2,
+// i.e. with d = y[k] - y[M-k] (y = the circular convolution, T[+-k] = c[k] y[+-k]):
+//     S_a[k] = Im(c[k] d) / 2,                S_b[k] = -Re(c[k] d) / 2.
+// Outputs are needed for k in [-n, n] and the kernel h[m] = conj(c[m]) for m in [-2n, n-1], so the circular
+// length must be >= 3n instead of 2n-1.  Whenever the power of two chosen for 2n-1 also covers 3n (41 % of all
+// line lengths, e.g. n = 1339 or 1199 or 659 -> M = 4096 / 4096 / 2048) the same FFTs carry twice the lines:
+// half the convolutions per image for one extra shared-memory round trip (y[k] and y[M-k] live in different
+// butterflies of the last pass, so that pass writes shared memory and a short combine loop follows).
+// =============================================================================================
+template <int LOG2M>
+struct QuadIds {
+    int gtid, group, ch, l0, nl;  // nl = valid lines of this quad (1..4)
+    Planes pl;
+    const float4* gtw;
+};
+
+template <int LOG2M>
+SCB_D QuadIds<LOG2M> quad_ids(float2* smem, int first_line, int line_end, const float4* __restrict__ gtw_global) {
+    using C = GCfg<LOG2M>;
+    QuadIds<LOG2M> g;
+    const int tid = threadIdx.x;
+    g.group = (C::NG == 1) ? 0 : tid / C::G;
+    g.gtid = tid - g.group * C::G;
+    g.ch = (C::NG == 1) ? (int)blockIdx.y : g.group;
+    g.l0 = first_line + 4 * (int)blockIdx.x;
+    g.nl = min(4, line_end - g.l0);
+    g.pl.re = smem + (size_t)g.group * 2 * C::PADDED;
+    g.pl.im = g.pl.re + C::PADDED;
+    g.gtw = gtw_global;
+    return g;
+}
+
+// (a0 + i a1) c[j] in lane a, (a2 + i a3) c[j] in lane b
+SCB_D P4 quad_pack(float2 ch, float a0, float a1, float a2, float a3) { return pmul(P4{make_float2(a0, a2), make_float2(a1, a3)}, ch.x, ch.y); }
+// c[k] (y[k] - y[M-k]):  .im = 2 S of lines 0 / 2,  -.re = 2 S of lines 1 / 3
+template <int LOG2M>
+SCB_D P4 quad_unpack(const Planes& pl, float2 ch, int k) {
+    const int pk = padi(k), pm = padi(GCfg<LOG2M>::M - k);
+    return pmul(psub(P4{pl.re[pk], pl.im[pk]}, P4{pl.re[pm], pl.im[pm]}), ch.x, ch.y);
+}
+
+// ---- pass A, four rows per group ----
+template <int LOG2M>
+__global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_fwd4_kernel(RowsFwd3Params pp) {
+    using C = GCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, smem);
+    const RowsFwdParams& p = pp.base;
+    const QuadIds<LOG2M> g = quad_ids<LOG2M>(smem, p.y0, pp.y_end, pp.gtw);
+    const int n = p.nx, c = g.ch, nl = g.nl;
+    const float* r0 = p.rhs_in + ((size_t)c * p.ny + g.l0) * p.rhs_pitch;
+    auto load = [&](int j) -> P4 {
+        if (j < 1 || j > n) return p4_zero();
+        float a[4];
+        SCB_UNROLL
+        for (int i = 0; i < 4; ++i) a[i] = (i < nl) ? __ldg(r0 + (size_t)i * p.rhs_pitch + (j - 1)) : 0.f;
+        return quad_pack(__ldg(p.tx.chirp + j), a[0], a[1], a[2], a[3]);
+    };
+    gpass<LOG2M, C::R0, C::M, false>(g.gtw, g.gtid, load, SmemOut{g.pl});
+    gconv_core<LOG2M>(g.gtw, p.tx.bhat_q, g.gtid, g.group, g.pl);
+    gpass<LOG2M, C::R0, C::M, true>(g.gtw, g.gtid, SmemIn{g.pl}, SmemOut{g.pl});
+    group_sync<C::NG>(g.group, C::G);
+    for (int k = 1 + g.gtid; k <= n; k += C::G) {
+        const P4 t = quad_unpack<LOG2M>(g.pl, __ldg(p.tx.chirp + k), k);
+        float* o = p.At + ((size_t)c * p.nx + (k - 1)) * p.ny + g.l0;
+        // OpenCV: Im of the odd-extension FFT = -2 S
+        o[0] = -t.im.x;
+        if (nl > 1) o[1] = t.re.x;
+        if (nl > 2) o[2] = -t.im.y;
+        if (nl > 3) o[3] = t.re.y;
+    }
+}
+
+// ---- pass B, four columns per group ----
+template <int LOG2M>
+__global__ void __launch_bounds__(GCfg<LOG2M>::T) cols4_kernel(Cols3Params pp) {
+    using C = GCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, smem);
+    const ColsParams& p = pp.base;
+    const QuadIds<LOG2M> g = quad_ids<LOG2M>(smem, p.x0, pp.x_end, pp.gtw);
+    const int n = p.ny, c = g.ch, nl = g.nl, k0 = g.l0;
+    const float* in0 = p.At + ((size_t)c * p.nx + k0) * p.ny;
+    float fxv[4];
+    SCB_UNROLL
+    for (int i = 0; i < 4; ++i) fxv[i] = (i < nl) ? __ldg(p.fx + k0 + i) : 0.f;
+    auto load = [&](int j) -> P4 {
+        if (j < 1 || j > n) return p4_zero();
+        float a[4];
+        SCB_UNROLL
+        for (int i = 0; i < 4; ++i) a[i] = (i < nl) ? __ldg(in0 + (size_t)i * p.ny + (j - 1)) : 0.f;
+        return quad_pack(__ldg(p.ty.chirp + j), a[0], a[1], a[2], a[3]);
+    };
+    gpass<LOG2M, C::R0, C::M, false>(g.gtw, g.gtid, load, SmemOut{g.pl});
+    gconv_core<LOG2M>(g.gtw, p.ty.bhat_q, g.gtid, g.group, g.pl);
+    gpass<LOG2M, C::R0, C::M, true>(g.gtw, g.gtid, SmemIn{g.pl}, SmemOut{g.pl});
+    group_sync<C::NG>(g.group, C::G);
+    // bridge: spectrum of the four columns -> refinement -> / eigenvalues -> operand of the inverse transform, in place.
+    // Position k is read and rewritten, position M-k read and zeroed, by the same thread: no hazard.
+    for (int pos = g.gtid; pos < C::M; pos += C::G) {
+        if (pos >= 1 && pos <= n) {
+            const int k = pos;
+            const float2 ch = __ldg(p.ty.chirp + k);
+            const P4 t = quad_unpack<LOG2M>(g.pl, ch, k);
+            float s[4] = {-t.im.x, t.re.x, -t.im.y, t.re.y};  // -2 S: OpenCV's unnormalised forward transform
+            const float fy = __ldg(p.fy + (k - 1));
+            float q[4];
+            SCB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                q[i] = 0.f;
+                if (i < nl) {
+                    if (p.lowspec && (k - 1) < p.lowky && k0 + i < p.lowkx) s[i] = __ldg(p.lowspec + ((size_t)c * p.lowkx + k0 + i) * p.lowky + (k - 1));
+                    if (p.spec_dump) p.spec_dump[((size_t)c * p.nx + k0 + i) * p.ny + (k - 1)] = s[i];
+                    // OpenCV: res /= (filter_X[i] + filter_Y[j] - 4), left to right in float32
+                    q[i] = __fdiv_rn(s[i], __fsub_rn(__fadd_rn(fxv[i], fy), 4.0f));
+                }
+            }
+            const P4 z = quad_pack(ch, q[0], q[1], q[2], q[3]);
+            const int pk = padi(k), pm = padi(C::M - k);
+            g.pl.re[pk] = z.re;
+            g.pl.im[pk] = z.im;
+            g.pl.re[pm] = make_float2(0.f, 0.f);
+            g.pl.im[pm] = make_float2(0.f, 0.f);
+        } else if (pos == 0 || (pos > n && pos < C::M - n)) {
+            const int pz = padi(pos);
+            g.pl.re[pz] = make_float2(0.f, 0.f);
+            g.pl.im[pz] = make_float2(0.f, 0.f);
+        }
+    }
+    // (gconv_core opens with the group barrier)
+    gpass_first_from_smem<LOG2M>(g.gtw, g.gtid, g.group, g.pl);
+    gconv_core<LOG2M>(g.gtw, p.ty.bhat_q, g.gtid, g.group, g.pl);
+    gpass<LOG2M, C::R0, C::M, true>(g.gtw, g.gtid, SmemIn{g.pl}, SmemOut{g.pl});
+    group_sync<C::NG>(g.group, C::G);
+    const float hs = 0.5f * p.inv_scale;
+    for (int k = 1 + g.gtid; k <= n; k += C::G) {
+        const P4 t = quad_unpack<LOG2M>(g.pl, __ldg(p.ty.chirp + k), k);
+        float* o = p.Ct + ((size_t)c * p.ny + (k - 1)) * p.nx + k0;
+        o[0] = t.im.x * hs;
+        if (nl > 1) o[1] = -t.re.x * hs;
+        if (nl > 2) o[2] = t.im.y * hs;
+        if (nl > 3) o[3] = -t.re.y * hs;
+    }
+}
+
+// ---- pass C, four rows per group ----
+template <int LOG2M>
+__global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_inv4_kernel(RowsInv3Params pp) {
+    using C = GCfg<LOG2M>;
+    SCB_DYN_SMEM(float2, smem);
+    const RowsInvParams& p = pp.base;
+    const QuadIds<LOG2M> g = quad_ids<LOG2M>(smem, p.y0, pp.y_end, pp.gtw);
+    const int n = p.nx, c = g.ch, nl = g.nl, y0 = g.l0;
+    const float* in0 = p.Ct + ((size_t)c * p.ny + y0) * p.nx;
+    auto load = [&](int j) -> P4 {
+        if (j < 1 || j > n) return p4_zero();
+        float a[4];
+        SCB_UNROLL
+        for (int i = 0; i < 4; ++i) a[i] = (i < nl) ? __ldg(in0 + (size_t)i * p.nx + (j - 1)) : 0.f;
+        return quad_pack(__ldg(p.tx.chirp + j), a[0], a[1], a[2], a[3]);
+    };
+    gpass<LOG2M, C::R0, C::M, false>(g.gtw, g.gtid, load, SmemOut{g.pl});
+    gconv_core<LOG2M>(g.gtw, p.tx.bhat_q, g.gtid, g.group, g.pl);
+    gpass<LOG2M, C::R0, C::M, true>(g.gtw, g.gtid, SmemIn{g.pl}, SmemOut{g.pl});
+    group_sync<C::NG>(g.group, C::G);
+    const float hs = 0.5f * p.inv_scale;
+    for (int k = 1 + g.gtid; k <= n; k += C::G) {
+        const P4 t = quad_unpack<LOG2M>(g.pl, __ldg(p.tx.chirp + k), k);
+        const float u[4] = {t.im.x * hs, -t.re.x * hs, t.im.y * hs, -t.re.y * hs};
+        unsigned char* o = p.out + (long long)y0 * p.out_pitch + 3 * (k - 1) + c;
+        SCB_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            if (i < nl) {
+                if (p.u_dump) p.u_dump[((size_t)c * p.ny + y0 + i) * p.nx + (k - 1)] = u[i];
+                o[(long long)i * p.out_pitch] = compose_u8(u[i]);
+            }
+        }
+    }
+}
+
 }  // namespace scb

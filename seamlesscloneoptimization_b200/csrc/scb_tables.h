@@ -25,6 +25,7 @@ struct HostLenTab {
     int n = 0, log2m = 0, lowk = 0;
     std::vector<HostF2> chirp;   // n+1 : exp(+i pi j^2 / 2N)
     std::vector<HostF2> bhat_t;  // M   : permuted spectrum of conj chirp, / M, operand-major
+    std::vector<HostF2> bhat_q;  // M   : the same over the support [-2n, n-1] (quad mode, scb_kernels3.cuh); empty when 3n > M
     std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)                       (scalar engine)
     std::vector<float> gtw;      // per-pass [row][i] float4 (re_q, re_q+1, im_q, im_q+1), q = 1,3,5,7  (group engine, scb_gfft.cuh)
     std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
@@ -36,6 +37,9 @@ inline int choose_log2m(int n) {
     while ((1 << l) < need) ++l;
     return l;  // caller checks against kMaxLog2M
 }
+
+// quad mode packs two real lines into one complex sequence; it needs outputs k in [-n, n], hence M >= 3n
+inline bool quad_ok(int n) { return n >= 2 && 3LL * n <= (1LL << choose_log2m(n)); }
 
 inline int first_radix(int log2m) { return (log2m % 4 == 0) ? 16 : (1 << (log2m % 4)); }
 
@@ -94,12 +98,27 @@ inline HostLenTab build_len_tab(int n) {
         if (m) b[M - m] = std::conj(c[m]);
     }
     host_dif_forward(b, t.log2m);
-    t.bhat_t.resize(M);
-    for (int blk = 0; blk < M / 16; ++blk)
-        for (int q = 0; q < 16; ++q) {
-            cd v = b[16 * blk + q] / (double)M;
-            t.bhat_t[(size_t)q * (M / 16) + blk] = HostF2{(float)v.real(), (float)v.imag()};
-        }
+    auto permute = [&](const std::vector<cd>& spec, std::vector<HostF2>& out) {
+        out.resize(M);
+        for (int blk = 0; blk < M / 16; ++blk)
+            for (int q = 0; q < 16; ++q) {
+                cd v = spec[16 * blk + q] / (double)M;
+                out[(size_t)q * (M / 16) + blk] = HostF2{(float)v.real(), (float)v.imag()};
+            }
+    };
+    permute(b, t.bhat_t);
+    if (quad_ok(n)) {
+        std::vector<cd> bq(M, cd(0, 0));
+        auto chirp_at = [&](long long m) {  // c[m] = exp(+i pi m^2 / 2N), even in m, for |m| up to 2n
+            long long ph = (m * m) % (4 * N);
+            double ang = PI * (double)ph / (2.0 * (double)N);
+            return cd(std::cos(ang), std::sin(ang));
+        };
+        for (long long m = 0; m <= n - 1; ++m) bq[m] = std::conj(chirp_at(m));
+        for (long long m = 1; m <= 2LL * n; ++m) bq[M - m] = std::conj(chirp_at(m));
+        host_dif_forward(bq, t.log2m);
+        permute(bq, t.bhat_q);
+    }
     t.tw.resize(M);
     for (int k = 0; k < M; ++k) {
         double ang = 2.0 * PI * (double)k / (double)M;

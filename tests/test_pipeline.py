@@ -110,7 +110,8 @@ def test_configs_vs_oracle(ctx, cfg, seed):
 
 
 # every convolution length class (LOG2M) and every first-radix variant, thin ROIs to stay cheap
-SIZES_EMU = [(3, 3), (4, 7), (10, 18), (19, 35), (66, 40), (131, 20), (20, 259), (515, 12), (12, 1027)]
+# (44, 45): n = 42 / 43 straddles the quad-mode threshold 3n <= M = 128 (two real lines per complex sequence, scb_kernels3.cuh)
+SIZES_EMU = [(3, 3), (4, 7), (10, 18), (19, 35), (44, 45), (66, 40), (131, 20), (20, 259), (515, 12), (12, 1027)]
 SIZES_GPU_ONLY = [(2051, 12), (12, 2052), (4099, 10), (8194, 9), (9, 8194), (8194, 3)]
 
 
