@@ -263,12 +263,15 @@ template <int LOG2M>
 static dim3 quad_grid(int nlines) { return dim3((nlines + 3) / 4, GCfg<LOG2M>::NG == 1 ? 3 : 1); }
 // quad mode (two real lines per complex sequence) whenever the length's table carries the extended chirp spectrum;
 // SCB_QUAD=0 disables it (A/B checks)
-static bool use_quad(const LenTabDev& t) {
+// Measured on B200 (profiles/r1_quad_sweep.txt): the row passes gain 1.0-1.7x at every length; the column pass, whose
+// in-register bridge between its two convolutions becomes two extra shared-memory round trips, gains 1.3-1.5x at
+// M >= 4096 but loses ~10 % at M <= 2048 -- so columns use quad mode from 4096 up.
+static bool use_quad(const LenTabDev& t, bool cols = false) {
     static const bool off = [] {
         const char* e = std::getenv("SCB_QUAD");
         return e && std::strcmp(e, "0") == 0;
     }();
-    return t.bhat_q != nullptr && !off;
+    return t.bhat_q != nullptr && !off && (!cols || t.log2m >= 12);
 }
 
 template <int LOG2M>
@@ -291,7 +294,7 @@ static void launch_cols_t(cudaStream_t stream, int nlines, const ColsParams& p) 
     if constexpr (LOG2M <= 13) {
         if (!use_scalar_engine(LOG2M)) {
             Cols3Params pp{p, p.ty.gtw, p.x0 + nlines};
-            if (use_quad(p.ty))
+            if (use_quad(p.ty, true))
                 SCB_LAUNCH(cols4_kernel<LOG2M>, quad_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
             else
                 SCB_LAUNCH(cols3_kernel<LOG2M>, group_grid<LOG2M>(nlines), dim3(GCfg<LOG2M>::T), GCfg<LOG2M>::SMEM, stream, pp);
