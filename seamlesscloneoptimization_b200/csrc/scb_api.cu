@@ -45,11 +45,16 @@ struct DevLenTab {
 // refinement, and a grow-only workspace arena.  Lane 0 is the context's main stream (the only one the
 // single-job entry points use); scb_clone_batch spreads independent jobs over all lanes so that one
 // job's transfers overlap another's kernels and small jobs share the 148 SMs.
+static const int kMaxBands = 4;
+
 struct Lane {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;              // low-frequency refinement runs here, beside pass A
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy = nullptr;              // HOST calls: banded H2D / D2H pipelined against the row passes
+    cudaEvent_t ev_copy = nullptr;            // DEVICE calls: dst -> blend copy done (runs on `side`, beside the passes)
+    cudaEvent_t ev_band[kMaxBands] = {}, ev_out[kMaxBands] = {};
     char* ws = nullptr;
     size_t ws_cap = 0;
     uint64_t ws_epoch = 0;                    // bumps when the arena moves (captured graphs hold its addresses)
@@ -157,6 +162,12 @@ static cudaError_t lane_create(Lane* l, cudaStream_t adopt) {
     if ((e = cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithFlags(&l->copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&l->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (int i = 0; i < kMaxBands; ++i) {
+        if ((e = cudaEventCreateWithFlags(&l->ev_band[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        if ((e = cudaEventCreateWithFlags(&l->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
     return cudaSuccess;
 }
 
@@ -167,8 +178,17 @@ static void lane_destroy(Lane* l) {
         cudaStreamDestroy(l->side);
     }
     if (l->ws) cudaFree(l->ws);
+    if (l->copy) {
+        cudaStreamSynchronize(l->copy);
+        cudaStreamDestroy(l->copy);
+    }
     if (l->ev_fork) cudaEventDestroy(l->ev_fork);
     if (l->ev_join) cudaEventDestroy(l->ev_join);
+    if (l->ev_copy) cudaEventDestroy(l->ev_copy);
+    for (int i = 0; i < kMaxBands; ++i) {
+        if (l->ev_band[i]) cudaEventDestroy(l->ev_band[i]);
+        if (l->ev_out[i]) cudaEventDestroy(l->ev_out[i]);
+    }
     if (l->own_stream && l->stream) cudaStreamDestroy(l->stream);
     *l = Lane();
 }
@@ -1218,56 +1238,116 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     unsigned char* out;
     long long out_pitch;
     tm.mark(ST_BEGIN);
+    Lane* L = p->lane;
+    cudaStream_t ms = L->stream;
+    // HOST calls on the FFT engine move the ROI in row bands on a copy stream so that the upload of band b+1 runs
+    // under the stencil + row transform of band b, and the download of band b under the inverse rows of band b+1.
+    int nb = 1;
+    if (host && !tm.on && !p->use_tc && !p->debug) {
+        const size_t roi_bytes = (size_t)3 * g.w * g.h;
+        nb = (int)(roi_bytes >> 21);  // ~2 MiB of ROI per band at least
+        if (const char* e = std::getenv("SCB_BANDS")) nb = std::atoi(e);  // tests force banding on small ROIs
+        if (nb > kMaxBands) nb = kMaxBands;
+        if (nb > g.ny / 4) nb = g.ny / 4;
+        if (nb < 1) nb = 1;
+    }
+    int yb[kMaxBands + 1];
+    for (int b = 0; b <= nb; ++b) yb[b] = (b == nb) ? g.ny : (int)(((long long)g.ny * b / nb) & ~3LL);  // multiples of 4: whole quads
+    const bool side_copy = !host && copy_dst && !tm.on;
     if (host) {
-        // ROI-only transfers (the reference uploads the whole dst every call: seamlessClone_imp.cpp:419-421)
-        SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, p->lane->stream));
-        SCB_CUDA(c, cudaMemcpy2DAsync(w.stS, (size_t)w.pS, sROI, (size_t)src->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, p->lane->stream));
         st = make_stencil(p, w.stD, w.pD, w.stS, w.pS);
         out = w.stO;
         out_pitch = w.pO;
+        if (nb == 1) {
+            // ROI-only transfers (the reference uploads the whole dst every call: seamlessClone_imp.cpp:419-421)
+            SCB_CUDA(c, cudaMemcpy2DAsync(w.stD, (size_t)w.pD, dROI, (size_t)dst->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, ms));
+            SCB_CUDA(c, cudaMemcpy2DAsync(w.stS, (size_t)w.pS, sROI, (size_t)src->stride, (size_t)3 * g.w, (size_t)g.h, cudaMemcpyHostToDevice, ms));
+        } else {
+            SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));  // the staging buffers are free once earlier work on this lane is done
+            SCB_CUDA(c, cudaStreamWaitEvent(L->copy, L->ev_fork, 0));
+            int r0 = 0;
+            for (int b = 0; b < nb; ++b) {
+                const int r1 = (b == nb - 1) ? g.h : yb[b + 1] + 2;  // interior rows [yb, yb1) read ROI rows [yb, yb1 + 2)
+                SCB_CUDA(c, cudaMemcpy2DAsync(w.stD + (size_t)r0 * w.pD, (size_t)w.pD, dROI + (size_t)r0 * dst->stride, (size_t)dst->stride, (size_t)3 * g.w, (size_t)(r1 - r0),
+                                              cudaMemcpyHostToDevice, L->copy));
+                SCB_CUDA(c, cudaMemcpy2DAsync(w.stS + (size_t)r0 * w.pS, (size_t)w.pS, sROI + (size_t)r0 * src->stride, (size_t)src->stride, (size_t)3 * g.w, (size_t)(r1 - r0),
+                                              cudaMemcpyHostToDevice, L->copy));
+                SCB_CUDA(c, cudaEventRecord(L->ev_band[b], L->copy));
+                r0 = r1;
+            }
+        }
     } else {
-        if (copy_dst) SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, p->lane->stream));
+        if (copy_dst && !side_copy) SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, ms));
         st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
         out = bInt;
         out_pitch = blend->stride;
     }
     if (p->debug) {
-        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, p->lane->stream, st, p->dbg_vx, p->dbg_vy);
+        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, ms, st, p->dbg_vx, p->dbg_vy);
         c->launches++;
     }
     tm.mark(ST_IN);
-    run_rhs(p, st, w.G, w.gp, 0, g.ny);
+    if (nb == 1) {
+        run_rhs(p, st, w.G, w.gp, 0, g.ny);
+    } else {
+        for (int b = 0; b < nb; ++b) {
+            SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
+            run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1]);
+            if (b + 1 < nb) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1]);  // the last band's rows follow the refinement fork
+        }
+    }
     tm.mark(ST_RHS);
     if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, p->lane->stream);
-        run_lowfreq_cols(p, w.R, w.lowspec, p->lane->stream);
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, ms);
+        run_lowfreq_cols(p, w.R, w.lowspec, ms);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
-        SCB_CUDA(c, cudaEventRecord(p->lane->ev_fork, p->lane->stream));
-        SCB_CUDA(c, cudaStreamWaitEvent(p->lane->side, p->lane->ev_fork, 0));
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, p->lane->side);
-        run_lowfreq_cols(p, w.R, w.lowspec, p->lane->side);
-        SCB_CUDA(c, cudaEventRecord(p->lane->ev_join, p->lane->side));
+        SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
+        SCB_CUDA(c, cudaStreamWaitEvent(L->side, L->ev_fork, 0));
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, L->side);
+        run_lowfreq_cols(p, w.R, w.lowspec, L->side);
+        SCB_CUDA(c, cudaEventRecord(L->ev_join, L->side));
+        if (side_copy) {  // blend = dst.copy() rides along on the side stream; only the compose pass has to wait for it
+            if ((size_t)blend->stride == row_bytes && (size_t)dst->stride == row_bytes)
+                SCB_CUDA(c, cudaMemcpyAsync(blend->data, dst->data, row_bytes * (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, L->side));
+            else
+                SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, L->side));
+            SCB_CUDA(c, cudaEventRecord(L->ev_copy, L->side));
+        }
     }
     tm.mark(ST_LOW);
     if (p->use_tc) {
+        if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
-        run_rows_fwd(p, st, w.G, w.gp, w.At, 0, g.ny);
-        if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(p->lane->stream, p->lane->ev_join, 0));
+        run_rows_fwd(p, st, w.G, w.gp, w.At, yb[nb - 1], g.ny);
+        if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
         run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
-        run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+        if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
+        if (nb == 1) {
+            run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+        } else {
+            for (int b = 0; b < nb; ++b) {
+                run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
+                SCB_CUDA(c, cudaEventRecord(L->ev_out[b], ms));
+                SCB_CUDA(c, cudaStreamWaitEvent(L->copy, L->ev_out[b], 0));
+                SCB_CUDA(c, cudaMemcpy2DAsync(bInt + (size_t)yb[b] * blend->stride, (size_t)blend->stride, w.stO + (size_t)yb[b] * w.pO, (size_t)w.pO, (size_t)3 * g.nx,
+                                              (size_t)(yb[b + 1] - yb[b]), cudaMemcpyDeviceToHost, L->copy));
+            }
+            SCB_CUDA(c, cudaEventRecord(L->ev_copy, L->copy));
+            SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));  // a sync of the lane's stream covers the downloads
+        }
         tm.mark(ST_ROWS_INV);
     }
     SCB_CUDA(c, cudaGetLastError());
     if (host) {
         // only the ROI interior comes back; everything else of blend is copied from dst on the host while the GPU works
-        SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, p->lane->stream));
+        if (nb == 1) SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, ms));
         tm.mark(ST_OUT);
         if (!defer_host) {
             if (copy_dst) host_copy_outside(dst, blend, g, host_threads());
-            SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
+            SCB_CUDA(c, cudaStreamSynchronize(ms));
             SCB_CUDA(c, cudaGetLastError());
         }
     } else {

@@ -467,3 +467,17 @@ def test_reference_module_name_shim(be):
         assert mod.SeamlessClone is scb.SeamlessClone
     finally:
         sys.path.remove(compat)
+
+
+def test_banded_host_transfers_equal_single_shot(be, ctx, monkeypatch):
+    """HOST calls move large ROIs in row bands (upload of band b+1 under the row passes of band b).  Forced
+    here on a small ROI: every band count must give the bytes of the single-shot path."""
+    src, dst, mask, p = so.make_config("small", 17)
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    monkeypatch.setenv("SCB_BANDS", "1")
+    ref = plan.execute(src, dst)
+    for nb in (2, 3, 4):
+        monkeypatch.setenv("SCB_BANDS", str(nb))
+        got = plan.execute(src, dst)
+        assert np.array_equal(got, ref), nb
+    plan.close()
