@@ -65,18 +65,21 @@ enum {
     SCB_EXEC_BLEND_PREFILLED = 1 /* blend already holds a copy of dst (or aliases it): write the ROI interior only */
 };
 
-/* transform engines.  FFT: the Bluestein shared-memory FFT engine (default; AUTO resolves to it).  TC: dense
+/* transform engines.  TRI (default; AUTO resolves to it): Bluestein FFT passes along x, and along y the
+ * mathematically identical tridiagonal (Thomas) solve of every spectral column, with the lowest 32 x 32
+ * frequencies in float64 against OpenCV's float32 denominators -- half the transform work of FFT.
+ * FFT: the Bluestein shared-memory FFT engine on both axes (also what the sharded entry points run).  TC: dense
  * sine-basis contraction on the tensor cores (tcgen05, 3xTF32, even/odd fold) for line lengths 16..4096 -- opt-in:
  * its FP32 accumulation error (~1e-5 relative at K ~ 900) is inside the 1e-4 bar for float intermediates but
- * costs exactly-matching bytes at some shapes.  The environment variable SCB_ENGINE=tc|fft sets the default. */
-enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2 };
+ * costs exactly-matching bytes at some shapes.  The environment variable SCB_ENGINE=tri|tc|fft sets the default. */
+enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2, SCB_ENGINE_TRI = 3 };
 
 /* scb_plan_get_intermediate selectors; all float32, planar [3][rows][cols] */
 enum {
     SCB_INT_GRADIENT_X = 0, /* [3][h][w]    blended forward-difference gradient                  */
     SCB_INT_GRADIENT_Y = 1, /* [3][h][w]                                                         */
     SCB_INT_RHS = 2,        /* [3][ny][nx]  divergence minus Dirichlet boundary (OpenCV mod_diff) */
-    SCB_INT_SPECTRUM = 3,   /* [3][nx][ny]  forward 2-D DST, TRANSPOSED, before the division      */
+    SCB_INT_SPECTRUM = 3,   /* [3][nx][ny]  forward 2-D DST, TRANSPOSED, before the division (FFT / TC engines only) */
     SCB_INT_SOLVED = 4,     /* [3][ny][nx]  solved field before clamp / truncation                */
     SCB_INT_ERODED_MASK = 5 /* [1][h][w]    eroded mask as float 0..255                           */
 };
@@ -125,7 +128,7 @@ int scb_plan_create(scb_context* ctx, const scb_image* mask, int mask_mem_kind, 
                     int dst_rows, int dst_cols, int px, int py, scb_plan** out);
 int scb_plan_destroy(scb_plan* plan);
 int scb_plan_geometry(const scb_plan* plan, scb_geometry* out);
-int scb_plan_engine(const scb_plan* plan); /* SCB_ENGINE_FFT or SCB_ENGINE_TC */
+int scb_plan_engine(const scb_plan* plan); /* SCB_ENGINE_TRI, SCB_ENGINE_FFT or SCB_ENGINE_TC */
 /* Asynchronous on the context stream for SCB_MEM_DEVICE; for SCB_MEM_HOST returns when blend is complete. */
 int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags);
 /* Same call with CUDA events between the stages (on the context stream); returns after a stream sync.

@@ -73,7 +73,7 @@ class Context:
         self._check(self.lib.scb_sync(self.handle))
 
     def set_engine(self, engine: int):
-        """DST engine of plans created from now on: capi.ENGINE_AUTO / ENGINE_FFT / ENGINE_TC."""
+        """DST engine of plans created from now on: capi.ENGINE_AUTO / ENGINE_TRI / ENGINE_FFT / ENGINE_TC."""
         self._check(self.lib.scb_set_engine(self.handle, int(engine)))
 
     def tc_selftest(self, n: int, lines: int, transposed: bool = False) -> float:

@@ -24,6 +24,7 @@
 #include "scb_platform.h"
 #include "scb_tables.h"
 #include "scb_tc.cuh"
+#include "scb_tri.cuh"
 
 using namespace scb;
 
@@ -70,8 +71,14 @@ struct DevTcTab {
 #endif
 };
 
+struct DevTriTab {
+    TriTabDev dev{};
+    void* block = nullptr;
+};
+
 struct scb_context {
     int device = 0;
+    std::map<std::pair<int, int>, DevTriTab> tritabs;  // keyed by ROI (w, h): LU factors of the tridiagonal engine
     int engine = SCB_ENGINE_AUTO;
     std::map<int, DevTcTab> tctabs;     // keyed by n (tensor-core engine: split sine bases + tensor maps)
     Lane lanes[kMaxLanes];
@@ -114,6 +121,8 @@ struct scb_plan {
     long long e_pitch = 0;
     LenTabDev tx{}, ty{};
     bool use_tc = false;                // tensor-core dense engine (scb_tc.cuh) instead of the FFT engine
+    bool use_tri = false;               // tridiagonal column solve (scb_tri.cuh) instead of the column FFT pass
+    TriTabDev tri{};
     const DevTcTab *ttx = nullptr, *tty = nullptr;
     const float* fx = nullptr;
     const float* fy = nullptr;
@@ -270,7 +279,7 @@ static cudaError_t configure_one() {
 #define SCB_FOR_LOG2M(X) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
 static cudaError_t configure_all() {
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemBytes);
 #define X(L) if (e == cudaSuccess) e = configure_one<L>();
     SCB_FOR_LOG2M(X)
 #undef X
@@ -385,7 +394,8 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     const size_t off_tw = align_up(off_bhq + h.bhat_q.size() * sizeof(float2), 256);
     const size_t off_ptw = align_up(off_tw + M * sizeof(float2), 256);
     const size_t off_sin = align_up(off_ptw + h.gtw.size() * sizeof(float), 256);
-    const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
+    const size_t off_sinf = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
+    const size_t total = align_up(off_sinf + h.sinfull.size() * sizeof(double), 256);
     std::vector<char> host(total, 0);
     std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
@@ -393,6 +403,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_ptw, h.gtw.data(), h.gtw.size() * sizeof(float));
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
+    std::memcpy(host.data() + off_sinf, h.sinfull.data(), h.sinfull.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
     SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->lanes[0].stream));
@@ -407,6 +418,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.tw = (const float2*)(b + off_tw);
     d.dev.gtw = (const float4*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);
+    d.dev.sinfull = (const double*)(b + off_sinf);
     c->lentabs[n] = d;
     *out = d.dev;
     return SCB_OK;
@@ -469,19 +481,76 @@ static int get_tctab(scb_context* c, int n, const DevTcTab** out) {
     return SCB_OK;
 }
 
-static bool tc_eligible(const scb_context* c, int nx, int ny) {
+static int wanted_engine(const scb_context* c) {
     static const int env_engine = [] {
         const char* e = std::getenv("SCB_ENGINE");
         if (!e) return (int)SCB_ENGINE_AUTO;
         if (std::strcmp(e, "tc") == 0) return (int)SCB_ENGINE_TC;
+        if (std::strcmp(e, "tri") == 0) return (int)SCB_ENGINE_TRI;
         if (std::strcmp(e, "fft") == 0 || std::strcmp(e, "scalar") == 0) return (int)SCB_ENGINE_FFT;
         return (int)SCB_ENGINE_AUTO;
     }();
+    return c->engine != SCB_ENGINE_AUTO ? c->engine : env_engine;
+}
+
+// AUTO resolves to the tridiagonal engine: FFT rows, Thomas columns (scb_tri.cuh).
+static bool tri_eligible(const scb_context* c) {
+    const int want = wanted_engine(c);
+    return want == SCB_ENGINE_AUTO || want == SCB_ENGINE_TRI;
+}
+
+// LU factors m[d][k] of tridiag(-1, 4 - fx[k], -1), built on the device at plan time, cached per ROI (w, h)
+static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
+    const auto key = std::make_pair(w, h);
+    auto it = c->tritabs.find(key);
+    if (it != c->tritabs.end()) {
+        *out = it->second.dev;
+        return SCB_OK;
+    }
+    const int nx = w - 2, ny = h - 2;
+    const std::vector<double> th = build_theta(build_filter(w));
+    const int pm = (int)align_up((size_t)nx, 4);
+    const size_t off_m32 = 0;
+    const size_t off_m64 = align_up(off_m32 + (size_t)ny * pm * sizeof(float), 256);
+    const size_t off_th = align_up(off_m64 + (size_t)ny * kTriLowK * sizeof(double), 256);
+    const size_t total = align_up(off_th + (size_t)nx * sizeof(double), 256);
+    DevTriTab d;
+    SCB_CUDA(c, cudaMalloc(&d.block, total));
+    char* b = (char*)d.block;
+    cudaStream_t s = c->lanes[0].stream;
+    SCB_CUDA(c, cudaMemsetAsync(b + off_m64, 0, (size_t)ny * kTriLowK * sizeof(double), s));
+    SCB_CUDA(c, cudaMemcpyAsync(b + off_th, th.data(), (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    TriTableParams tp;
+    tp.theta = (const double*)(b + off_th);
+    tp.nx = nx;
+    tp.ny = ny;
+    tp.pm = pm;
+    tp.m32 = (float*)(b + off_m32);
+    tp.m64 = (double*)(b + off_m64);
+    {
+        const long long total_e = (long long)ny * pm;
+        long long blocks = (total_e + 255) / 256;
+        if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
+        SCB_LAUNCH(tri_table_kernel, dim3((unsigned)blocks), dim3(256), 0, s, tp);
+        c->launches++;
+    }
+    SCB_CUDA(c, cudaStreamSynchronize(s));  // `th` dies at scope exit; also publishes the table to every lane
+    SCB_CUDA(c, cudaGetLastError());
+    d.dev.m32 = tp.m32;
+    d.dev.pm = pm;
+    d.dev.m64 = tp.m64;
+    d.dev.theta = tp.theta;
+    c->tritabs[key] = d;
+    *out = d.dev;
+    return SCB_OK;
+}
+
+static bool tc_eligible(const scb_context* c, int nx, int ny) {
     // AUTO resolves to the FFT engine: FP32 accumulation inside the tensor core truncates at every MMA step,
     // which leaves ~1e-5 relative error after ~340 steps (K ~ 900) -- inside the 1e-4 bar for the float
     // intermediates but enough to cost 0.2 % of exactly matching bytes at some shapes.
     // The tensor-core engine is therefore opt-in (scb_set_engine / SCB_ENGINE=tc) until its accumulation is chunked.
-    const int want = c->engine != SCB_ENGINE_AUTO ? c->engine : env_engine;
+    const int want = wanted_engine(c);
     if (want != SCB_ENGINE_TC) return false;
     return nx >= kTcMinN && ny >= kTcMinN && nx <= kTcMaxN && ny <= kTcMaxN;
 }
@@ -563,6 +632,7 @@ extern "C" int scb_destroy(scb_context* c) {
     for (auto& kv : c->lentabs) cudaFree(kv.second.block);
     for (auto& kv : c->filters) cudaFree(kv.second);
     for (auto& kv : c->tctabs) cudaFree(kv.second.block);
+    for (auto& kv : c->tritabs) cudaFree(kv.second.block);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
     delete c;
@@ -579,7 +649,7 @@ extern "C" int scb_sync(scb_context* c) {
 
 extern "C" int scb_set_engine(scb_context* c, int engine) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
-    if (engine != SCB_ENGINE_AUTO && engine != SCB_ENGINE_FFT && engine != SCB_ENGINE_TC) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_engine: unknown engine");
+    if (engine != SCB_ENGINE_AUTO && engine != SCB_ENGINE_FFT && engine != SCB_ENGINE_TC && engine != SCB_ENGINE_TRI) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_engine: unknown engine");
     c->engine = engine;
     return SCB_OK;
 }
@@ -762,6 +832,11 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
         scb_plan_destroy(p);
         return rc;
     }
+    p->use_tri = !p->use_tc && tri_eligible(c);
+    if (p->use_tri && (rc = get_tritab(c, g.w, g.h, &p->tri))) {
+        scb_plan_destroy(p);
+        return rc;
+    }
     return SCB_OK;
 }
 
@@ -794,7 +869,7 @@ extern "C" int scb_plan_geometry(const scb_plan* p, scb_geometry* out) {
 }
 extern "C" int scb_plan_engine(const scb_plan* p) {
     if (!p) return -1;
-    return p->use_tc ? SCB_ENGINE_TC : SCB_ENGINE_FFT;
+    return p->use_tc ? SCB_ENGINE_TC : (p->use_tri ? SCB_ENGINE_TRI : SCB_ENGINE_FFT);
 }
 extern "C" int scb_plan_lowk(const scb_plan* p, int* lowkx, int* lowky) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
@@ -834,7 +909,11 @@ extern "C" int scb_plan_get_intermediate(scb_plan* p, int which, float* out_host
         case SCB_INT_GRADIENT_X: src = p->dbg_vx; n = roi; break;
         case SCB_INT_GRADIENT_Y: src = p->dbg_vy; n = roi; break;
         case SCB_INT_RHS: src = p->dbg_rhs; n = in; break;
-        case SCB_INT_SPECTRUM: src = p->dbg_spec; n = in; break;
+        case SCB_INT_SPECTRUM:
+            if (p->use_tri) return fail(c, SCB_ERR_UNSUPPORTED, "scb_plan_get_intermediate: the tridiagonal engine never forms the 2-D spectrum (use SCB_ENGINE_FFT)");
+            src = p->dbg_spec;
+            n = in;
+            break;
         case SCB_INT_SOLVED: src = p->dbg_u; n = in; break;
         case SCB_INT_ERODED_MASK: {
             n = (size_t)p->g.w * p->g.h;
@@ -921,6 +1000,7 @@ struct Workspace {
     int gp = 0;
     int tpx = 0, tpy = 0;  // tensor-core engine: line pitches of the [..][nx] and [..][ny] orientations
     double* R = nullptr;
+    double* Y64 = nullptr;  // tridiagonal engine: float64 columns k < kTriLowK
 };
 
 static int carve(scb_plan* p, bool host, Workspace* w) {
@@ -947,6 +1027,7 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     const size_t oG = take((size_t)3 * g.ny * w->gp * sizeof(float));
     const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
+    const size_t oY64 = take(p->use_tri ? (size_t)3 * g.ny * kTriLowK * sizeof(double) : 0);
     size_t oD = 0, oS = 0, oO = 0;
     if (host) {
         oD = take((size_t)w->pD * g.h);
@@ -960,6 +1041,7 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     w->G = (float*)(p->lane->ws + oG);
     w->R = (double*)(p->lane->ws + oR);
     w->lowspec = (float*)(p->lane->ws + oLow);
+    w->Y64 = (double*)(p->lane->ws + oY64);
     if (host) {
         w->stD = (unsigned char*)(p->lane->ws + oD);
         w->stS = (unsigned char*)(p->lane->ws + oS);
@@ -1028,7 +1110,7 @@ static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec, cudaS
     SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, stream, lc);
     c->launches++;
 }
-static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1) {
+static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1, bool natural = false) {
     RowsFwdParams a;
     a.st = st;
     a.tx = p->tx;
@@ -1039,6 +1121,7 @@ static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int 
     a.rhs_in = G;
     a.rhs_pitch = gp;
     a.y0 = y0;
+    a.natural = natural ? 1 : 0;
     launch_rows_fwd(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, a);
 }
 static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
@@ -1058,6 +1141,39 @@ static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowsp
     b.x0 = x0;
     launch_cols(p->ctx, p->lane->stream, p->g.log2m_y, x1 - x0, b);
 }
+// Tridiagonal engine, pass B: Thomas solve of every spectral column (A [3][ny][nx] -> Ct [3][ny][nx]), then the
+// float64 low-frequency block with OpenCV's float32 denominators (scb_tri.cuh).
+static void run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64) {
+    scb_context* c = p->ctx;
+    const scb_geometry& g = p->g;
+    TriSolveParams t;
+    t.tab = p->tri;
+    t.nx = g.nx;
+    t.ny = g.ny;
+    t.A = A;
+    t.Ct = Ct;
+    t.R = R;
+    t.lowkx = p->lowkx;
+    t.Y64 = Y64;
+    t.x0 = 0;
+    t.x1 = g.nx;
+    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(2 * kTriCols), kTriSmemBytes, p->lane->stream, t);
+    c->launches++;
+    TriLowParams l;
+    l.nx = g.nx;
+    l.ny = g.ny;
+    l.A = A;
+    l.R = R;
+    l.lowkx = p->lowkx;
+    l.Y64 = Y64;
+    l.sinfull = p->ty.sinfull;
+    l.fx = p->fx;
+    l.fy = p->fy;
+    l.Ct = Ct;
+    SCB_LAUNCH(tri_lowcorr_kernel, dim3(g.nx < kTriLowK ? g.nx : kTriLowK, 3), dim3(kTriLowThreads), 0, p->lane->stream, l);
+    c->launches++;
+}
+
 static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1) {
     RowsInvParams r;
     r.tx = p->tx;
@@ -1293,18 +1409,18 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         for (int b = 0; b < nb; ++b) {
             SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
             run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1]);
-            if (b + 1 < nb) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1]);  // the last band's rows follow the refinement fork
+            if (b + 1 < nb) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
         }
     }
     tm.mark(ST_RHS);
     if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
         run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, ms);
-        run_lowfreq_cols(p, w.R, w.lowspec, ms);
+        if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, ms);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
         SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
         SCB_CUDA(c, cudaStreamWaitEvent(L->side, L->ev_fork, 0));
         run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, L->side);
-        run_lowfreq_cols(p, w.R, w.lowspec, L->side);
+        if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, L->side);
         SCB_CUDA(c, cudaEventRecord(L->ev_join, L->side));
         if (side_copy) {  // blend = dst.copy() rides along on the side stream; only the compose pass has to wait for it
             if ((size_t)blend->stride == row_bytes && (size_t)dst->stride == row_bytes)
@@ -1319,10 +1435,13 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
-        run_rows_fwd(p, st, w.G, w.gp, w.At, yb[nb - 1], g.ny);
+        run_rows_fwd(p, st, w.G, w.gp, w.At, yb[nb - 1], g.ny, p->use_tri);
         if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
-        run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
+        if (p->use_tri)
+            run_tri(p, w.At, w.Ct, w.R, w.Y64);
+        else
+            run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if (nb == 1) {

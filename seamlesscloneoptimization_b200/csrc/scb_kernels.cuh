@@ -35,6 +35,7 @@ struct LenTabDev {
     const float2* tw;
     const float4* gtw;  // per-pass twiddle tables of the group engine (scb_gfft.cuh)
     const double* sinlow;
+    const double* sinfull;  // [2N] sin(pi i / N)
 };
 
 struct StencilSrc {
@@ -248,6 +249,7 @@ struct RowsFwdParams {
     const float* rhs_in;  // [3][ny][rhs_pitch] from rhs_kernel, or null: evaluate the stencil in place
     int rhs_pitch;
     int y0;               // first interior row handled by this launch (row-sharded solves)
+    int natural;          // 1: store At as [3][ny][nx] (tridiagonal engine: the column solve reads rows of 32 columns)
 };
 
 template <int LOG2M, int NCH>
@@ -283,7 +285,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_fwd_kernel(RowsFwdParam
             for (int c = 0; c < NCH; ++c) {
                 const float2 v = buf[c * C::PADDED + padi(k)];
                 const float s = ch.x * v.y + ch.y * v.x;  // Im(c[k] * conv[k]) = sum_j x[j] sin(pi j k / N)
-                p.At[((size_t)(c0 + c) * p.nx + (k - 1)) * p.ny + y] = -2.0f * s;  // OpenCV: Im of the odd-extension FFT
+                const size_t o = p.natural ? ((size_t)(c0 + c) * p.ny + y) * p.nx + (k - 1) : ((size_t)(c0 + c) * p.nx + (k - 1)) * p.ny + y;
+                p.At[o] = -2.0f * s;  // OpenCV: Im of the odd-extension FFT
             }
         }
         if (NCH < 3) __syncthreads();

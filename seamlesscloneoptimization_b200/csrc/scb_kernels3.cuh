@@ -112,6 +112,12 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_fwd3_kernel(RowsFwd3Param
     auto store = [&](int k, const P4& v) {
         if (k < 1 || k > n) return;
         const float2 s = chirp_imag2(__ldg(p.tx.chirp + k), v);
+        if (p.natural) {
+            float* o = p.At + ((size_t)c * p.ny + y0) * p.nx + (k - 1);
+            o[0] = -2.0f * s.x;
+            if (has1) o[p.nx] = -2.0f * s.y;
+            return;
+        }
         float* o = p.At + ((size_t)c * p.nx + (k - 1)) * p.ny + y0;
         o[0] = -2.0f * s.x;  // OpenCV: Im of the odd-extension FFT = -2 sum x sin
         if (has1) o[1] = -2.0f * s.y;
@@ -290,12 +296,13 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_fwd4_kernel(RowsFwd3Param
     group_sync<C::NG>(g.group, C::G);
     for (int k = 1 + g.gtid; k <= n; k += C::G) {
         const P4 t = quad_unpack<LOG2M>(g.pl, __ldg(p.tx.chirp + k), k);
-        float* o = p.At + ((size_t)c * p.nx + (k - 1)) * p.ny + g.l0;
         // OpenCV: Im of the odd-extension FFT = -2 S
+        const size_t st = p.natural ? (size_t)p.nx : 1;
+        float* o = p.natural ? p.At + ((size_t)c * p.ny + g.l0) * p.nx + (k - 1) : p.At + ((size_t)c * p.nx + (k - 1)) * p.ny + g.l0;
         o[0] = -t.im.x;
-        if (nl > 1) o[1] = t.re.x;
-        if (nl > 2) o[2] = -t.im.y;
-        if (nl > 3) o[3] = t.re.y;
+        if (nl > 1) o[st] = t.re.x;
+        if (nl > 2) o[2 * st] = -t.im.y;
+        if (nl > 3) o[3 * st] = t.re.y;
     }
 }
 

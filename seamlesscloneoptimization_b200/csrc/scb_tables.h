@@ -29,6 +29,7 @@ struct HostLenTab {
     std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)                       (scalar engine)
     std::vector<float> gtw;      // per-pass [row][i] float4 (re_q, re_q+1, im_q, im_q+1), q = 1,3,5,7  (group engine, scb_gfft.cuh)
     std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
+    std::vector<double> sinfull; // 2N : sin(pi i / N)   (tridiagonal engine: low-frequency correction, scb_tri.cuh)
 };
 
 inline int choose_log2m(int n) {
@@ -154,6 +155,8 @@ inline HostLenTab build_len_tab(int n) {
             long long e = ((long long)(j + 1) * (k + 1)) % (2 * N);
             t.sinlow[(size_t)k * n + j] = std::sin(PI * (double)e / (double)N);
         }
+    t.sinfull.resize((size_t)(2 * N));
+    for (long long i = 0; i < 2 * N; ++i) t.sinfull[(size_t)i] = std::sin(PI * (double)i / (double)N);
     return t;
 }
 
@@ -164,6 +167,17 @@ inline std::vector<float> build_filter(int extent) {
     const double scale = CV_PI_ / (extent - 1);
     for (int i = 0; i < extent - 2; ++i) f[i] = 2.0f * (float)std::cos(scale * (i + 1));
     return f;
+}
+
+// theta[k] = acosh((4 - filter[k]) / 2): the tridiagonal engine's pivots are sinh ratios in theta (scb_tri.cuh).
+// filter[k] is OpenCV's float32 value, taken as exact.
+inline std::vector<double> build_theta(const std::vector<float>& filter) {
+    std::vector<double> th(filter.size());
+    for (size_t k = 0; k < filter.size(); ++k) {
+        const double half_beta_m1 = (2.0 - (double)filter[k]) * 0.5;  // beta/2 - 1 >= 0, exact in double
+        th[k] = half_beta_m1 > 0.0 ? std::log1p(half_beta_m1 + std::sqrt(half_beta_m1 * (half_beta_m1 + 2.0))) : 0.0;  // acosh(1 + e)
+    }
+    return th;
 }
 
 }  // namespace scb
