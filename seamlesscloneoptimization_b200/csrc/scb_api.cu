@@ -279,7 +279,7 @@ static cudaError_t configure_one() {
 #define SCB_FOR_LOG2M(X) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
 static cudaError_t configure_all() {
-    cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemBytes);
+    cudaError_t e = cudaSuccess;
 #define X(L) if (e == cudaSuccess) e = configure_one<L>();
     SCB_FOR_LOG2M(X)
 #undef X
@@ -510,25 +510,30 @@ static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
     const int nx = w - 2, ny = h - 2;
     const std::vector<double> th = build_theta(build_filter(w));
     const int pm = (int)align_up((size_t)nx, 4);
+    const int rows = tri_seg_len(ny) + 1;
     const size_t off_m32 = 0;
-    const size_t off_m64 = align_up(off_m32 + (size_t)ny * pm * sizeof(float), 256);
-    const size_t off_th = align_up(off_m64 + (size_t)ny * kTriLowK * sizeof(double), 256);
+    const size_t off_p32 = align_up(off_m32 + (size_t)rows * pm * sizeof(float), 256);
+    const size_t off_m64 = align_up(off_p32 + (size_t)rows * pm * sizeof(float), 256);
+    const size_t off_p64 = align_up(off_m64 + (size_t)rows * kTriLowK * sizeof(double), 256);
+    const size_t off_th = align_up(off_p64 + (size_t)rows * kTriLowK * sizeof(double), 256);
     const size_t total = align_up(off_th + (size_t)nx * sizeof(double), 256);
     DevTriTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
     char* b = (char*)d.block;
     cudaStream_t s = c->lanes[0].stream;
-    SCB_CUDA(c, cudaMemsetAsync(b + off_m64, 0, (size_t)ny * kTriLowK * sizeof(double), s));
+    SCB_CUDA(c, cudaMemsetAsync(b + off_m64, 0, off_th - off_m64, s));
     SCB_CUDA(c, cudaMemcpyAsync(b + off_th, th.data(), (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, s));
     TriTableParams tp;
     tp.theta = (const double*)(b + off_th);
     tp.nx = nx;
-    tp.ny = ny;
+    tp.rows = rows;
     tp.pm = pm;
     tp.m32 = (float*)(b + off_m32);
+    tp.p32 = (float*)(b + off_p32);
     tp.m64 = (double*)(b + off_m64);
+    tp.p64 = (double*)(b + off_p64);
     {
-        const long long total_e = (long long)ny * pm;
+        const long long total_e = (long long)rows * pm;
         long long blocks = (total_e + 255) / 256;
         if (blocks > (long long)c->sm_count * 16) blocks = (long long)c->sm_count * 16;
         SCB_LAUNCH(tri_table_kernel, dim3((unsigned)blocks), dim3(256), 0, s, tp);
@@ -537,8 +542,11 @@ static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
     SCB_CUDA(c, cudaStreamSynchronize(s));  // `th` dies at scope exit; also publishes the table to every lane
     SCB_CUDA(c, cudaGetLastError());
     d.dev.m32 = tp.m32;
+    d.dev.p32 = tp.p32;
     d.dev.pm = pm;
+    d.dev.rows = rows;
     d.dev.m64 = tp.m64;
+    d.dev.p64 = tp.p64;
     d.dev.theta = tp.theta;
     c->tritabs[key] = d;
     *out = d.dev;
@@ -1152,12 +1160,11 @@ static void run_tri(scb_plan* p, const float* A, float* Ct, const double* R, dou
     t.ny = g.ny;
     t.A = A;
     t.Ct = Ct;
-    t.R = R;
-    t.lowkx = p->lowkx;
     t.Y64 = Y64;
     t.x0 = 0;
     t.x1 = g.nx;
-    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(2 * kTriCols), kTriSmemBytes, p->lane->stream, t);
+    t.seg_len = tri_seg_len(g.ny);
+    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
     c->launches++;
     TriLowParams l;
     l.nx = g.nx;

@@ -23,9 +23,8 @@
 // LU factors in closed form.  With beta = 2 cosh(theta), rho = exp(-theta), the pivots of M are
 //     p_j = sinh((j+1) theta) / sinh(j theta),   m_j = 1 / p_j = rho (1 - rho^2j) / (1 - rho^(2j+2)),   j = 1..n,
 // evaluated in float64 at plan time (tri_table_kernel; cached per (w, h) in the context) and rounded once.
-// The pivot sequence is the same from either end of the column, so each column is eliminated from BOTH ends towards
-// the middle (two warps per 32 columns: twice the parallelism, half the dependent chain), the two halves meet in a
-// 2 x 2 system and substitute back outwards.
+// A column is cut into up to 16 segments solved concurrently (SPIKE partitioning, see tri_segments): a plain Thomas
+// sweep is a dependent chain of ny steps per column with only 3 nx columns to spread over 148 SMs.
 #pragma once
 
 #include <cstring>
@@ -37,38 +36,55 @@ namespace scb {
 
 static constexpr int kTriLowK = 32;  // spectral columns solved in float64 and corrected to OpenCV's float32 denominators
 static constexpr int kTriLowL = 32;  // ... for this many lowest frequencies along y
-static constexpr int kTriCols = 32;  // columns per CTA (one warp per column end)
-static constexpr int kTriU = 16;     // rows per cp.async stage
+static constexpr int kTriCols = 32;  // columns per CTA (lanes of a warp)
+static constexpr int kTriSegs = 16;  // segments per column (warps of a CTA)
+
+// Segment length for ny unknowns: at most kTriSegs segments, none shorter than 4 rows unless the column is.
+SCB_HD int tri_seg_len(int ny) {
+    int s = ny / 4;
+    if (s < 1) s = 1;
+    if (s > kTriSegs) s = kTriSegs;
+    return (ny + s - 1) / s;
+}
 
 struct TriTabDev {
-    const float* m32;    // [ny][pm]   m_(d+1) of column k, d = distance from the column end
-    int pm;
-    const double* m64;   // [ny][kTriLowK]
-    const double* theta; // [nx]
+    const float* m32;   // [rows][pm]  m_d = sinh((d+1) theta) / sinh((d+2) theta): reciprocal pivot at distance d from a segment end
+    const float* p32;   // [rows][pm]  P_d = sinh(theta) / sinh((d+1) theta)     : prod_{i<d} m_i
+    int pm, rows;       // rows = tri_seg_len(ny) + 1
+    const double* m64;  // [rows][kTriLowK]
+    const double* p64;  // [rows][kTriLowK]
+    const double* theta;  // [nx]
 };
 
 struct TriTableParams {
     const double* theta;  // [nx]  acosh((4 - fx[k]) / 2)
-    int nx, ny, pm;
-    float* m32;
-    double* m64;
+    int nx, rows, pm;
+    float *m32, *p32;
+    double *m64, *p64;
 };
 
-// m_(d+1) = rho (1 - rho^(2d+2)) / (1 - rho^(2d+4))
+// rho = exp(-theta):  m_d = rho (1 - rho^(2d+2)) / (1 - rho^(2d+4)),   P_d = rho^d (1 - rho^2) / (1 - rho^(2d+2))
 __global__ void __launch_bounds__(256) tri_table_kernel(TriTableParams p) {
-    const long long total = (long long)p.ny * p.pm;
+    const long long total = (long long)p.rows * p.pm;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int d = (int)(i / p.pm), k = (int)(i - (long long)d * p.pm);
-        double m = 0.0;
+        double m = 0.0, P = 0.0;
         if (k < p.nx) {
             const double th = p.theta[k];
-            if (th < 1e-10)
+            if (th < 1e-10) {
                 m = (double)(d + 1) / (double)(d + 2);
-            else
+                P = 1.0 / (double)(d + 1);
+            } else {
                 m = exp(-th) * (expm1(-2.0 * (d + 1) * th) / expm1(-2.0 * (d + 2) * th));
+                P = exp(-(double)d * th) * (expm1(-2.0 * th) / expm1(-2.0 * (d + 1) * th));
+            }
         }
         p.m32[i] = (float)m;
-        if (k < kTriLowK) p.m64[(size_t)d * kTriLowK + k] = m;
+        p.p32[i] = (float)P;
+        if (k < kTriLowK) {
+            p.m64[(size_t)d * kTriLowK + k] = m;
+            p.p64[(size_t)d * kTriLowK + k] = P;
+        }
     }
 }
 
@@ -77,187 +93,160 @@ struct TriSolveParams {
     int nx, ny;
     const float* A;    // [3][ny][nx]  row-transformed RHS (OpenCV scale: -2 sum g sin)
     float* Ct;         // [3][ny][nx]
-    const double* R;   // [3][lowkx][ny] exact row sums (A = -2 R) for k < lowkx, or null
-    int lowkx;
     double* Y64;       // [3][ny][kTriLowK] float64 work / result columns k < kTriLowK
-    int x0, x1;        // columns of this launch (multiples of kTriCols except the end)
+    int x0, x1;        // columns of this launch (x0 a multiple of kTriCols)
+    int seg_len;       // tri_seg_len(ny)
 };
 
-// cp.async (LDGSTS): global -> shared without a register stop, so a warp keeps D x kTriU rows in flight
-// while its dependent chain works on the oldest stage.  Each lane copies, and later reads, only its own column:
-// no cross-lane synchronisation, cp.async.wait_group is enough.
-#ifdef SCB_EMU
-template <int B>
-SCB_D void cp_async(void* smem, const void* g) { std::memcpy(smem, g, B); }
-SCB_D void cp_async_commit() {}
-template <int N>
-SCB_D void cp_async_wait() {}
-#else
-template <int B>
-SCB_D void cp_async(void* smem, const void* g) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(g), "n"(B) : "memory");
-}
-SCB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-SCB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
+// Partitioned (SPIKE) Thomas solve of M u = a, M = tridiag(-1, beta, -1), one thread per (column, segment):
+//   pass 1  every segment eliminates its own rows downwards (v, stored) and upwards (kept in a register): the two ends
+//           w_first, w_last of its LOCAL solution (neighbours taken as zero) fall out without a back substitution;
+//   reduce  per column, the 2 (S-1) values next to the segment interfaces solve a small banded system whose coefficients
+//           are the spike ends  e = sinh(theta)/sinh((L+1) theta),  f = sinh(L theta)/sinh((L+1) theta)  (table entries);
+//   pass 2  back substitution with the TRUE neighbours: u_d = m_d (v_d + alpha P_d + u_(d+1)),  u_L = beta
+//           (alpha = u just above the segment, beta = u just below).
+// The pivots restart in every segment, so only seg_len + 1 table rows exist and they stay in L1/L2.
+template <class T>
+struct TriIo;  // global-memory views of one column: a(y), v/u(y) and the tables
 
-static constexpr int kTriRingBytesPerWarp = 32768;  // D stages x {operand, factor} x kTriU rows x 32 lanes x sizeof(T)
-static constexpr size_t kTriSmemBytes = 2 * kTriRingBytesPerWarp;
-
-// One column end: eliminates towards the middle, meets the other end, substitutes back.  T = float or double.
-//   issue_a(slot, y) / read_a(slot)  RHS element of row y          issue_m(slot, d)  factor m_d
-//   issue_v(slot, y)                 eliminated RHS of row y (written by store_v)
-template <class T, class IssueA, class ReadA, class IssueM, class IssueV, class StoreV, class StoreU>
-SCB_D void tri_column(int n, bool top, int lane, T* ring, T* xch /* smem [2][kTriCols] */, const IssueA& issue_a, const ReadA& read_a, const IssueM& issue_m,
-                      const IssueV& issue_v, const StoreV& store_v, const StoreU& store_u, bool active) {
-    constexpr int U = kTriU, D = kTriRingBytesPerWarp / (2 * U * 32 * (int)sizeof(T));
-    static_assert(D >= 2, "ring too small");
-    const int h = (n + 1) / 2;
-    const int len = top ? h : n - h;
-    auto row = [&](int d) { return top ? d : n - 1 - d; };
-    auto slot = [&](int stage, int arr, int i) { return ring + ((size_t)((stage % D) * 2 + arr) * U + i) * 32 + lane; };
-    // ---- forward elimination: v_d = a_row(d) + m_(d-1) v_(d-1) ----
-    {
-        const int nb = (len + U - 1) / U;
-        auto issue = [&](int b) {
-            if (active && b < nb) {
-                SCB_UNROLL
-                for (int i = 0; i < U; ++i) {
-                    const int d = b * U + i;
-                    if (d < len) {
-                        issue_a(slot(b, 0, i), row(d));
-                        if (d > 0) issue_m(slot(b, 1, i), d - 1);
-                    }
-                }
+template <class T, class LoadA, class LoadM, class LoadP, class LoadV, class StoreV>
+SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][kTriSegs][32] */, const LoadA& load_a, const LoadM& load_m, const LoadP& load_p,
+                        const LoadV& load_v, const StoreV& store_v, bool active) {
+    const int r0 = seg * L;
+    const int len = (seg < nseg) ? ((n - r0 < L) ? n - r0 : L) : 0;
+    T* wl = sm + (0 * kTriSegs + seg) * 32 + lane;
+    T* wf = sm + (1 * kTriSegs + seg) * 32 + lane;
+    // ---- pass 1 ----
+    if (active && len > 0) {
+        T v = load_a(r0), b = load_a(r0 + len - 1);
+        store_v(r0, v);
+        int d = 1;
+        for (; d + 4 <= len; d += 4) {
+            T av[4], ab[4], mm[4];
+            SCB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                av[i] = load_a(r0 + d + i);
+                ab[i] = load_a(r0 + len - 1 - d - i);
+                mm[i] = load_m(d + i - 1);
             }
-            cp_async_commit();
-        };
-        for (int s = 0; s < D - 1; ++s) issue(s);
-        T v = T(0);
-        for (int b = 0; b < nb; ++b) {
-            issue(b + D - 1);
-            cp_async_wait<D - 1>();
-            if (active) {
-                SCB_UNROLL
-                for (int i = 0; i < U; ++i) {
-                    const int d = b * U + i;
-                    if (d < len) {
-                        const T a = read_a(slot(b, 0, i));
-                        const T m = d > 0 ? *slot(b, 1, i) : T(0);
-                        v = m * v + a;
-                        store_v(row(d), v);
-                    }
-                }
+            SCB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                v = mm[i] * v + av[i];
+                b = mm[i] * b + ab[i];
+                store_v(r0 + d + i, v);
             }
         }
-        cp_async_wait<0>();
-        // ---- the two halves meet ----
-        if (active) xch[(top ? 0 : 1) * kTriCols + lane] = v;
+        for (; d < len; ++d) {
+            const T m = load_m(d - 1);
+            v = m * v + load_a(r0 + d);
+            b = m * b + load_a(r0 + len - 1 - d);
+            store_v(r0 + d, v);
+        }
+        const T ml = load_m(len - 1);
+        *wl = ml * v;
+        *wf = ml * b;
     }
     __syncthreads();
-    // pivots of rows h-1 (from the top) and h (from the bottom): two plain loads
-    T u = T(0);
-    if (active) {
-        T mP, mQ = T(1);
-        issue_m(slot(0, 1, 0), h - 1);
-        if (n - h > 0) issue_m(slot(0, 1, 1), n - h - 1);
-        cp_async_commit();
-        cp_async_wait<0>();
-        mP = *slot(0, 1, 0);
-        if (n - h > 0) mQ = *slot(0, 1, 1);
-        const T t = xch[lane];
-        if (n - h == 0) {  // a single row
-            u = t * mP;
-        } else {
-            const T b = xch[kTriCols + lane];
-            const T P = T(1) / mP, Q = T(1) / mQ;
-            const T det = P * Q - T(1);
-            u = top ? (Q * t + b) / det : (t + P * b) / det;
+    // ---- reduced system: thread (lane, seg 0) of every column ----
+    T* al = sm + (2 * kTriSegs) * 32 + lane;  // alpha[s] at al[s * 32]
+    T* be = sm + (3 * kTriSegs) * 32 + lane;  // beta[s]
+    T* Js = sm + (4 * kTriSegs) * 32 + lane;
+    T* Ks = sm + (5 * kTriSegs) * 32 + lane;
+    if (active && seg == 0) {
+        const int lastlen = n - (nseg - 1) * L;
+        auto ecoef = [&](int s) { return load_p((s == nseg - 1) ? lastlen : L); };      // sinh(theta) / sinh((len+1) theta)
+        auto fcoef = [&](int s) { return load_m(((s == nseg - 1) ? lastlen : L) - 1); };  // sinh(len theta) / sinh((len+1) theta)
+        const T* WL = sm + lane;
+        const T* WF = sm + kTriSegs * 32 + lane;
+        // p_s = G + H q_s  (p_s: last row of segment s, q_s: first row of segment s+1);  q_s = J_s + K_s q_(s+1)
+        T G = WL[0], H = fcoef(0);
+        T* Gs = al;  // alpha/beta slots double as G/H storage until the back substitution
+        T* Hs = be;
+        for (int s = 0; s + 1 < nseg; ++s) {
+            const T e1 = ecoef(s + 1), f1 = fcoef(s + 1);
+            const T den = T(1) - f1 * H;
+            const T J = (WF[(s + 1) * 32] + f1 * G) / den, K = e1 / den;
+            Js[s * 32] = J;
+            Ks[s * 32] = K;
+            Gs[s * 32] = G;
+            Hs[s * 32] = H;
+            const T Gn = WL[(s + 1) * 32] + e1 * (G + H * J);
+            H = f1 + e1 * H * K;
+            G = Gn;
         }
-        if (len > 0) store_u(row(len - 1), u);
+        // back substitution: q_(nseg-1) = 0 (Dirichlet boundary below the last segment);  alpha_s = p_(s-1),  beta_s = q_s
+        T qn = T(0);
+        be[(nseg - 1) * 32] = T(0);
+        for (int s = nseg - 2; s >= 0; --s) {
+            const T q = Js[s * 32] + Ks[s * 32] * qn;
+            const T pp = Gs[s * 32] + Hs[s * 32] * q;
+            be[s * 32] = q;         // H_s consumed
+            al[(s + 1) * 32] = pp;  // G_(s+1) consumed
+            qn = q;
+        }
+        al[0] = T(0);
     }
-    // ---- back substitution outwards: u_row(d) = m_d (v_d + u_row(d+1)),  e = 0.. <-> d = len-2-e ----
-    {
-        const int cnt = len - 1;
-        const int nb = cnt > 0 ? (cnt + U - 1) / U : 0;
-        auto issue = [&](int b) {
-            if (active && b < nb) {
-                SCB_UNROLL
-                for (int i = 0; i < U; ++i) {
-                    const int e = b * U + i;
-                    if (e < cnt) {
-                        const int d = len - 2 - e;
-                        issue_v(slot(b, 0, i), row(d));
-                        issue_m(slot(b, 1, i), d);
-                    }
-                }
+    __syncthreads();
+    // ---- pass 2 ----
+    if (active && len > 0) {
+        const T alpha = al[seg * 32];
+        T u = be[seg * 32];
+        int d = len - 1;
+        for (; d >= 3; d -= 4) {
+            T vv[4], mm[4], pp[4];
+            SCB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                vv[i] = load_v(r0 + d - i);
+                mm[i] = load_m(d - i);
+                pp[i] = load_p(d - i);
             }
-            cp_async_commit();
-        };
-        for (int s = 0; s < D - 1; ++s) issue(s);
-        for (int b = 0; b < nb; ++b) {
-            issue(b + D - 1);
-            cp_async_wait<D - 1>();
-            if (active) {
-                SCB_UNROLL
-                for (int i = 0; i < U; ++i) {
-                    const int e = b * U + i;
-                    if (e < cnt) {
-                        const T vv = *slot(b, 0, i), m = *slot(b, 1, i);
-                        u = m * u + m * vv;
-                        store_u(row(len - 2 - e), u);
-                    }
-                }
+            SCB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                u = mm[i] * (u + (pp[i] * alpha + vv[i]));
+                store_v(r0 + d - i, u);
             }
         }
-        cp_async_wait<0>();
+        for (; d >= 0; --d) {
+            u = load_m(d) * (u + (load_p(d) * alpha + load_v(r0 + d)));
+            store_v(r0 + d, u);
+        }
     }
 }
 
-// grid = (ceil((x1 - x0) / 32), 3), block = 64: warp 0 eliminates from the top, warp 1 from the bottom.
-__global__ void __launch_bounds__(2 * kTriCols) tri_solve_kernel(TriSolveParams p) {
-    SCB_DYN_SMEM(unsigned char, ring_raw);
-    __shared__ double xch_raw[2 * kTriCols];
-    const int lane = threadIdx.x & 31;
-    const bool top = threadIdx.x < kTriCols;
+// grid = (ceil((x1 - x0) / 32), 3), block = 32 x kTriSegs
+__global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolveParams p) {
+    __shared__ double sm_raw[6 * kTriSegs * 32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int c = blockIdx.y;
     const int kb = p.x0 + (int)blockIdx.x * kTriCols;
     const int k = kb + lane;
     const bool active = k < p.x1;
-    const int n = p.ny;
+    const int n = p.ny, L = p.seg_len;
+    const int nseg = (n + L - 1) / L;
     const float* A = p.A + (size_t)c * n * p.nx + k;
     float* Ct = p.Ct + (size_t)c * n * p.nx + k;
-    unsigned char* ring = ring_raw + (top ? 0 : kTriRingBytesPerWarp);
-    if (kb < kTriLowK) {  // float64 columns (whole warp: kTriLowK == kTriCols)
+    if (kb < kTriLowK) {  // float64 columns (whole CTA: kTriLowK == kTriCols)
         double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
         const double* m = p.tab.m64 + k;
-        const double* R = (p.R && k < p.lowkx) ? p.R + ((size_t)c * p.lowkx + k) * n : nullptr;
-        tri_column<double>(
-            n, top, lane, reinterpret_cast<double*>(ring), xch_raw,
-            [&](double* s, int y) {
-                if (R)
-                    cp_async<8>(s, R + y);
-                else
-                    cp_async<4>(s, A + (size_t)y * p.nx);
-            },
-            [&](const double* s) { return R ? -2.0 * *s : (double)*reinterpret_cast<const float*>(s); },
-            [&](double* s, int d) { cp_async<8>(s, m + (size_t)d * kTriLowK); },
-            [&](double* s, int y) { cp_async<8>(s, Y + (size_t)y * kTriLowK); },
-            [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; },
-            [&](int y, double u) { Y[(size_t)y * kTriLowK] = u; }, active);
+        const double* P = p.tab.p64 + k;
+        tri_segments<double>(
+            n, L, seg, nseg, lane, sm_raw,
+            [&](int y) { return (double)__ldg(A + (size_t)y * p.nx); },
+            [&](int d) { return __ldg(m + (size_t)d * kTriLowK); },
+            [&](int d) { return __ldg(P + (size_t)d * kTriLowK); },
+            [&](int y) { return Y[(size_t)y * kTriLowK]; },
+            [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; }, active);
     } else {
         const float* m = p.tab.m32 + k;
+        const float* P = p.tab.p32 + k;
         const int pm = p.tab.pm;
-        tri_column<float>(
-            n, top, lane, reinterpret_cast<float*>(ring), reinterpret_cast<float*>(xch_raw),
-            [&](float* s, int y) { cp_async<4>(s, A + (size_t)y * p.nx); },
-            [&](const float* s) { return *s; },
-            [&](float* s, int d) { cp_async<4>(s, m + (size_t)d * pm); },
-            [&](float* s, int y) { cp_async<4>(s, Ct + (size_t)y * p.nx); },
-            [&](int y, float v) { Ct[(size_t)y * p.nx] = v; },
-            [&](int y, float u) { Ct[(size_t)y * p.nx] = u; }, active);
+        tri_segments<float>(
+            n, L, seg, nseg, lane, reinterpret_cast<float*>(sm_raw),
+            [&](int y) { return __ldg(A + (size_t)y * p.nx); },
+            [&](int d) { return __ldg(m + (size_t)d * pm); },
+            [&](int d) { return __ldg(P + (size_t)d * pm); },
+            [&](int y) { return Ct[(size_t)y * p.nx]; },
+            [&](int y, float v) { Ct[(size_t)y * p.nx] = v; }, active);
     }
 }
 
@@ -268,7 +257,7 @@ __global__ void __launch_bounds__(2 * kTriCols) tri_solve_kernel(TriSolveParams 
 struct TriLowParams {
     int nx, ny;
     const float* A;        // [3][ny][nx]
-    const double* R;       // [3][lowkx][ny] or null
+    const double* R;       // [3][lowkx][ny] exact float64 row sums (A = -2 R up to the FFT's rounding) for k < lowkx, or null
     int lowkx;
     const double* Y64;     // [3][ny][kTriLowK] float64 tridiagonal solution of the low columns
     const double* sinfull; // [2 (ny+1)]  sin(pi i / (ny+1))
@@ -281,51 +270,83 @@ static constexpr int kTriLowThreads = 128;
 
 __global__ void __launch_bounds__(kTriLowThreads) tri_lowcorr_kernel(TriLowParams p) {
     __shared__ double red[(kTriLowThreads / 32) * kTriLowL];
-    __shared__ double wl[kTriLowL];
+    __shared__ double c32[kTriLowL], cex[kTriLowL], wl[kTriLowL];
     const int tid = threadIdx.x, k = blockIdx.x, c = blockIdx.y, n = p.ny;
     const int N2 = 2 * (n + 1);
     const int L = n < kTriLowL ? n : kTriLowL;
     const double* R = (p.R && k < p.lowkx) ? p.R + ((size_t)c * p.lowkx + k) * n : nullptr;
     const float* A = p.A + (size_t)c * n * p.nx + k;
+    if (tid < kTriLowL) {
+        double a = 0.0, b = 0.0;
+        if (tid < L) {
+            const float fxk = __ldg(p.fx + k), fyl = __ldg(p.fy + tid);
+            a = 1.0 / (double)__fsub_rn(__fadd_rn(fxk, fyl), 4.0f);                                   // OpenCV: (filter_X + filter_Y) - 4 in float32
+            b = 1.0 / ((double)fxk + 2.0 * cospi((double)(tid + 1) / (double)(n + 1)) - 4.0);  // what the tridiagonal solve divides by
+        }
+        c32[tid] = a;
+        cex[tid] = b;
+    }
+    __syncthreads();
+    // acc_l = sum_y sin_l[y] (a_exact[y] / den32_l - a_fft[y] / den_l):  the solve used a_fft and den, OpenCV's arithmetic
+    // applied to the exact row sums gives a_exact / den32
     double acc[kTriLowL];
     SCB_UNROLL
     for (int l = 0; l < kTriLowL; ++l) acc[l] = 0.0;
-    for (int y = tid; y < n; y += kTriLowThreads) {
-        const double a = R ? -2.0 * R[y] : (double)__ldg(A + (size_t)y * p.nx);
-        int idx = 0;  // ((y+1)(l+1)) mod 2N, incrementally
+    constexpr int PF = 4;
+    for (int y0 = tid; y0 < n; y0 += PF * kTriLowThreads) {
+        double af[PF], ae[PF];
         SCB_UNROLL
-        for (int l = 0; l < kTriLowL; ++l) {
-            idx += y + 1;
-            if (idx >= N2) idx -= N2;
-            if (l < L) acc[l] += a * __ldg(p.sinfull + idx);
+        for (int i = 0; i < PF; ++i) {
+            const int y = y0 + i * kTriLowThreads;
+            af[i] = y < n ? (double)__ldg(A + (size_t)y * p.nx) : 0.0;
+            ae[i] = (R && y < n) ? -2.0 * __ldg(R + y) : af[i];
+        }
+        SCB_UNROLL
+        for (int i = 0; i < PF; ++i) {
+            const int y = y0 + i * kTriLowThreads;
+            if (y < n) {
+                int idx = 0;  // ((y+1)(l+1)) mod 2N, incrementally
+                SCB_UNROLL
+                for (int l = 0; l < kTriLowL; ++l) {
+                    idx += y + 1;
+                    if (idx >= N2) idx -= N2;
+                    if (l < L) acc[l] += __ldg(p.sinfull + idx) * (ae[i] * c32[l] - af[i] * cex[l]);
+                }
+            }
         }
     }
     block_reduce_store<kTriLowL>(acc, red, tid);
     if (tid < kTriLowL) {
-        double w = 0.0;
-        if (tid < L) {
-            double t = 0.0;
+        double t = 0.0;
+        if (tid < L)
             for (int wi = 0; wi < kTriLowThreads / 32; ++wi) t += red[wi * kTriLowL + tid];
-            const float fxk = __ldg(p.fx + k), fyl = __ldg(p.fy + tid);
-            const double den32 = (double)__fsub_rn(__fadd_rn(fxk, fyl), 4.0f);             // OpenCV: (filter_X + filter_Y) - 4 in float32
-            const double den = (double)fxk + 2.0 * cospi((double)(tid + 1) / (double)(n + 1)) - 4.0;  // what the tridiagonal solve divides by
-            w = -(2.0 / (double)(n + 1)) * t * (1.0 / den32 - 1.0 / den);
-        }
-        wl[tid] = w;
+        wl[tid] = -(2.0 / (double)(n + 1)) * t;
     }
     __syncthreads();
     const double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
     float* Ct = p.Ct + (size_t)c * n * p.nx + k;
-    for (int y = tid; y < n; y += kTriLowThreads) {
-        double s = Y[(size_t)y * kTriLowK];
-        int idx = 0;
+    for (int y0 = tid; y0 < n; y0 += PF * kTriLowThreads) {
+        double sv[PF];
         SCB_UNROLL
-        for (int l = 0; l < kTriLowL; ++l) {
-            idx += y + 1;
-            if (idx >= N2) idx -= N2;
-            if (l < L) s += wl[l] * __ldg(p.sinfull + idx);
+        for (int i = 0; i < PF; ++i) {
+            const int y = y0 + i * kTriLowThreads;
+            sv[i] = y < n ? Y[(size_t)y * kTriLowK] : 0.0;
         }
-        Ct[(size_t)y * p.nx] = (float)s;
+        SCB_UNROLL
+        for (int i = 0; i < PF; ++i) {
+            const int y = y0 + i * kTriLowThreads;
+            if (y < n) {
+                double sum = sv[i];
+                int idx = 0;
+                SCB_UNROLL
+                for (int l = 0; l < kTriLowL; ++l) {
+                    idx += y + 1;
+                    if (idx >= N2) idx -= N2;
+                    if (l < L) sum += wl[l] * __ldg(p.sinfull + idx);
+                }
+                Ct[(size_t)y * p.nx] = (float)sum;
+            }
+        }
     }
 }
 
