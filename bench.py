@@ -41,7 +41,8 @@ from seamlesscloneoptimization_b200 import workloads  # noqa: E402
 METRIC = "solved_mpix_per_s"
 UNIT = "Mpix/s"
 ALG_BYTES = {"rhs": 19, "rows_fwd": 24, "cols": 24, "rows_inv": 15}  # per solved RGB pixel
-KERNEL_NAMES = {"rhs": "rhs_kernel", "rows_fwd": "rows_fwd", "cols": "cols", "rows_inv": "rows_inv"}
+KERNEL_NAMES = {"rhs": "rhs_kernel", "rows_fwd": "rows_fwd{3,4}_kernel", "cols": "cols{3,4}_kernel (FFT engine) / tri_solve_kernel + tri_low*_kernel (tridiagonal engine)",
+                "rows_inv": "rows_inv{3,4}_kernel"}
 
 
 def measured_peak_gbs():

@@ -770,8 +770,7 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
     int* slot_dev = c->bbox_dev + 4 * slot;
     cudaMemcpyAsync(slot_dev, c->bbox_pinned, 4 * sizeof(int), cudaMemcpyHostToDevice, prep);
     {
-        const long long total = (long long)mv.rows * mv.cols;
-        long long blocks = (total + 255) / 256;
+        long long blocks = ((long long)mv.rows + 7) / 8;  // one warp per row, 8 warps per CTA
         if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
         SCB_LAUNCH(mask_bbox_kernel, dim3((unsigned)blocks), dim3(256), 0, prep, mv, slot_dev);
         c->launches++;
@@ -825,7 +824,7 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
         if (ce != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
         p->E = (unsigned char*)e;
     }
-    SCB_LAUNCH(mask_erode_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, lane->stream, in.mv, g.x, g.y, g.w, g.h, p->E, p->e_pitch);
+    SCB_LAUNCH(mask_erode_kernel, dim3((g.w + kErodeTW - 1) / kErodeTW, (g.h + kErodeTH - 1) / kErodeTH), dim3(256), 0, lane->stream, in.mv, g.x, g.y, g.w, g.h, p->E, p->e_pitch);
     c->launches++;
     release_stage();  // stream-ordered: freed after the erosion has read it
     int rc;
@@ -1009,6 +1008,7 @@ struct Workspace {
     int tpx = 0, tpy = 0;  // tensor-core engine: line pitches of the [..][nx] and [..][ny] orientations
     double* R = nullptr;
     double* Y64 = nullptr;  // tridiagonal engine: float64 columns k < kTriLowK
+    double* W = nullptr;    // tridiagonal engine: low-frequency block coefficients [3][kTriLowL][kTriLowK]
 };
 
 static int carve(scb_plan* p, bool host, Workspace* w) {
@@ -1036,6 +1036,7 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
     const size_t oY64 = take(p->use_tri ? (size_t)3 * g.ny * kTriLowK * sizeof(double) : 0);
+    const size_t oW = take(p->use_tri ? (size_t)3 * kTriLowL * kTriLowK * sizeof(double) : 0);
     size_t oD = 0, oS = 0, oO = 0;
     if (host) {
         oD = take((size_t)w->pD * g.h);
@@ -1050,6 +1051,7 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     w->R = (double*)(p->lane->ws + oR);
     w->lowspec = (float*)(p->lane->ws + oLow);
     w->Y64 = (double*)(p->lane->ws + oY64);
+    w->W = (double*)(p->lane->ws + oW);
     if (host) {
         w->stD = (unsigned char*)(p->lane->ws + oD);
         w->stS = (unsigned char*)(p->lane->ws + oS);
@@ -1149,23 +1151,13 @@ static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowsp
     b.x0 = x0;
     launch_cols(p->ctx, p->lane->stream, p->g.log2m_y, x1 - x0, b);
 }
-// Tridiagonal engine, pass B: Thomas solve of every spectral column (A [3][ny][nx] -> Ct [3][ny][nx]), then the
-// float64 low-frequency block with OpenCV's float32 denominators (scb_tri.cuh).
-static void run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64) {
+// Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][ny][nx] -> Ct [3][ny][nx]);
+// the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
+static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream) {
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
-    TriSolveParams t;
-    t.tab = p->tri;
-    t.nx = g.nx;
-    t.ny = g.ny;
-    t.A = A;
-    t.Ct = Ct;
-    t.Y64 = Y64;
-    t.x0 = 0;
-    t.x1 = g.nx;
-    t.seg_len = tri_seg_len(g.ny);
-    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
-    c->launches++;
+    Lane* L = p->lane;
+    cudaStream_t ms = L->stream;
     TriLowParams l;
     l.nx = g.nx;
     l.ny = g.ny;
@@ -1176,9 +1168,33 @@ static void run_tri(scb_plan* p, const float* A, float* Ct, const double* R, dou
     l.sinfull = p->ty.sinfull;
     l.fx = p->fx;
     l.fy = p->fy;
+    l.W = W;
     l.Ct = Ct;
-    SCB_LAUNCH(tri_lowcorr_kernel, dim3(g.nx < kTriLowK ? g.nx : kTriLowK, 3), dim3(kTriLowThreads), 0, p->lane->stream, l);
+    const dim3 lgrid((g.ny + kTriLowRows - 1) / kTriLowRows, 3), lblock(32 * kTriLowWarps);
+    if (proj_stream != ms) {
+        SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
+        SCB_CUDA(c, cudaStreamWaitEvent(proj_stream, L->ev_fork, 0));
+    }
+    SCB_CUDA(c, cudaMemsetAsync(W, 0, (size_t)3 * kTriLowL * kTriLowK * sizeof(double), proj_stream));
+    SCB_LAUNCH(tri_lowproj_kernel, lgrid, lblock, 0, proj_stream, l);
     c->launches++;
+    if (proj_stream != ms) SCB_CUDA(c, cudaEventRecord(L->ev_join, proj_stream));
+    TriSolveParams t;
+    t.tab = p->tri;
+    t.nx = g.nx;
+    t.ny = g.ny;
+    t.A = A;
+    t.Ct = Ct;
+    t.Y64 = Y64;
+    t.x0 = 0;
+    t.x1 = g.nx;
+    t.seg_len = tri_seg_len(g.ny);
+    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, ms, t);
+    c->launches++;
+    if (proj_stream != ms) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
+    SCB_LAUNCH(tri_lowapply_kernel, lgrid, lblock, 0, ms, l);
+    c->launches++;
+    return SCB_OK;
 }
 
 static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1) {
@@ -1445,9 +1461,9 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         run_rows_fwd(p, st, w.G, w.gp, w.At, yb[nb - 1], g.ny, p->use_tri);
         if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
-        if (p->use_tri)
-            run_tri(p, w.At, w.Ct, w.R, w.Y64);
-        else
+        if (p->use_tri) {
+            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, tm.on ? ms : L->side))) return rc;
+        } else
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));

@@ -522,16 +522,24 @@ struct MaskView {
 
 // bbox of non-zero pixels of the ring-zeroed mask.  bbox = {minx, miny, maxx, maxy}, pre-set to
 // {INT_MAX, INT_MAX, -1, -1}.  OpenCV: copyMakeBorder(mask(1..-1), 0) + boundingRect.
+// A warp owns whole rows (lanes stride over the columns: coalesced byte loads, no index division).
 __global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
     int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
-    const long long total = (long long)m.rows * m.cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / m.cols), x = (int)(i - (long long)y * m.cols);
-        if (x == 0 || y == 0 || x == m.cols - 1 || y == m.rows - 1) continue;
-        if (__ldg(m.data + (long long)y * m.pitch + x)) {
-            minx = min(minx, x);
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int y = 1 + warp; y < m.rows - 1; y += nwarps) {
+        const unsigned char* row = m.data + (long long)y * m.pitch;
+        int lo = 0x7fffffff, hi = -1;
+        for (int x = 1 + lane; x < m.cols - 1; x += 32) {
+            if (__ldg(row + x)) {
+                lo = min(lo, x);
+                hi = x;  // x grows within the lane
+            }
+        }
+        if (hi >= 0) {
+            minx = min(minx, lo);
+            maxx = max(maxx, hi);
             miny = min(miny, y);
-            maxx = max(maxx, x);
             maxy = max(maxy, y);
         }
     }
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
         maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, off));
         maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, off));
     }
-    if ((threadIdx.x & 31) == 0 && maxx >= 0) {
+    if (lane == 0 && maxx >= 0) {
         atomicMin(bbox + 0, minx);
         atomicMin(bbox + 1, miny);
         atomicMax(bbox + 2, maxx);
@@ -551,22 +559,43 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
 
 // E = erode(ring-zeroed mask, 3x3 ones, iterations = 3) cropped to the ROI: a 7x7 minimum over the
 // FULL mask (pixels outside the ROI take part; outside the image the border does not lower the min).
+// Separable through shared memory: a 64 x 16 output tile stages its (64+6) x (16+6) inputs once, takes the
+// horizontal 7-minimum, then the vertical one.   grid = (ceil(w/64), ceil(h/16)), block = 256
+static constexpr int kErodeTW = 64, kErodeTH = 16;
+
 __global__ void __launch_bounds__(256) mask_erode_kernel(MaskView m, int x0, int y0, int w, int h, unsigned char* E, long long e_pitch) {
-    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (X >= w || Y >= h) return;
-    int v = 255;
-    for (int dy = -3; dy <= 3; ++dy) {
-        const int yy = y0 + Y + dy;
-        if (yy < 0 || yy >= m.rows) continue;
-        for (int dx = -3; dx <= 3; ++dx) {
-            const int xx = x0 + X + dx;
-            if (xx < 0 || xx >= m.cols) continue;
+    __shared__ unsigned char raw[kErodeTH + 6][kErodeTW + 8];
+    __shared__ unsigned char hm[kErodeTH + 6][kErodeTW];
+    const int tid = threadIdx.x, bx = blockIdx.x * kErodeTW, by = blockIdx.y * kErodeTH;
+    for (int i = tid; i < (kErodeTH + 6) * (kErodeTW + 6); i += 256) {
+        const int ry = i / (kErodeTW + 6), rx = i - ry * (kErodeTW + 6);
+        const int yy = y0 + by + ry - 3, xx = x0 + bx + rx - 3;
+        int v = 255;
+        if (yy >= 0 && yy < m.rows && xx >= 0 && xx < m.cols) {
             const bool ring = (xx == 0 || yy == 0 || xx == m.cols - 1 || yy == m.rows - 1);
-            const int pv = ring ? 0 : (int)__ldg(m.data + (long long)yy * m.pitch + xx);
-            v = min(v, pv);
+            v = ring ? 0 : (int)__ldg(m.data + (long long)yy * m.pitch + xx);
+        }
+        raw[ry][rx] = (unsigned char)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < (kErodeTH + 6) * kErodeTW; i += 256) {
+        const int ry = i / kErodeTW, rx = i - ry * kErodeTW;
+        int v = 255;
+        SCB_UNROLL
+        for (int d = 0; d < 7; ++d) v = min(v, (int)raw[ry][rx + d]);
+        hm[ry][rx] = (unsigned char)v;
+    }
+    __syncthreads();
+    for (int i = tid; i < kErodeTH * kErodeTW; i += 256) {
+        const int ry = i / kErodeTW, rx = i - ry * kErodeTW;
+        const int X = bx + rx, Y = by + ry;
+        if (X < w && Y < h) {
+            int v = 255;
+            SCB_UNROLL
+            for (int d = 0; d < 7; ++d) v = min(v, (int)hm[ry + d][rx]);
+            E[(long long)Y * e_pitch + X] = (unsigned char)v;
         }
     }
-    E[(long long)Y * e_pitch + X] = (unsigned char)v;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -251,102 +251,99 @@ __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolve
 }
 
 // ---------------------------------------------------------------------------------------------
-// Low-frequency block: float64 solution of columns k < kTriLowK + OpenCV's float32 denominators for l < kTriLowL.
-//   grid = (min(kTriLowK, nx), 3), block = 128
+// Low-frequency block: OpenCV's float32 denominators for k < kTriLowK, l < kTriLowL, in float64.
+//   W[c][l][k] = -(2/Ny) ( <sin_l, a_exact_k> / den32[k][l]  -  <sin_l, a_fft_k> / den[k][l] )
+//     a_fft   = the float32 row-transform output the tridiagonal solve consumed,
+//     a_exact = -2 R (float64 row sums) where they exist (k < lowkx), else a_fft,
+//     den32   = fl(fl(fx[k] + fy[l]) - 4)  (OpenCV),   den = fx[k] + 2 cos(pi (l+1) / (ny+1)) - 4  (what M inverts)
+//   Ct[c][y][k] = Y64[c][y][k] + sum_l W[c][l][k] sin_l[y]
+// tri_lowproj_kernel (sums over y, needs only pass A: runs on the side stream beside the column solve) and
+// tri_lowapply_kernel.  Lanes run over k (coalesced rows of A / Y64 / Ct), warps over y.
 // ---------------------------------------------------------------------------------------------
 struct TriLowParams {
     int nx, ny;
     const float* A;        // [3][ny][nx]
-    const double* R;       // [3][lowkx][ny] exact float64 row sums (A = -2 R up to the FFT's rounding) for k < lowkx, or null
+    const double* R;       // [3][lowkx][ny] exact float64 row sums for k < lowkx, or null
     int lowkx;
     const double* Y64;     // [3][ny][kTriLowK] float64 tridiagonal solution of the low columns
     const double* sinfull; // [2 (ny+1)]  sin(pi i / (ny+1))
     const float* fx;       // OpenCV filter_X (nx)
     const float* fy;       // OpenCV filter_Y (ny)
+    double* W;             // [3][kTriLowL][kTriLowK], zeroed before tri_lowproj_kernel
     float* Ct;             // [3][ny][nx]
 };
 
-static constexpr int kTriLowThreads = 128;
+static constexpr int kTriLowWarps = 8;
+static constexpr int kTriLowRows = 32;  // rows of y per CTA
 
-__global__ void __launch_bounds__(kTriLowThreads) tri_lowcorr_kernel(TriLowParams p) {
-    __shared__ double red[(kTriLowThreads / 32) * kTriLowL];
-    __shared__ double c32[kTriLowL], cex[kTriLowL], wl[kTriLowL];
-    const int tid = threadIdx.x, k = blockIdx.x, c = blockIdx.y, n = p.ny;
+// grid = (ceil(ny / kTriLowRows), 3), block = 32 x kTriLowWarps
+__global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj_kernel(TriLowParams p) {
+    __shared__ double red[2][kTriLowL][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y, n = p.ny;
+    for (int i = threadIdx.x; i < 2 * kTriLowL * 32; i += 32 * kTriLowWarps) (&red[0][0][0])[i] = 0.0;
+    __syncthreads();
+    const int k = lane;
+    const bool kin = k < p.nx;
     const int N2 = 2 * (n + 1);
     const int L = n < kTriLowL ? n : kTriLowL;
-    const double* R = (p.R && k < p.lowkx) ? p.R + ((size_t)c * p.lowkx + k) * n : nullptr;
-    const float* A = p.A + (size_t)c * n * p.nx + k;
-    if (tid < kTriLowL) {
-        double a = 0.0, b = 0.0;
-        if (tid < L) {
-            const float fxk = __ldg(p.fx + k), fyl = __ldg(p.fy + tid);
-            a = 1.0 / (double)__fsub_rn(__fadd_rn(fxk, fyl), 4.0f);                                   // OpenCV: (filter_X + filter_Y) - 4 in float32
-            b = 1.0 / ((double)fxk + 2.0 * cospi((double)(tid + 1) / (double)(n + 1)) - 4.0);  // what the tridiagonal solve divides by
-        }
-        c32[tid] = a;
-        cex[tid] = b;
-    }
-    __syncthreads();
-    // acc_l = sum_y sin_l[y] (a_exact[y] / den32_l - a_fft[y] / den_l):  the solve used a_fft and den, OpenCV's arithmetic
-    // applied to the exact row sums gives a_exact / den32
-    double acc[kTriLowL];
+    const bool has_r = p.R && k < p.lowkx;
+    double tf[kTriLowL], te[kTriLowL];  // <sin_l, a_fft>, <sin_l, a_exact - a_fft>
     SCB_UNROLL
-    for (int l = 0; l < kTriLowL; ++l) acc[l] = 0.0;
-    constexpr int PF = 4;
-    for (int y0 = tid; y0 < n; y0 += PF * kTriLowThreads) {
-        double af[PF], ae[PF];
+    for (int l = 0; l < kTriLowL; ++l) tf[l] = te[l] = 0.0;
+    const int yb = blockIdx.x * kTriLowRows;
+    for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
+        const double af = kin ? (double)__ldg(p.A + ((size_t)c * n + y) * p.nx + k) : 0.0;
+        const double dx = has_r ? -2.0 * __ldg(p.R + ((size_t)c * p.lowkx + k) * n + y) - af : 0.0;
+        int idx = 0;  // ((y+1)(l+1)) mod 2N, incrementally (warp-uniform: a broadcast load)
         SCB_UNROLL
-        for (int i = 0; i < PF; ++i) {
-            const int y = y0 + i * kTriLowThreads;
-            af[i] = y < n ? (double)__ldg(A + (size_t)y * p.nx) : 0.0;
-            ae[i] = (R && y < n) ? -2.0 * __ldg(R + y) : af[i];
-        }
-        SCB_UNROLL
-        for (int i = 0; i < PF; ++i) {
-            const int y = y0 + i * kTriLowThreads;
-            if (y < n) {
-                int idx = 0;  // ((y+1)(l+1)) mod 2N, incrementally
-                SCB_UNROLL
-                for (int l = 0; l < kTriLowL; ++l) {
-                    idx += y + 1;
-                    if (idx >= N2) idx -= N2;
-                    if (l < L) acc[l] += __ldg(p.sinfull + idx) * (ae[i] * c32[l] - af[i] * cex[l]);
-                }
-            }
+        for (int l = 0; l < kTriLowL; ++l) {
+            idx += y + 1;
+            if (idx >= N2) idx -= N2;
+            const double sv = (l < L) ? __ldg(p.sinfull + idx) : 0.0;
+            tf[l] += sv * af;
+            te[l] += sv * dx;
         }
     }
-    block_reduce_store<kTriLowL>(acc, red, tid);
-    if (tid < kTriLowL) {
-        double t = 0.0;
-        if (tid < L)
-            for (int wi = 0; wi < kTriLowThreads / 32; ++wi) t += red[wi * kTriLowL + tid];
-        wl[tid] = -(2.0 / (double)(n + 1)) * t;
+    SCB_UNROLL
+    for (int l = 0; l < kTriLowL; ++l) {
+        atomicAdd(&red[0][l][lane], tf[l]);
+        atomicAdd(&red[1][l][lane], te[l]);
     }
     __syncthreads();
-    const double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
-    float* Ct = p.Ct + (size_t)c * n * p.nx + k;
-    for (int y0 = tid; y0 < n; y0 += PF * kTriLowThreads) {
-        double sv[PF];
-        SCB_UNROLL
-        for (int i = 0; i < PF; ++i) {
-            const int y = y0 + i * kTriLowThreads;
-            sv[i] = y < n ? Y[(size_t)y * kTriLowK] : 0.0;
+    // thread (warp, lane) finishes frequencies l = warp, warp + 8, ... of column k = lane
+    if (kin) {
+        const float fxk = __ldg(p.fx + k);
+        for (int l = warp; l < L; l += kTriLowWarps) {
+            const double sf = red[0][l][lane], se = red[1][l][lane];
+            const double i32 = 1.0 / (double)__fsub_rn(__fadd_rn(fxk, __ldg(p.fy + l)), 4.0f);             // OpenCV: (filter_X + filter_Y) - 4 in float32
+            const double iex = 1.0 / ((double)fxk + 2.0 * cospi((double)(l + 1) / (double)(n + 1)) - 4.0);  // what the tridiagonal solve divides by
+            const double w = -(2.0 / (double)(n + 1)) * ((sf + se) * i32 - sf * iex);
+            atomicAdd(p.W + ((size_t)c * kTriLowL + l) * kTriLowK + k, w);
         }
+    }
+}
+
+// grid = (ceil(ny / kTriLowRows), 3), block = 32 x kTriLowWarps
+__global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y, n = p.ny;
+    const int k = lane;
+    if (k >= p.nx) return;
+    const int N2 = 2 * (n + 1);
+    const int L = n < kTriLowL ? n : kTriLowL;
+    double w[kTriLowL];
+    SCB_UNROLL
+    for (int l = 0; l < kTriLowL; ++l) w[l] = (l < L) ? p.W[((size_t)c * kTriLowL + l) * kTriLowK + k] : 0.0;
+    const int yb = blockIdx.x * kTriLowRows;
+    for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
+        double sum = p.Y64[((size_t)c * n + y) * kTriLowK + k];
+        int idx = 0;
         SCB_UNROLL
-        for (int i = 0; i < PF; ++i) {
-            const int y = y0 + i * kTriLowThreads;
-            if (y < n) {
-                double sum = sv[i];
-                int idx = 0;
-                SCB_UNROLL
-                for (int l = 0; l < kTriLowL; ++l) {
-                    idx += y + 1;
-                    if (idx >= N2) idx -= N2;
-                    if (l < L) sum += wl[l] * __ldg(p.sinfull + idx);
-                }
-                Ct[(size_t)y * p.nx] = (float)sum;
-            }
+        for (int l = 0; l < kTriLowL; ++l) {
+            idx += y + 1;
+            if (idx >= N2) idx -= N2;
+            if (l < L) sum += w[l] * __ldg(p.sinfull + idx);
         }
+        p.Ct[((size_t)c * n + y) * p.nx + k] = (float)sum;
     }
 }
 

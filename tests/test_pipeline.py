@@ -349,7 +349,7 @@ def test_launch_counter(ctx):
     before = ctx.kernel_launches
     plan.execute(src, dst)
     # FFT engine: rhs, lowfreq rows, lowfreq cols, rows fwd, cols, rows inv; tensor-core engine: 4 passes + compose instead of 3
-    assert ctx.kernel_launches - before == (8 if plan.engine == capi.ENGINE_TC else 6)
+    assert ctx.kernel_launches - before == {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7}.get(plan.engine, 6)
     plan.close()
 
 
@@ -427,7 +427,7 @@ def test_graph_replay_equals_plain_execute(be, ctx):
         for _ in range(3):  # first call captures, the next two replay
             plan.execute_graph(vs, vd, vb1)
         ctx.sync()
-        assert ctx.kernel_launches - before == 3 * (8 if plan.engine == capi.ENGINE_TC else 6)
+        assert ctx.kernel_launches - before == 3 * {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7}.get(plan.engine, 6)
         assert np.array_equal(be.to_host(hb0), be.to_host(hb1))
     plan.close()
 
