@@ -394,8 +394,7 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     const size_t off_tw = align_up(off_bhq + h.bhat_q.size() * sizeof(float2), 256);
     const size_t off_ptw = align_up(off_tw + M * sizeof(float2), 256);
     const size_t off_sin = align_up(off_ptw + h.gtw.size() * sizeof(float), 256);
-    const size_t off_sinf = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
-    const size_t total = align_up(off_sinf + h.sinfull.size() * sizeof(double), 256);
+    const size_t total = align_up(off_sin + h.sinlow.size() * sizeof(double), 256);
     std::vector<char> host(total, 0);
     std::memcpy(host.data() + off_chirp, h.chirp.data(), h.chirp.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_bhat, h.bhat_t.data(), h.bhat_t.size() * sizeof(HostF2));
@@ -403,7 +402,6 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     std::memcpy(host.data() + off_tw, h.tw.data(), h.tw.size() * sizeof(HostF2));
     std::memcpy(host.data() + off_ptw, h.gtw.data(), h.gtw.size() * sizeof(float));
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
-    std::memcpy(host.data() + off_sinf, h.sinfull.data(), h.sinfull.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
     SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->lanes[0].stream));
@@ -418,7 +416,6 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.tw = (const float2*)(b + off_tw);
     d.dev.gtw = (const float4*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);
-    d.dev.sinfull = (const double*)(b + off_sinf);
     c->lentabs[n] = d;
     *out = d.dev;
     return SCB_OK;
@@ -1165,7 +1162,6 @@ static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, doub
     l.R = R;
     l.lowkx = p->lowkx;
     l.Y64 = Y64;
-    l.sinfull = p->ty.sinfull;
     l.fx = p->fx;
     l.fy = p->fy;
     l.W = W;

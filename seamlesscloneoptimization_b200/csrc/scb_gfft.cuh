@@ -5,7 +5,10 @@
 //     (im_a, im_b).  A complex add is two FADD2, a complex multiply 2 FMUL2 + 2 FFMA2 -- Blackwell's
 //     packed fp32x2 pipe, which is also the only way to reach the full FP32 rate on sm_100 -- and
 //     every access is a conflict-free 64-bit LDS/STS (an AoS float4 layout costs 4 MOVs per STS.128).
-// (2) Groups.  A CTA holds NG independent pairs (one per colour channel); pair g is owned by its own
+// (2) Groups.  A CTA holds NG independent pairs (one per colour channel; NG = 1 from 512-point sequences up,
+//     where blockIdx.y selects the channel -- measured on B200: three independent 1-group CTAs per SM finish
+//     15-25 % sooner than one 3-group CTA, because the CTAs desynchronise and one CTA's exposed first-pass
+//     load latency hides under the others' butterflies); pair g is owned by its own
 //     group of G threads that synchronises on its own named barrier (bar.sync g+1, G).  The groups
 //     drift apart, so one group's shared-memory bursts overlap another's FMA bursts.  With a single
 //     CTA-wide barrier all warps load, compute and store in lockstep and the two pipes serialise
@@ -110,6 +113,9 @@ SCB_HD constexpr int gtw_offset16(int log2m, int L) {
 SCB_HD constexpr int gtw_total_c(int log2m) { return gtw_offset16(log2m, 16); }
 
 // ---- configuration ------------------------------------------------------------------------------
+#ifndef SCB_NG1_FROM
+#define SCB_NG1_FROM 9
+#endif
 template <int LOG2M>
 struct GCfg {
     static_assert(LOG2M >= 5 && LOG2M <= 13, "group engine: convolution lengths 32 .. 8192");
@@ -117,7 +123,7 @@ struct GCfg {
     static constexpr int R0 = (LOG2M % 4 == 0) ? 16 : (1 << (LOG2M % 4));
     static constexpr int G = (M / 32 < 32) ? 32 : (M / 32);  // threads per group: two radix-16 butterflies each
     static constexpr int PADDED = M + (M >> 4);              // float2 elements per plane
-    static constexpr int NG = (LOG2M <= 12) ? 3 : 1;         // groups (channels) per CTA; 8192-point pairs: one per CTA
+    static constexpr int NG = (LOG2M < SCB_NG1_FROM) ? 3 : 1;  // groups (channels) per CTA; from 2^SCB_NG1_FROM points up: one pair per CTA, blockIdx.y = channel
     static constexpr int T = NG * G;
     static constexpr size_t DATA_BYTES = (size_t)NG * 2 * PADDED * sizeof(float2);
     // Twiddle tables live in shared memory when the CTA owns the SM anyway (M >= 4096: 17 KB / 81 KB

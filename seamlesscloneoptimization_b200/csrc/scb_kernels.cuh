@@ -35,7 +35,6 @@ struct LenTabDev {
     const float2* tw;
     const float4* gtw;  // per-pass twiddle tables of the group engine (scb_gfft.cuh)
     const double* sinlow;
-    const double* sinfull;  // [2N] sin(pi i / N)
 };
 
 struct StencilSrc {

@@ -29,7 +29,6 @@ struct HostLenTab {
     std::vector<HostF2> tw;      // M   : exp(-2 pi i t / M)                       (scalar engine)
     std::vector<float> gtw;      // per-pass [row][i] float4 (re_q, re_q+1, im_q, im_q+1), q = 1,3,5,7  (group engine, scb_gfft.cuh)
     std::vector<double> sinlow;  // lowk x n : sin(pi (j+1)(k+1) / N)
-    std::vector<double> sinfull; // 2N : sin(pi i / N)   (tridiagonal engine: low-frequency correction, scb_tri.cuh)
 };
 
 inline int choose_log2m(int n) {
@@ -155,8 +154,6 @@ inline HostLenTab build_len_tab(int n) {
             long long e = ((long long)(j + 1) * (k + 1)) % (2 * N);
             t.sinlow[(size_t)k * n + j] = std::sin(PI * (double)e / (double)N);
         }
-    t.sinfull.resize((size_t)(2 * N));
-    for (long long i = 0; i < 2 * N; ++i) t.sinfull[(size_t)i] = std::sin(PI * (double)i / (double)N);
     return t;
 }
 

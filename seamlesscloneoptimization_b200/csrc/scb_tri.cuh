@@ -266,7 +266,6 @@ struct TriLowParams {
     const double* R;       // [3][lowkx][ny] exact float64 row sums for k < lowkx, or null
     int lowkx;
     const double* Y64;     // [3][ny][kTriLowK] float64 tridiagonal solution of the low columns
-    const double* sinfull; // [2 (ny+1)]  sin(pi i / (ny+1))
     const float* fx;       // OpenCV filter_X (nx)
     const float* fy;       // OpenCV filter_Y (ny)
     double* W;             // [3][kTriLowL][kTriLowK], zeroed before tri_lowproj_kernel
@@ -284,7 +283,6 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj_kernel(TriLowPa
     __syncthreads();
     const int k = lane;
     const bool kin = k < p.nx;
-    const int N2 = 2 * (n + 1);
     const int L = n < kTriLowL ? n : kTriLowL;
     const bool has_r = p.R && k < p.lowkx;
     double tf[kTriLowL], te[kTriLowL];  // <sin_l, a_fft>, <sin_l, a_exact - a_fft>
@@ -294,14 +292,18 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj_kernel(TriLowPa
     for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
         const double af = kin ? (double)__ldg(p.A + ((size_t)c * n + y) * p.nx + k) : 0.0;
         const double dx = has_r ? -2.0 * __ldg(p.R + ((size_t)c * p.lowkx + k) * n + y) - af : 0.0;
-        int idx = 0;  // ((y+1)(l+1)) mod 2N, incrementally (warp-uniform: a broadcast load)
+        // sin(pi (y+1)(l+1) / N), l = 0.., by the three-term recurrence s_(l+1) = 2 cos(phi) s_l - s_(l-1) in float64
+        // (32 steps from phi >= pi / 8193: error < 1e-11, against 1e-9 needed)
+        const double ph = (double)(y + 1) / (double)(n + 1);
+        const double twoc = 2.0 * cospi(ph);
+        double s0 = 0.0, s1 = sinpi(ph);
         SCB_UNROLL
         for (int l = 0; l < kTriLowL; ++l) {
-            idx += y + 1;
-            if (idx >= N2) idx -= N2;
-            const double sv = (l < L) ? __ldg(p.sinfull + idx) : 0.0;
-            tf[l] += sv * af;
-            te[l] += sv * dx;
+            tf[l] += s1 * af;
+            te[l] += s1 * dx;
+            const double s2 = twoc * s1 - s0;
+            s0 = s1;
+            s1 = s2;
         }
     }
     SCB_UNROLL
@@ -328,7 +330,6 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowP
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y, n = p.ny;
     const int k = lane;
     if (k >= p.nx) return;
-    const int N2 = 2 * (n + 1);
     const int L = n < kTriLowL ? n : kTriLowL;
     double w[kTriLowL];
     SCB_UNROLL
@@ -336,12 +337,15 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowP
     const int yb = blockIdx.x * kTriLowRows;
     for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
         double sum = p.Y64[((size_t)c * n + y) * kTriLowK + k];
-        int idx = 0;
+        const double ph = (double)(y + 1) / (double)(n + 1);
+        const double twoc = 2.0 * cospi(ph);
+        double s0 = 0.0, s1 = sinpi(ph);
         SCB_UNROLL
         for (int l = 0; l < kTriLowL; ++l) {
-            idx += y + 1;
-            if (idx >= N2) idx -= N2;
-            if (l < L) sum += w[l] * __ldg(p.sinfull + idx);
+            sum += w[l] * s1;
+            const double s2 = twoc * s1 - s0;
+            s0 = s1;
+            s1 = s2;
         }
         p.Ct[((size_t)c * n + y) * p.nx + k] = (float)sum;
     }
