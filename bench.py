@@ -10,7 +10,8 @@ NORMAL_CLONE of the workload (cfg3: one pass over the whole batch of jobs).
   N > 1 (torchrun, one rank per GPU)
     cfg1/2/5  every rank clones its own independent job of that shape, no collective: "weak"
     cfg3      the 512 jobs are split over the ranks (LPT by solved pixels), no collective: "strong"
-    cfg4      ONE solve, rows/columns sharded over the ranks, NCCL all-to-all between the passes: "strong"
+    cfg4      ONE solve, rows sharded over the ranks along the segments of the partitioned tridiagonal solve, two small NCCL all-reduces
+              (--sharded-fft: rows/columns sharded, NCCL all-to-all transposes between the passes): "strong"
 
   value     device-resident: images already in HBM, plan (mask prep + tables) made once, CUDA events on the
             library's stream, L2 flushed (256 MiB write) between timed steps
@@ -485,7 +486,8 @@ def sharded_leg(env: Env, args):
     src, dst, mask, p = workloads.make_config("cfg4", seed=0)  # every rank holds the same u8 inputs (no halo exchange)
     stream = torch.cuda.Stream(device=env.dev)  # the library, torch's pack/unpack copies and NCCL all order on this stream
     ctx = scb.Context(env.local_rank, stream=stream.cuda_stream)
-    ctx.set_engine(capi.ENGINE_FFT)  # row/column-sharded passes exist for the FFT engine
+    if args.sharded_fft:  # the transpose scheme (two all-to-alls) instead of the segment scheme of the tridiagonal engine
+        ctx.set_engine(capi.ENGINE_FFT)
     d_src, d_dst, d_mask = (torch.from_numpy(a).to(env.dev) for a in (src, dst, mask))
     d_blend = d_dst.clone()
     torch.cuda.synchronize()
@@ -536,14 +538,19 @@ def sharded_leg(env: Env, args):
         e2e_ms_max, = env.max_over_ranks(sum(e2e_ts) * 1e3)
     line = None
     if env.rank == 0:
-        a2a_bytes = 2 * 4 * 3 * px * (env.world - 1) // (env.world * env.world)  # sent per rank per solve, both exchanges
+        if solve.tri:
+            par = f"rows sharded x{env.world} along the segments of the partitioned tridiagonal solve; 2 small all-reduces (NCCL), no transpose"
+            xbytes = solve.exchange_bytes
+        else:
+            par = f"rows/cols sharded x{env.world}, 2 all-to-all (NCCL grouped send/recv)"
+            xbytes = 2 * 4 * 3 * px * (env.world - 1) // (env.world * env.world)  # sent per rank per solve, both exchanges
         line = {
             "metric": METRIC, "value": px * args.steps / (total_ms_max * 1e-3) / 1e6, "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
             "warmup": env.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS["cfg4"], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
-                       "l2": "256 MiB flush write between timed steps", "parallelism": f"rows/cols sharded x{env.world}, 2 all-to-all (NCCL grouped send/recv)",
-                       "a2a_bytes_sent_per_rank_per_step": int(a2a_bytes)},
+                       "l2": "256 MiB flush write between timed steps", "parallelism": par,
+                       "bytes_exchanged_per_rank_per_step": int(xbytes)},
             "clocks": sampler.summary(),
             "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(src.size + dst.size), "d2h_bytes_per_step": int(h_rows.numel()),
                     "ms_per_step": e2e_ms_max / args.steps, "call": "pinned src+dst H2D per rank, ShardedSolve.run, own row slab D2H"},
@@ -565,6 +572,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as a CUDA graph (default for cfg5)")
     ap.add_argument("--cpu-baseline-calls", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded-fft", action="store_true", help="cfg4, N > 1: the FFT engine's transpose scheme (two all-to-alls) instead of the tridiagonal engine's segment scheme")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

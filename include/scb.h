@@ -115,6 +115,10 @@ int scb_device_count(void);
 /* Chooses the DST engine of plans created afterwards (SCB_ENGINE_*).  The reference makes the same choice at
  * compile time: SC_FFT_ENABLE, seamlessClone_imp.h:15 (cuFFT solver vs cuBLAS sine-basis solver). */
 int scb_set_engine(scb_context* ctx, int engine);
+/* Tridiagonal engine: which axis carries the FFT passes (the other one is solved as tridiagonal systems).
+ * -1 = chosen per plan by transform cost (default), 0 = along x (rows), 1 = along y (columns).  Results agree to
+ * rounding; the choice only moves time.  (No reference counterpart: its solver is fixed at compile time.) */
+int scb_set_orientation(scb_context* ctx, int orientation);
 /* Unit check of one tensor-core pass: random lines of length n against float64 direct sums; max error relative
  * to the largest output of the line.  (No reference counterpart: SC_Test, seamlessClone_imp.cpp:532-554, is dead code.) */
 int scb_tc_selftest(scb_context* ctx, int n, int lines, int transposed, double* max_rel_err);
@@ -164,6 +168,17 @@ int scb_plan_lowfreq_finish(scb_plan* plan, const double* lowrows_dev, float* lo
 /* Runs pass C for interior rows [y0, y1): reads ct_dev, writes the blend interior rows. */
 int scb_plan_rows_inverse(scb_plan* plan, const float* ct_dev, scb_image* blend, int mem_kind, int y0, int y1);
 int scb_plan_lowk(const scb_plan* plan, int* lowkx, int* lowky);
+
+/* ---- the same on the tridiagonal engine: NO transpose exchange.  The column solve is a partitioned (SPIKE) Thomas solve whose
+ * segments follow the row shards, so a rank keeps its rows from the stencil to the composed bytes; the ranks only combine
+ *   ends32 / ends64 : the two end values of every segment's local solution (3 x 16 x 2 x nx floats, ~1.5 MB at 8K), and
+ *   w               : the 32 x 32 low-frequency projections (3 x 32 x 32 doubles),
+ * each filled (zero elsewhere) by scb_plan_tri_forward so that one all-reduce(SUM) per buffer completes them.
+ * Rank r owns segments [seg0, seg1) = interior rows [seg0 * seg_len, min(ny, seg1 * seg_len)).  The plan's workspace carries
+ * the field between the two calls: run nothing else on the plan in between.  (The reference has no multi-GPU path.) */
+int scb_plan_tri_layout(const scb_plan* plan, int* seg_len, int* n_segs, size_t* ends32_floats, size_t* ends64_doubles, size_t* w_doubles);
+int scb_plan_tri_forward(scb_plan* plan, const scb_image* src, const scb_image* dst, int mem_kind, int seg0, int seg1, float* ends32_dev, double* ends64_dev, double* w_dev);
+int scb_plan_tri_finish(scb_plan* plan, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev, const double* w_dev);
 
 /* ---- the reference's four entry points (seamlessclone_cuda.h:4-63), POD views instead of cv::Mat* ---- */
 void* my_seamlessclone_api_imp_create_instance(int gpu_id);

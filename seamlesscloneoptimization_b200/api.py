@@ -76,6 +76,10 @@ class Context:
         """DST engine of plans created from now on: capi.ENGINE_AUTO / ENGINE_TRI / ENGINE_FFT / ENGINE_TC."""
         self._check(self.lib.scb_set_engine(self.handle, int(engine)))
 
+    def set_orientation(self, orientation: int):
+        """Tridiagonal engine: -1 = FFT axis chosen per plan by cost (default), 0 = FFT along x, 1 = FFT along y."""
+        self._check(self.lib.scb_set_orientation(self.handle, int(orientation)))
+
     def tc_selftest(self, n: int, lines: int, transposed: bool = False) -> float:
         err = C.c_double()
         self._check(self.lib.scb_tc_selftest(self.handle, int(n), int(lines), int(bool(transposed)), C.byref(err)))

@@ -80,6 +80,7 @@ struct scb_context {
     int device = 0;
     std::map<std::pair<int, int>, DevTriTab> tritabs;  // keyed by ROI (w, h): LU factors of the tridiagonal engine
     int engine = SCB_ENGINE_AUTO;
+    int orientation = -1;               // tridiagonal engine: -1 cost model, 0 FFT passes along x, 1 along y (scb_set_orientation)
     std::map<int, DevTcTab> tctabs;     // keyed by n (tensor-core engine: split sine bases + tensor maps)
     Lane lanes[kMaxLanes];
     int n_lanes = 0;
@@ -122,7 +123,8 @@ struct scb_plan {
     LenTabDev tx{}, ty{};
     bool use_tc = false;                // tensor-core dense engine (scb_tc.cuh) instead of the FFT engine
     bool use_tri = false;               // tridiagonal column solve (scb_tri.cuh) instead of the column FFT pass
-    TriTabDev tri{};
+    bool swap = false;                  // tridiagonal engine: FFT passes along y and the tridiagonal solve along x (choose_swap)
+    TriTabDev tri{};                    // LU factors for the chosen orientation
     const DevTcTab *ttx = nullptr, *tty = nullptr;
     const float* fx = nullptr;
     const float* fy = nullptr;
@@ -659,6 +661,12 @@ extern "C" int scb_set_engine(scb_context* c, int engine) {
     return SCB_OK;
 }
 
+extern "C" int scb_set_orientation(scb_context* c, int orientation) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (orientation < -1 || orientation > 1) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_orientation: -1 (auto), 0 (FFT along x) or 1 (FFT along y)");
+    c->orientation = orientation;
+    return SCB_OK;
+}
 extern "C" void* scb_stream(scb_context* c) { return c ? (void*)c->lanes[0].stream : nullptr; }
 extern "C" const char* scb_last_error(const scb_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 extern "C" uint64_t scb_kernel_launches(const scb_context* c) { return c ? c->launches : 0; }
@@ -715,6 +723,8 @@ extern "C" int scb_plan_destroy(scb_plan* p) {
 // before the first host sync (the reference's initMask blocks on a D2H per call: imp.cpp:1012).
 //   plan_begin : validate, stage the mask (HOST), launch the bbox reduction into slot `slot`
 //   plan_finish: (after a sync of the lane) geometry, erosion, tables
+static bool choose_swap(const scb_plan* p);
+
 struct PlanInput {
     MaskView mv;
     int px, py;
@@ -837,7 +847,8 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
         return rc;
     }
     p->use_tri = !p->use_tc && tri_eligible(c);
-    if (p->use_tri && (rc = get_tritab(c, g.w, g.h, &p->tri))) {
+    p->swap = p->use_tri && choose_swap(p);
+    if (p->use_tri && (rc = p->swap ? get_tritab(c, g.h, g.w, &p->tri) : get_tritab(c, g.w, g.h, &p->tri))) {
         scb_plan_destroy(p);
         return rc;
     }
@@ -889,6 +900,11 @@ extern "C" int scb_plan_set_debug(scb_plan* p, int on) {
     SCB_CUDA(c, cudaStreamSynchronize(p->lane->stream));
     plan_free_debug(p);
     p->debug = false;
+    if (on && !p->g.empty && p->swap) {  // the intermediates are defined in the natural orientation
+        p->swap = false;
+        int rc = get_tritab(c, p->g.w, p->g.h, &p->tri);
+        if (rc) return rc;
+    }
     if (on && !p->g.empty) {
         const size_t roi = (size_t)3 * p->g.w * p->g.h * sizeof(float), in = (size_t)3 * p->g.nx * p->g.ny * sizeof(float);
         SCB_CUDA(c, cudaMalloc(&p->dbg_vx, roi));
@@ -1029,10 +1045,13 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
         buf = a > b ? a : b;
     }
     const size_t oAt = take(buf * sizeof(float)), oCt = take(buf * sizeof(float));
-    const size_t oG = take((size_t)3 * g.ny * w->gp * sizeof(float));
-    const size_t oR = take((size_t)3 * p->lowkx * g.ny * sizeof(double));
+    const size_t gpt = align_up((size_t)g.ny, 4);
+    const size_t gN = (size_t)3 * g.ny * w->gp, gT = (size_t)3 * g.nx * gpt;
+    const size_t oG = take((p->swap && gT > gN ? gT : gN) * sizeof(float));
+    const size_t rN = (size_t)3 * p->lowkx * g.ny, rT = (size_t)3 * p->lowky * g.nx;
+    const size_t oR = take((p->swap && rT > rN ? rT : rN) * sizeof(double));
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
-    const size_t oY64 = take(p->use_tri ? (size_t)3 * g.ny * kTriLowK * sizeof(double) : 0);
+    const size_t oY64 = take(p->use_tri ? (size_t)3 * (p->swap ? g.nx : g.ny) * kTriLowK * sizeof(double) : 0);
     const size_t oW = take(p->use_tri ? (size_t)3 * kTriLowL * kTriLowK * sizeof(double) : 0);
     size_t oD = 0, oS = 0, oO = 0;
     if (host) {
@@ -1070,7 +1089,40 @@ static StencilSrc make_stencil(const scb_plan* p, const unsigned char* D, long l
     return s;
 }
 
-static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0, int y1) {
+// The tridiagonal engine transforms along ONE axis and solves tridiagonal systems along the other; which is which is
+// free.  A frame names the two roles: lines (FFT direction, length len, cnt of them per channel) and the cross direction.
+struct Frame {
+    LenTabDev tl;
+    int len, cnt, log2m, lowk;
+    const float *fl, *fc;  // OpenCV's filter along the lines / across them
+};
+static Frame frame_of(const scb_plan* p, bool swap) {
+    const scb_geometry& g = p->g;
+    if (swap) return Frame{p->ty, g.ny, g.nx, g.log2m_y, p->lowky, p->fy, p->fx};
+    return Frame{p->tx, g.nx, g.ny, g.log2m_x, p->lowkx, p->fx, p->fy};
+}
+// FFT work of the two row passes: sequences x length x log2(length); quad mode packs 4 lines per sequence, else 2.
+static double fft_cost(const LenTabDev& t, int lines) {
+    const double seqs = 3.0 * lines / (use_quad(t) ? 4.0 : 2.0);
+    return seqs * (double)(1 << t.log2m) * t.log2m;
+}
+// Lines along y when that is clearly cheaper (4K irregular mask: 1337-point lines run in quad mode, 1808-point ones
+// do not).  The transposed stencil stores and the byte-scattered compose cost a little, hence the margin.  SCB_SWAP=0|1 forces.
+static bool choose_swap(const scb_plan* p) {
+    static const int forced = [] {
+        const char* e = std::getenv("SCB_SWAP");
+        return e ? std::atoi(e) : -1;
+    }();
+    if (p->ctx->orientation >= 0) return p->ctx->orientation != 0;
+    if (forced >= 0) return forced != 0;
+    // Measured on B200 (profiles/r1_s3_ab_swap.txt): at 4K the row passes drop from 221 to 186 us with the lines along y, but the
+    // transposed stencil stores (+35 us), the longer tridiagonal chains (+25 us) and the byte-scattered compose cost more than
+    // that, so the cost model is off until those stores go through shared-memory transposes.
+    (void)fft_cost;
+    return false;
+}
+
+static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0, int y1, bool swap = false) {
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
     RhsParams rp;
@@ -1080,24 +1132,27 @@ static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0,
     rp.g = G;
     rp.gp = gp;
     rp.y0 = y0;
+    rp.transposed = swap ? 1 : 0;
+    rp.gpt = (int)align_up((size_t)p->g.ny, 4);
     const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
     SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
     c->launches++;
-    if (p->debug)  // dense [3][ny][nx] copy for scb_plan_get_intermediate
+    if (p->debug && !swap)  // dense [3][ny][nx] copy for scb_plan_get_intermediate (debug plans keep the natural orientation)
         for (int ch = 0; ch < 3; ++ch)
             cudaMemcpy2DAsync(p->dbg_rhs + ((size_t)ch * p->g.ny + y0) * p->g.nx, (size_t)p->g.nx * sizeof(float), G + ((size_t)ch * p->g.ny + y0) * gp,
                               (size_t)gp * sizeof(float), (size_t)p->g.nx * sizeof(float), (size_t)(y1 - y0), cudaMemcpyDeviceToDevice, p->lane->stream);
 }
 
-static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, const float* G, int gp, double* R, int y0, int y1, cudaStream_t stream) {
+static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, const float* G, int gp, double* R, int y0, int y1, cudaStream_t stream, bool swap = false) {
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
+    const Frame f = frame_of(p, swap);
     LowRowsParams lp;
     lp.st = st;
-    lp.sinx = p->tx.sinlow;
-    lp.nx = p->g.nx;
-    lp.ny = p->g.ny;
-    lp.lowkx = p->lowkx;
+    lp.sinx = f.tl.sinlow;
+    lp.nx = f.len;
+    lp.ny = f.cnt;
+    lp.lowkx = f.lowk;
     lp.R = R;
     lp.rhs_in = G;
     lp.rhs_pitch = gp;
@@ -1117,19 +1172,20 @@ static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec, cudaS
     SCB_LAUNCH(lowfreq_cols_kernel, dim3(3 * p->lowkx), dim3(kLowThreads), 0, stream, lc);
     c->launches++;
 }
-static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1, bool natural = false) {
+static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1, bool natural = false, bool swap = false) {
+    const Frame f = frame_of(p, swap);
     RowsFwdParams a;
     a.st = st;
-    a.tx = p->tx;
-    a.nx = p->g.nx;
-    a.ny = p->g.ny;
+    a.tx = f.tl;
+    a.nx = f.len;
+    a.ny = f.cnt;
     a.At = At;
     a.rhs_dump = nullptr;
     a.rhs_in = G;
     a.rhs_pitch = gp;
     a.y0 = y0;
     a.natural = natural ? 1 : 0;
-    launch_rows_fwd(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, a);
+    launch_rows_fwd(p->ctx, p->lane->stream, f.log2m, y1 - y0, a);
 }
 static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
     ColsParams b;
@@ -1150,61 +1206,89 @@ static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowsp
 }
 // Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][ny][nx] -> Ct [3][ny][nx]);
 // the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
-static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream) {
-    scb_context* c = p->ctx;
-    const scb_geometry& g = p->g;
-    Lane* L = p->lane;
-    cudaStream_t ms = L->stream;
+static TriLowParams tri_low_params(scb_plan* p, const Frame& f, const float* A, float* Ct, const double* R, double* Y64, double* W, int y0, int y1) {
     TriLowParams l;
-    l.nx = g.nx;
-    l.ny = g.ny;
+    l.nx = f.len;
+    l.ny = f.cnt;
     l.A = A;
     l.R = R;
-    l.lowkx = p->lowkx;
+    l.lowkx = f.lowk;
     l.Y64 = Y64;
-    l.fx = p->fx;
-    l.fy = p->fy;
+    l.fx = f.fl;
+    l.fy = f.fc;
     l.W = W;
     l.Ct = Ct;
-    const dim3 lgrid((g.ny + kTriLowRows - 1) / kTriLowRows, 3), lblock(32 * kTriLowWarps);
+    l.y0 = y0;
+    l.y1 = y1;
+    return l;
+}
+static TriSolveParams tri_solve_params(scb_plan* p, const Frame& f, const float* A, float* Ct, double* Y64) {
+    TriSolveParams t;
+    t.tab = p->tri;
+    t.nx = f.len;
+    t.ny = f.cnt;
+    t.A = A;
+    t.Ct = Ct;
+    t.Y64 = Y64;
+    t.x0 = 0;
+    t.x1 = f.len;
+    t.seg_len = tri_seg_len(f.cnt);
+    t.phase = 0;
+    t.seg0 = 0;
+    t.seg1 = kTriSegs;
+    t.ends32 = nullptr;
+    t.ends64 = nullptr;
+    return t;
+}
+static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
+    SCB_LAUNCH(tri_solve_kernel, dim3((t.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
+    p->ctx->launches++;
+}
+static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaStream_t stream) {
+    const dim3 grid((l.y1 - l.y0 + kTriLowRows - 1) / kTriLowRows, 3), block(32 * kTriLowWarps);
+    if (l.y1 <= l.y0) return;
+    if (apply)
+        SCB_LAUNCH(tri_lowapply_kernel, grid, block, 0, stream, l);
+    else
+        SCB_LAUNCH(tri_lowproj_kernel, grid, block, 0, stream, l);
+    p->ctx->launches++;
+}
+
+// Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][cnt][len] -> Ct [3][cnt][len]);
+// the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
+static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap) {
+    scb_context* c = p->ctx;
+    const Frame f = frame_of(p, swap);  // "columns" of the solve = the f.len frequencies of a line, solved across the f.cnt lines
+    Lane* L = p->lane;
+    cudaStream_t ms = L->stream;
+    const TriLowParams l = tri_low_params(p, f, A, Ct, R, Y64, W, 0, f.cnt);
     if (proj_stream != ms) {
         SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
         SCB_CUDA(c, cudaStreamWaitEvent(proj_stream, L->ev_fork, 0));
     }
     SCB_CUDA(c, cudaMemsetAsync(W, 0, (size_t)3 * kTriLowL * kTriLowK * sizeof(double), proj_stream));
-    SCB_LAUNCH(tri_lowproj_kernel, lgrid, lblock, 0, proj_stream, l);
-    c->launches++;
+    launch_tri_low(p, false, l, proj_stream);
     if (proj_stream != ms) SCB_CUDA(c, cudaEventRecord(L->ev_join, proj_stream));
-    TriSolveParams t;
-    t.tab = p->tri;
-    t.nx = g.nx;
-    t.ny = g.ny;
-    t.A = A;
-    t.Ct = Ct;
-    t.Y64 = Y64;
-    t.x0 = 0;
-    t.x1 = g.nx;
-    t.seg_len = tri_seg_len(g.ny);
-    SCB_LAUNCH(tri_solve_kernel, dim3((g.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, ms, t);
-    c->launches++;
+    launch_tri_solve(p, tri_solve_params(p, f, A, Ct, Y64));
     if (proj_stream != ms) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
-    SCB_LAUNCH(tri_lowapply_kernel, lgrid, lblock, 0, ms, l);
-    c->launches++;
+    launch_tri_low(p, true, l, ms);
     return SCB_OK;
 }
 
-static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1) {
+static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1, bool swap = false) {
+    const Frame f = frame_of(p, swap);
     RowsInvParams r;
-    r.tx = p->tx;
-    r.nx = p->g.nx;
-    r.ny = p->g.ny;
+    r.tx = f.tl;
+    r.nx = f.len;
+    r.ny = f.cnt;
     r.Ct = Ct;
     r.out = out;
     r.out_pitch = out_pitch;
     r.u_dump = p->debug ? p->dbg_u : nullptr;
-    r.inv_scale = (float)(1.0 / (double)(p->g.nx + 1));
+    r.inv_scale = (float)(1.0 / (double)(f.len + 1));
     r.y0 = y0;
-    launch_rows_inv(p->ctx, p->lane->stream, p->g.log2m_x, y1 - y0, r);
+    r.transposed = swap ? 1 : 0;
+    launch_rows_inv(p->ctx, p->lane->stream, f.log2m, y1 - y0, r);
 }
 
 // ---- tensor-core engine: the four passes + compose (scb_tc.cuh) ----
@@ -1386,6 +1470,9 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (nb > g.ny / 4) nb = g.ny / 4;
         if (nb < 1) nb = 1;
     }
+    const bool swap = p->use_tri && p->swap;  // lines along y: the stencil still runs band by band, the passes need the whole ROI
+    const Frame fr = frame_of(p, swap);
+    const int nb_out = swap ? 1 : nb;
     int yb[kMaxBands + 1];
     for (int b = 0; b <= nb; ++b) yb[b] = (b == nb) ? g.ny : (int)(((long long)g.ny * b / nb) & ~3LL);  // multiples of 4: whole quads
     const bool side_copy = !host && copy_dst && !tm.on;
@@ -1422,23 +1509,24 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         c->launches++;
     }
     tm.mark(ST_IN);
+    const int gpl = swap ? (int)align_up((size_t)g.ny, 4) : w.gp;  // pitch of a line of G in the solve's frame
     if (nb == 1) {
-        run_rhs(p, st, w.G, w.gp, 0, g.ny);
+        run_rhs(p, st, w.G, w.gp, 0, g.ny, swap);
     } else {
         for (int b = 0; b < nb; ++b) {
             SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
-            run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1]);
-            if (b + 1 < nb) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
+            run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1], swap);
+            if (b + 1 < nb && !swap) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
         }
     }
     tm.mark(ST_RHS);
     if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, ms);
+        run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, ms, swap);
         if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, ms);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
         SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
         SCB_CUDA(c, cudaStreamWaitEvent(L->side, L->ev_fork, 0));
-        run_lowfreq_rows(p, st, w.G, w.gp, w.R, 0, g.ny, L->side);
+        run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, L->side, swap);
         if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, L->side);
         SCB_CUDA(c, cudaEventRecord(L->ev_join, L->side));
         if (side_copy) {  // blend = dst.copy() rides along on the side stream; only the compose pass has to wait for it
@@ -1454,17 +1542,17 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
-        run_rows_fwd(p, st, w.G, w.gp, w.At, yb[nb - 1], g.ny, p->use_tri);
+        run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
         if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
         if (p->use_tri) {
-            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, tm.on ? ms : L->side))) return rc;
+            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, tm.on ? ms : L->side, swap))) return rc;
         } else
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
-        if (nb == 1) {
-            run_rows_inv(p, w.Ct, out, out_pitch, 0, g.ny);
+        if (nb_out == 1) {
+            run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
         } else {
             for (int b = 0; b < nb; ++b) {
                 run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
@@ -1481,7 +1569,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     SCB_CUDA(c, cudaGetLastError());
     if (host) {
         // only the ROI interior comes back; everything else of blend is copied from dst on the host while the GPU works
-        if (nb == 1) SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, ms));
+        if (nb_out == 1) SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, ms));
         tm.mark(ST_OUT);
         if (!defer_host) {
             if (copy_dst) host_copy_outside(dst, blend, g, host_threads());
@@ -1763,6 +1851,97 @@ extern "C" int scb_plan_rows_inverse(scb_plan* p, const float* ct_dev, scb_image
     const scb_geometry& g = p->g;
     unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
     run_rows_inv(p, ct_dev, bInt, blend->stride, y0, y1);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+// ---- row-sharded solve on the tridiagonal engine -------------------------------------------------
+// A rank owns the segments [seg0, seg1) of every spectral column = the interior rows [seg0 L, min(ny, seg1 L)).  Nothing of
+// the field ever moves between the ranks: the partitioned Thomas solve (scb_tri.cuh) couples the ranks only through the two
+// end values of every segment's local solution and through the 32 x 32 low-frequency projections.
+static int tri_shard_check(scb_plan* p, int seg0, int seg1, int* y0, int* y1) {
+    scb_context* c = p->ctx;
+    if (p->g.empty) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan");
+    if (!p->use_tri || p->swap) return fail(c, SCB_ERR_UNSUPPORTED, "sharded tridiagonal solve: the plan must use SCB_ENGINE_TRI in its natural orientation");
+    const int L = tri_seg_len(p->g.ny), nseg = (p->g.ny + L - 1) / L;
+    if (seg0 < 0 || seg1 < seg0 || seg1 > nseg) return fail(c, SCB_ERR_INVALID_ARGUMENT, "sharded tridiagonal solve: segment range outside [0, n_segs]");
+    *y0 = seg0 * L;
+    *y1 = seg1 * L < p->g.ny ? seg1 * L : p->g.ny;
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_tri_layout(const scb_plan* p, int* seg_len, int* n_segs, size_t* ends32_floats, size_t* ends64_doubles, size_t* w_doubles) {
+    if (!p || p->g.empty) return SCB_ERR_INVALID_ARGUMENT;
+    const int L = tri_seg_len(p->g.ny);
+    if (seg_len) *seg_len = L;
+    if (n_segs) *n_segs = (p->g.ny + L - 1) / L;
+    if (ends32_floats) *ends32_floats = (size_t)3 * kTriSegs * 2 * align_up((size_t)p->g.nx, 4);
+    if (ends64_doubles) *ends64_doubles = (size_t)3 * kTriSegs * 2 * kTriLowK;
+    if (w_doubles) *w_doubles = (size_t)3 * kTriLowL * kTriLowK;
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_tri_forward(scb_plan* p, const scb_image* src, const scb_image* dst, int mem_kind, int seg0, int seg1, float* ends32_dev, double* ends64_dev,
+                                    double* w_dev) {
+    if (!p || !ends32_dev || !ends64_dev || !w_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_UNSUPPORTED, "sharded solve: images must be device resident");
+    int rc, y0, y1;
+    if ((rc = tri_shard_check(p, seg0, seg1, &y0, &y1))) return rc;
+    if ((rc = check_image(c, src, p->src_rows, p->src_cols, "src"))) return rc;
+    if ((rc = check_image(c, dst, p->dst_rows, p->dst_cols, "dst"))) return rc;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const scb_geometry& g = p->g;
+    const unsigned char* dROI = (const unsigned char*)dst->data + (size_t)g.ry * dst->stride + (size_t)3 * g.rx;
+    const unsigned char* sROI = (const unsigned char*)src->data + (size_t)g.y * src->stride + (size_t)3 * g.x;
+    StencilSrc st = make_stencil(p, dROI, dst->stride, sROI, src->stride);
+    Workspace w;
+    if ((rc = carve(p, false, &w))) return rc;
+    cudaStream_t ms = p->lane->stream;
+    size_t n32, n64, nw;
+    scb_plan_tri_layout(p, nullptr, nullptr, &n32, &n64, &nw);
+    // zero-filled so that the ranks can combine their parts with a plain sum
+    SCB_CUDA(c, cudaMemsetAsync(ends32_dev, 0, n32 * sizeof(float), ms));
+    SCB_CUDA(c, cudaMemsetAsync(ends64_dev, 0, n64 * sizeof(double), ms));
+    SCB_CUDA(c, cudaMemsetAsync(w_dev, 0, nw * sizeof(double), ms));
+    run_rhs(p, st, w.G, w.gp, y0, y1);
+    run_lowfreq_rows(p, st, w.G, w.gp, w.R, y0, y1, ms);
+    run_rows_fwd(p, st, w.G, w.gp, w.At, y0, y1, /*natural=*/true);
+    const Frame f = frame_of(p, false);
+    launch_tri_low(p, false, tri_low_params(p, f, w.At, w.Ct, w.R, w.Y64, w_dev, y0, y1), ms);
+    TriSolveParams t = tri_solve_params(p, f, w.At, w.Ct, w.Y64);
+    t.phase = 1;
+    t.seg0 = seg0;
+    t.seg1 = seg1;
+    t.ends32 = ends32_dev;
+    t.ends64 = ends64_dev;
+    if (seg1 > seg0) launch_tri_solve(p, t);
+    SCB_CUDA(c, cudaGetLastError());
+    return SCB_OK;
+}
+
+extern "C" int scb_plan_tri_finish(scb_plan* p, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev, const double* w_dev) {
+    if (!p || !ends32_dev || !ends64_dev || !w_dev) return SCB_ERR_INVALID_ARGUMENT;
+    scb_context* c = p->ctx;
+    if (mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_UNSUPPORTED, "sharded solve: images must be device resident");
+    int rc, y0, y1;
+    if ((rc = tri_shard_check(p, seg0, seg1, &y0, &y1))) return rc;
+    if ((rc = check_image(c, blend, p->dst_rows, p->dst_cols, "blend"))) return rc;
+    SCB_CUDA(c, cudaSetDevice(c->device));
+    const scb_geometry& g = p->g;
+    Workspace w;
+    if ((rc = carve(p, false, &w))) return rc;  // same arena, same offsets as in scb_plan_tri_forward
+    const Frame f = frame_of(p, false);
+    TriSolveParams t = tri_solve_params(p, f, w.At, w.Ct, w.Y64);
+    t.phase = 2;
+    t.seg0 = seg0;
+    t.seg1 = seg1;
+    t.ends32 = const_cast<float*>(ends32_dev);
+    t.ends64 = const_cast<double*>(ends64_dev);
+    if (seg1 > seg0) launch_tri_solve(p, t);
+    launch_tri_low(p, true, tri_low_params(p, f, w.At, w.Ct, w.R, w.Y64, const_cast<double*>(w_dev), y0, y1), p->lane->stream);
+    unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
+    run_rows_inv(p, w.Ct, bInt, blend->stride, y0, y1);
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }

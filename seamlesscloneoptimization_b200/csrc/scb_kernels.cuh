@@ -102,7 +102,22 @@ struct RhsParams {
     float* g;  // [3][ny][gp]
     int gp;    // row pitch of g in floats, multiple of 4
     int y0;    // first interior row of this launch
+    int transposed;  // 1: store g as [3][nx][gpt] (lines along y: the solve runs its FFT passes along y, scb_api.cu choose_swap)
+    int gpt;         // line pitch of the transposed layout in floats
 };
+
+// four consecutive pixels x0..x0+3 of row y, channel c
+SCB_D void rhs_store4(const RhsParams& p, int c, int x0, int y, float a, float b, float d, float e) {
+    if (!p.transposed) {
+        *reinterpret_cast<float4*>(p.g + ((size_t)c * p.ny + y) * p.gp + x0) = make_float4(a, b, d, e);
+    } else {
+        float* o = p.g + ((size_t)c * p.nx + x0) * p.gpt + y;
+        o[0] = a;
+        o[(size_t)p.gpt] = b;
+        o[2 * (size_t)p.gpt] = d;
+        o[3 * (size_t)p.gpt] = e;
+    }
+}
 
 template <int N>
 SCB_D void load_unaligned_words(const unsigned char* p, unsigned (&out)[N]) {
@@ -131,7 +146,10 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
         for (int k = 0; k < 4; ++k) {
             float g[3] = {0.f, 0.f, 0.f};
             if (x0 + k < p.nx) rhs_pixel(s, x0 + k, y, g);
-            if (x0 + k < p.gp) {
+            if (p.transposed) {
+                if (x0 + k < p.nx)
+                    for (int c = 0; c < 3; ++c) p.g[((size_t)c * p.nx + x0 + k) * p.gpt + y] = g[c];
+            } else if (x0 + k < p.gp) {
                 g0[k] = g[0];
                 g0[plane + k] = g[1];
                 g0[2 * plane + k] = g[2];
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
                 }
             }
             SCB_UNROLL
-            for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(g0 + c * plane) = make_float4(o[c], o[3 + c], o[6 + c], o[9 + c]);
+            for (int c = 0; c < 3; ++c) rhs_store4(p, c, x0, y, o[c], o[3 + c], o[6 + c], o[9 + c]);
             return;
         }
     }
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
         }
     }
     SCB_UNROLL
-    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(g0 + c * plane) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+    for (int c = 0; c < 3; ++c) rhs_store4(p, c, x0, y, out[c][0], out[c][1], out[c][2], out[c][3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,6 +394,7 @@ struct RowsInvParams {
     float* u_dump;       // [3][ny][nx] solved field before clamp/truncate, or null
     float inv_scale;     // 1 / (nx + 1)
     int y0;
+    int transposed;      // 1: the lines run along y of the image: line L, position k -> pixel (row k, column L)
 };
 
 SCB_D unsigned char compose_u8(float v) {
@@ -402,12 +421,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_inv_kernel(RowsInvParam
         fft_convolve<LOG2M, NCH>(buf, p.tx.tw, p.tx.bhat_t, tid);
         for (int k = tid + 1; k <= n; k += C::T) {
             const float2 ch = __ldg(p.tx.chirp + k);
-            unsigned char* px = p.out + (long long)y * p.out_pitch + 3 * (k - 1);
+            unsigned char* px = p.transposed ? p.out + (long long)(k - 1) * p.out_pitch + 3 * y : p.out + (long long)y * p.out_pitch + 3 * (k - 1);
             SCB_UNROLL
             for (int c = 0; c < NCH; ++c) {
                 const float2 v = buf[c * C::PADDED + padi(k)];
                 const float u = (ch.x * v.y + ch.y * v.x) * p.inv_scale;
-                if (p.u_dump) p.u_dump[((size_t)(c0 + c) * p.ny + y) * p.nx + (k - 1)] = u;
+                if (p.u_dump) p.u_dump[p.transposed ? ((size_t)(c0 + c) * p.nx + (k - 1)) * p.ny + y : ((size_t)(c0 + c) * p.ny + y) * p.nx + (k - 1)] = u;
                 px[c0 + c] = compose_u8(u);
             }
         }

@@ -216,12 +216,13 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_inv3_kernel(RowsInv3Param
         const float2 s = chirp_imag2(__ldg(p.tx.chirp + k), v);
         const float ua = s.x * p.inv_scale, ub = s.y * p.inv_scale;
         if (p.u_dump) {
-            p.u_dump[((size_t)c * p.ny + y0) * p.nx + (k - 1)] = ua;
-            if (has1) p.u_dump[((size_t)c * p.ny + y1) * p.nx + (k - 1)] = ub;
+            const size_t d0 = p.transposed ? ((size_t)c * p.nx + (k - 1)) * p.ny + y0 : ((size_t)c * p.ny + y0) * p.nx + (k - 1);
+            p.u_dump[d0] = ua;
+            if (has1) p.u_dump[d0 + (p.transposed ? 1 : p.nx)] = ub;
         }
-        unsigned char* o = p.out + (long long)y0 * p.out_pitch + 3 * (k - 1) + c;
+        unsigned char* o = p.transposed ? p.out + (long long)(k - 1) * p.out_pitch + 3 * y0 + c : p.out + (long long)y0 * p.out_pitch + 3 * (k - 1) + c;
         o[0] = compose_u8(ua);
-        if (has1) o[p.out_pitch] = compose_u8(ub);
+        if (has1) o[p.transposed ? 3 : p.out_pitch] = compose_u8(ub);
     };
     gpass<LOG2M, C::R0, C::M, false>(g.gtw, g.gtid, load, SmemOut{g.pl});
     gconv_core<LOG2M>(g.gtw, p.tx.bhat_t, g.gtid, g.group, g.pl);
@@ -401,12 +402,13 @@ __global__ void __launch_bounds__(GCfg<LOG2M>::T) rows_inv4_kernel(RowsInv3Param
     for (int k = 1 + g.gtid; k <= n; k += C::G) {
         const P4 t = quad_unpack<LOG2M>(g.pl, __ldg(p.tx.chirp + k), k);
         const float u[4] = {t.im.x * hs, -t.re.x * hs, t.im.y * hs, -t.re.y * hs};
-        unsigned char* o = p.out + (long long)y0 * p.out_pitch + 3 * (k - 1) + c;
+        unsigned char* o = p.transposed ? p.out + (long long)(k - 1) * p.out_pitch + 3 * y0 + c : p.out + (long long)y0 * p.out_pitch + 3 * (k - 1) + c;
+        const long long ostep = p.transposed ? 3 : p.out_pitch;
         SCB_UNROLL
         for (int i = 0; i < 4; ++i) {
             if (i < nl) {
-                if (p.u_dump) p.u_dump[((size_t)c * p.ny + y0 + i) * p.nx + (k - 1)] = u[i];
-                o[(long long)i * p.out_pitch] = compose_u8(u[i]);
+                if (p.u_dump) p.u_dump[p.transposed ? ((size_t)c * p.nx + (k - 1)) * p.ny + y0 + i : ((size_t)c * p.ny + y0 + i) * p.nx + (k - 1)] = u[i];
+                o[(long long)i * ostep] = compose_u8(u[i]);
             }
         }
     }

@@ -96,6 +96,13 @@ struct TriSolveParams {
     double* Y64;       // [3][ny][kTriLowK] float64 work / result columns k < kTriLowK
     int x0, x1;        // columns of this launch (x0 a multiple of kTriCols)
     int seg_len;       // tri_seg_len(ny)
+    // Row-sharded solves (one rank per GPU owns the segments [seg0, seg1) of every column):
+    //   phase 0  everything in one launch (seg0 = 0, seg1 = all)
+    //   phase 1  pass 1 of the own segments; their local-solution ends go to `ends32` / `ends64`
+    //   phase 2  (after the ranks have exchanged the ends) reduced systems, then pass 2 of the own segments
+    int phase, seg0, seg1;
+    float* ends32;     // [3][kTriSegs][2][pm]        w_last, w_first of every segment, columns >= kTriLowK
+    double* ends64;    // [3][kTriSegs][2][kTriLowK]  the same for the float64 columns
 };
 
 // Partitioned (SPIKE) Thomas solve of M u = a, M = tridiag(-1, beta, -1), one thread per (column, segment):
@@ -111,13 +118,15 @@ struct TriIo;  // global-memory views of one column: a(y), v/u(y) and the tables
 
 template <class T, class LoadA, class LoadM, class LoadP, class LoadV, class StoreV>
 SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][kTriSegs][32] */, const LoadA& load_a, const LoadM& load_m, const LoadP& load_p,
-                        const LoadV& load_v, const StoreV& store_v, bool active) {
+                        const LoadV& load_v, const StoreV& store_v, bool active, int phase, int seg0, int seg1, T* ends /* global [kTriSegs][2][estride] + column, or null */,
+                        size_t estride) {
     const int r0 = seg * L;
-    const int len = (seg < nseg) ? ((n - r0 < L) ? n - r0 : L) : 0;
+    const bool mine = seg >= seg0 && seg < seg1 && seg < nseg;
+    const int len = mine ? ((n - r0 < L) ? n - r0 : L) : 0;
     T* wl = sm + (0 * kTriSegs + seg) * 32 + lane;
     T* wf = sm + (1 * kTriSegs + seg) * 32 + lane;
     // ---- pass 1 ----
-    if (active && len > 0) {
+    if (active && len > 0 && phase != 2) {
         T v = load_a(r0), b = load_a(r0 + len - 1);
         store_v(r0, v);
         int d = 1;
@@ -143,8 +152,20 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
             store_v(r0 + d, v);
         }
         const T ml = load_m(len - 1);
-        *wl = ml * v;
-        *wf = ml * b;
+        if (phase == 1) {
+            ends[((size_t)seg * 2 + 0) * estride] = ml * v;
+            ends[((size_t)seg * 2 + 1) * estride] = ml * b;
+        } else {
+            *wl = ml * v;
+            *wf = ml * b;
+        }
+    }
+    if (phase == 1) return;
+    if (phase == 2) {  // every segment's ends, gathered from all ranks
+        if (active && seg < nseg) {
+            *wl = ends[((size_t)seg * 2 + 0) * estride];
+            *wf = ends[((size_t)seg * 2 + 1) * estride];
+        }
     }
     __syncthreads();
     // ---- reduced system: thread (lane, seg 0) of every column ----
@@ -235,7 +256,8 @@ __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolve
             [&](int d) { return __ldg(m + (size_t)d * kTriLowK); },
             [&](int d) { return __ldg(P + (size_t)d * kTriLowK); },
             [&](int y) { return Y[(size_t)y * kTriLowK]; },
-            [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; }, active);
+            [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; }, active, p.phase, p.seg0, p.seg1,
+            p.ends64 ? p.ends64 + (size_t)c * kTriSegs * 2 * kTriLowK + k : nullptr, (size_t)kTriLowK);
     } else {
         const float* m = p.tab.m32 + k;
         const float* P = p.tab.p32 + k;
@@ -246,7 +268,8 @@ __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolve
             [&](int d) { return __ldg(m + (size_t)d * pm); },
             [&](int d) { return __ldg(P + (size_t)d * pm); },
             [&](int y) { return Ct[(size_t)y * p.nx]; },
-            [&](int y, float v) { Ct[(size_t)y * p.nx] = v; }, active);
+            [&](int y, float v) { Ct[(size_t)y * p.nx] = v; }, active, p.phase, p.seg0, p.seg1,
+            p.ends32 ? p.ends32 + (size_t)c * kTriSegs * 2 * pm + k : nullptr, (size_t)pm);
     }
 }
 
@@ -270,6 +293,7 @@ struct TriLowParams {
     const float* fy;       // OpenCV filter_Y (ny)
     double* W;             // [3][kTriLowL][kTriLowK], zeroed before tri_lowproj_kernel
     float* Ct;             // [3][ny][nx]
+    int y0, y1;            // rows of this launch (row-sharded solves: the own rows; W then holds a partial sum)
 };
 
 static constexpr int kTriLowWarps = 8;
@@ -288,8 +312,8 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj_kernel(TriLowPa
     double tf[kTriLowL], te[kTriLowL];  // <sin_l, a_fft>, <sin_l, a_exact - a_fft>
     SCB_UNROLL
     for (int l = 0; l < kTriLowL; ++l) tf[l] = te[l] = 0.0;
-    const int yb = blockIdx.x * kTriLowRows;
-    for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
+    const int yb = p.y0 + blockIdx.x * kTriLowRows;
+    for (int y = yb + warp; y < yb + kTriLowRows && y < p.y1; y += kTriLowWarps) {
         const double af = kin ? (double)__ldg(p.A + ((size_t)c * n + y) * p.nx + k) : 0.0;
         const double dx = has_r ? -2.0 * __ldg(p.R + ((size_t)c * p.lowkx + k) * n + y) - af : 0.0;
         // sin(pi (y+1)(l+1) / N), l = 0.., by the three-term recurrence s_(l+1) = 2 cos(phi) s_l - s_(l-1) in float64
@@ -334,8 +358,8 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowP
     double w[kTriLowL];
     SCB_UNROLL
     for (int l = 0; l < kTriLowL; ++l) w[l] = (l < L) ? p.W[((size_t)c * kTriLowL + l) * kTriLowK + k] : 0.0;
-    const int yb = blockIdx.x * kTriLowRows;
-    for (int y = yb + warp; y < yb + kTriLowRows && y < n; y += kTriLowWarps) {
+    const int yb = p.y0 + blockIdx.x * kTriLowRows;
+    for (int y = yb + warp; y < yb + kTriLowRows && y < p.y1; y += kTriLowWarps) {
         double sum = p.Y64[((size_t)c * n + y) * kTriLowK + k];
         const double ph = (double)(y + 1) / (double)(n + 1);
         const double twoc = 2.0 * cospi(ph);

@@ -1,5 +1,14 @@
 """One large solve sharded over the ranks of a torch.distributed group (BASELINE cfg4).
 
+Two schemes, chosen by the plan's engine:
+
+  tridiagonal engine (default) -- ShardedSolve runs scb_plan_tri_forward / scb_plan_tri_finish: rank r keeps its rows from the
+  stencil to the composed bytes.  The column solve is a partitioned (SPIKE) Thomas solve whose segments follow the row shards,
+  so the ranks only combine the segment-end values (3 x 16 x 2 x nx floats) and the 32 x 32 low-frequency projections with two
+  small all-reduces.  No transpose, no all-to-all: 1.5 MB instead of 2 x 200 MB at 8K.
+
+  FFT engine -- the transpose scheme below (two all-to-alls):
+
   rank r owns interior rows [ys[r], ys[r+1]) for the row passes and columns [xs[r], xs[r+1]) for the
   column pass; between the passes the row-transformed field is exchanged with an all-to-all:
 
@@ -46,6 +55,19 @@ class ShardedSolve:
             raise capi.ScbError(capi.SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan")
         self.nx, self.ny = int(g.nx), int(g.ny)
         self.ys, self.xs = split(self.ny, self.world), split(self.nx, self.world)
+        self.tri = plan.engine == capi.ENGINE_TRI
+        if self.tri:
+            seg_len, n_segs = C.c_int(), C.c_int()
+            n32, n64, nw = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            ctx._check(ctx.lib.scb_plan_tri_layout(plan.handle, C.byref(seg_len), C.byref(n_segs), C.byref(n32), C.byref(n64), C.byref(nw)))
+            self.seg_len, self.n_segs = seg_len.value, n_segs.value
+            self.segs = split(self.n_segs, self.world)  # rank r owns segments [segs[r], segs[r+1])
+            self.ys = [min(self.ny, s * self.seg_len) for s in self.segs]
+            self.ends32 = torch.zeros(n32.value, dtype=torch.float32, device=device)
+            self.f64 = torch.zeros(n64.value + nw.value, dtype=torch.float64, device=device)  # ends64 | w: one all-reduce
+            self.n64 = n64.value
+            self.exchange_bytes = 4 * n32.value + 8 * (n64.value + nw.value)
+            return
         lkx, lky = C.c_int(), C.c_int()
         ctx._check(ctx.lib.scb_plan_lowk(plan.handle, C.byref(lkx), C.byref(lky)))
         self.lowkx, self.lowky = lkx.value, lky.value
@@ -104,6 +126,15 @@ class ShardedSolve:
         of `blend` are solved; blend must already hold a copy of dst (or alias it)."""
         lib, ph, r = self.ctx.lib, self.plan.handle, self.rank
         chk = self.ctx._check
+        if self.tri:
+            s0, s1 = self.segs[r], self.segs[r + 1]
+            e32, e64, wd = self.ends32.data_ptr(), self.f64.data_ptr(), self.f64.data_ptr() + 8 * self.n64
+            chk(lib.scb_plan_tri_forward(ph, C.byref(src_view), C.byref(dst_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
+            if self.world > 1:  # every rank filled only its own segments / summed only its own rows: zeros elsewhere
+                dist.all_reduce(self.ends32, group=self.group)
+                dist.all_reduce(self.f64, group=self.group)
+            chk(lib.scb_plan_tri_finish(ph, C.byref(blend_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
+            return
         y0, y1, x0, x1 = self.ys[r], self.ys[r + 1], self.xs[r], self.xs[r + 1]
         self.lowrows.zero_()
         chk(lib.scb_plan_rows_forward(ph, C.byref(src_view), C.byref(dst_view), capi.MEM_DEVICE, y0, y1, self.At.data_ptr(), self.lowrows.data_ptr()))

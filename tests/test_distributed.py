@@ -25,14 +25,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, lib_path, out_dir):
+def _worker(rank, world, port, lib_path, out_dir, engine):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         src, dst, mask, p = so.make_config("small", 12)
         ctx = scb.Context(0, lib_path=lib_path)
-        ctx.set_engine(capi.ENGINE_FFT)  # the sharded passes are the FFT engine's
+        ctx.set_engine(engine)
         hm, hs, hd = (np.ascontiguousarray(a) for a in (mask, src, dst))
         plan = scb.Plan(ctx, capi.host_view(hm), src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
         blend = torch.from_numpy(dst.copy())
@@ -48,12 +48,14 @@ def _worker(rank, world, port, lib_path, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_solve_over_gloo(tmp_path, emu_lib, world):
+@pytest.mark.parametrize("engine", [capi.ENGINE_TRI, capi.ENGINE_FFT], ids=["tri-segments", "fft-transpose"])
+def test_sharded_solve_over_gloo(tmp_path, emu_lib, world, engine):
+    """tri: row shards = segment groups of the partitioned Thomas solve, two small all-reduces;  fft: two all-to-all transposes."""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, emu_lib, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, emu_lib, str(tmp_path), engine), nprocs=world, join=True)
     src, dst, mask, p = so.make_config("small", 12)
     with scb.Context(0, lib_path=emu_lib) as ctx:
-        ctx.set_engine(capi.ENGINE_FFT)
+        ctx.set_engine(engine)
         single = ctx.seamless_clone(src, dst, mask, p)
     for r in range(world):
         got = np.load(tmp_path / f"blend_{r}.npy")

@@ -487,3 +487,42 @@ def test_banded_host_transfers_equal_single_shot(be, ctx, monkeypatch):
         got = plan.execute(src, dst)
         assert np.array_equal(got, ref), nb
     plan.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# tridiagonal engine: both orientations (FFT passes along x or along y) give the same image
+@pytest.mark.parametrize("w,h", [(10, 18), (44, 45), (131, 20), (20, 259), (66, 140)])
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_tri_orientations_agree_with_oracle(be, w, h, mem, monkeypatch):
+    rng = np.random.default_rng(77 * w + h)
+    ws, hs = w + 2, h + 2
+    src = so.smooth_rand(rng, hs, ws, 2.0)
+    dst = so.smooth_rand(rng, hs + 5, ws + 7, 2.0)
+    mask = np.full((hs, ws), 255, np.uint8)
+    mask[:3, :5] = 0  # not a plain rectangle: part of the ROI keeps dst gradients
+    p = (3 + w // 2 + 1, 2 + h // 2 + 1)
+    ref = so.restate(src, dst, mask, p, transform="f64")
+    if mem == "host":
+        monkeypatch.setenv("SCB_BANDS", "3")  # banded uploads with the passes along y
+    ctx = be.context()
+    try:
+        ctx.set_engine(capi.ENGINE_TRI)
+        outs = []
+        for orientation in (0, 1):
+            ctx.set_orientation(orientation)
+            plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+            if mem == "host":
+                blend = plan.execute(src, dst)
+            else:
+                vs, hs_ = be.to_device(src)
+                vd, hd = be.to_device(dst)
+                vb, hb = be.to_device(np.zeros_like(dst))
+                ctx._check(ctx.lib.scb_plan_execute(plan.handle, C.byref(vs), C.byref(vd), C.byref(vb), scb.MEM_DEVICE, scb.EXEC_DEFAULT))
+                ctx.sync()
+                blend = be.to_host(hb)
+            assert_matches(blend, ref.blend, plan.geometry, f"orientation {orientation}", ref.solved)
+            outs.append(blend)
+            plan.close()
+        assert int((outs[0] != outs[1]).sum()) <= common.allowed_mismatches(roi_interior(outs[0], ref.geom).size)
+    finally:
+        ctx.close()
