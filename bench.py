@@ -513,15 +513,18 @@ def sharded_leg(env: Env, args):
         sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in evs]
         total_ms_max, = env.max_over_ranks(sum(step_ms))
-        # e2e: pinned host inputs -> device -> sharded solve -> own row slab back to the host
+        # e2e: pinned host inputs -> device -> sharded solve -> own row slab back to the host.  A rank moves only the rows of
+        # src / dst its shard reads (own interior rows + the one-row halo of the stencil).
         h_src, h_dst = env.pinned(src), env.pinned(dst)
         y0, y1 = solve.ys[env.rank], solve.ys[env.rank + 1]
         h_rows = torch.empty((y1 - y0, g.nx, 3), dtype=torch.uint8, pin_memory=True)
+        s0, s1 = g.y + y0, g.y + y1 + 2
+        t0_, t1_ = g.ry + y0, g.ry + y1 + 2
 
         def e2e_step():
-            d_src.copy_(h_src, non_blocking=True)
-            d_dst.copy_(h_dst, non_blocking=True)
-            d_blend.copy_(d_dst, non_blocking=True)
+            d_src[s0:s1].copy_(h_src[s0:s1], non_blocking=True)
+            d_dst[t0_:t1_].copy_(h_dst[t0_:t1_], non_blocking=True)
+            d_blend[t0_:t1_].copy_(d_dst[t0_:t1_], non_blocking=True)
             solve.run(vs, vd, vb)
             h_rows.copy_(d_blend[g.ry + 1 + y0 : g.ry + 1 + y1, g.rx + 1 : g.rx + 1 + g.nx], non_blocking=True)
             torch.cuda.synchronize()
@@ -552,8 +555,8 @@ def sharded_leg(env: Env, args):
                        "l2": "256 MiB flush write between timed steps", "parallelism": par,
                        "bytes_exchanged_per_rank_per_step": int(xbytes)},
             "clocks": sampler.summary(),
-            "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(src.size + dst.size), "d2h_bytes_per_step": int(h_rows.numel()),
-                    "ms_per_step": e2e_ms_max / args.steps, "call": "pinned src+dst H2D per rank, ShardedSolve.run, own row slab D2H"},
+            "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int((s1 - s0) * src.shape[1] * 3 + (t1_ - t0_) * dst.shape[1] * 3), "d2h_bytes_per_step": int(h_rows.numel()),
+                    "ms_per_step": e2e_ms_max / args.steps, "call": "pinned H2D of the shard's src+dst rows (rank 0's byte counts), ShardedSolve.run, own row slab D2H"},
             "gpu_launches": int(launches), "p50_ms_device": statistics.median(step_ms),
         }
     plan.close()
