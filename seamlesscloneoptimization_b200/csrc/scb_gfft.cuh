@@ -116,12 +116,16 @@ SCB_HD constexpr int gtw_total_c(int log2m) { return gtw_offset16(log2m, 16); }
 #ifndef SCB_NG1_FROM
 #define SCB_NG1_FROM 9
 #endif
+#ifndef SCB_G1_FROM
+#define SCB_G1_FROM 12
+#endif
 template <int LOG2M>
 struct GCfg {
     static_assert(LOG2M >= 5 && LOG2M <= 13, "group engine: convolution lengths 32 .. 8192");
     static constexpr int M = 1 << LOG2M;
     static constexpr int R0 = (LOG2M % 4 == 0) ? 16 : (1 << (LOG2M % 4));
-    static constexpr int G = (M / 32 < 32) ? 32 : (M / 32);  // threads per group: two radix-16 butterflies each
+    // threads per group: two radix-16 butterflies each; from 2^SCB_G1_FROM points up ONE butterfly each (twice the warps)
+    static constexpr int G = (LOG2M >= SCB_G1_FROM) ? (M / 16) : ((M / 32 < 32) ? 32 : (M / 32));
     static constexpr int PADDED = M + (M >> 4);              // float2 elements per plane
     static constexpr int NG = (LOG2M < SCB_NG1_FROM) ? 3 : 1;  // groups (channels) per CTA; from 2^SCB_NG1_FROM points up: one pair per CTA, blockIdx.y = channel
     static constexpr int T = NG * G;
