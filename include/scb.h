@@ -47,14 +47,19 @@ enum {
     SCB_OK = 0,
     SCB_ERR_INVALID_ARGUMENT = 1,  /* null pointers, wrong channel counts, sizes that disagree   */
     SCB_ERR_ROI_OUT_OF_BOUNDS = 2, /* OpenCV: (-215) assertion on roi inside dst                 */
-    SCB_ERR_UNSUPPORTED = 3,       /* flags != NORMAL_CLONE, ROI side > 8194, bbox smaller than 3 */
+    SCB_ERR_UNSUPPORTED = 3,       /* unknown clone flags, ROI side > 8194, bbox smaller than 3  */
     SCB_ERR_CUDA = 4,              /* a CUDA call failed; scb_last_error has the text            */
     SCB_ERR_NO_DEVICE = 5,
     SCB_ERR_OUT_OF_MEMORY = 6
 };
 
-/* cv::seamlessClone flags (photo.hpp); only NORMAL_CLONE is implemented */
-enum { SCB_NORMAL_CLONE = 1, SCB_MIXED_CLONE = 2, SCB_MONOCHROME_TRANSFER = 3 };
+/* cv::seamlessClone flags (photo.hpp).  NORMAL_CLONE is the hot path (vectorised integer stencil); MIXED_CLONE and
+ * MONOCHROME_TRANSFER run the same solver behind a per-pixel float stencil with OpenCV's gradient selection; the _WIDE
+ * variants (OpenCV >= 4.11) place the centre of src, instead of the centre of the mask bounding box, at p. */
+enum {
+    SCB_NORMAL_CLONE = 1, SCB_MIXED_CLONE = 2, SCB_MONOCHROME_TRANSFER = 3,
+    SCB_NORMAL_CLONE_WIDE = 9, SCB_MIXED_CLONE_WIDE = 10, SCB_MONOCHROME_TRANSFER_WIDE = 11
+};
 
 /* where the pixel buffers of a call live */
 enum { SCB_MEM_HOST = 0, SCB_MEM_DEVICE = 1 };
@@ -130,6 +135,9 @@ int scb_host_free(void* p);
 /* ---- plan: everything that depends on (mask, sizes, p) only ---- */
 int scb_plan_create(scb_context* ctx, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
                     int dst_rows, int dst_cols, int px, int py, scb_plan** out);
+/* The same with cv::seamlessClone's `flags` (SCB_*_CLONE*); scb_plan_create == NORMAL_CLONE. */
+int scb_plan_create_ex(scb_context* ctx, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                       int dst_rows, int dst_cols, int px, int py, int clone_flags, scb_plan** out);
 int scb_plan_destroy(scb_plan* plan);
 int scb_plan_geometry(const scb_plan* plan, scb_geometry* out);
 int scb_plan_engine(const scb_plan* plan); /* SCB_ENGINE_TRI, SCB_ENGINE_FFT or SCB_ENGINE_TC */

@@ -24,7 +24,10 @@
 
 namespace scb {
 
-enum { NORMAL_CLONE = SCB_NORMAL_CLONE, MIXED_CLONE = SCB_MIXED_CLONE, MONOCHROME_TRANSFER = SCB_MONOCHROME_TRANSFER };
+enum {
+    NORMAL_CLONE = SCB_NORMAL_CLONE, MIXED_CLONE = SCB_MIXED_CLONE, MONOCHROME_TRANSFER = SCB_MONOCHROME_TRANSFER,
+    NORMAL_CLONE_WIDE = SCB_NORMAL_CLONE_WIDE, MIXED_CLONE_WIDE = SCB_MIXED_CLONE_WIDE, MONOCHROME_TRANSFER_WIDE = SCB_MONOCHROME_TRANSFER_WIDE
+};
 
 struct Point {
     int x = 0, y = 0;

@@ -36,6 +36,9 @@ import numpy as np
 NORMAL_CLONE = 1
 MIXED_CLONE = 2
 MONOCHROME_TRANSFER = 3
+NORMAL_CLONE_WIDE = 9  # OpenCV >= 4.11: the centre of src (not of the mask bounding box) goes to p; same arithmetic
+MIXED_CLONE_WIDE = 10
+MONOCHROME_TRANSFER_WIDE = 11
 
 
 class OracleError(ValueError):
@@ -139,7 +142,7 @@ def erode3(mask_rz: np.ndarray) -> np.ndarray:
     return out
 
 
-def plan_geometry(mask_gray: np.ndarray, dst_shape, p) -> tuple[Geometry, np.ndarray]:
+def plan_geometry(mask_gray: np.ndarray, dst_shape, p, wide: bool = False) -> tuple[Geometry, np.ndarray]:
     """Prologue of cv::seamlessClone: ring-zero, bbox, ROI placement (truncating integer
     division on the BBOX size), bounds check.  Returns geometry + ring-zeroed mask."""
     mrz = ring_zero(mask_gray)
@@ -149,6 +152,8 @@ def plan_geometry(mask_gray: np.ndarray, dst_shape, p) -> tuple[Geometry, np.nda
     x, y, w, h = bb
     px, py = int(p[0]), int(p[1])
     rx, ry = px - w // 2, py - h // 2
+    if wide:  # PROBE (cv2 4.13): flags 9/10/11 == flags 1/2/3 with the ROI at p - src_size/2 + bbox origin
+        rx, ry = px - mask_gray.shape[1] // 2 + x, py - mask_gray.shape[0] // 2 + y
     H, W = dst_shape[:2]
     if not (0 <= rx and rx + w <= W and 0 <= ry and ry + h <= H):
         raise OracleError("ROI outside dst (OpenCV: -215 Assertion failed ... roi)")
@@ -160,12 +165,24 @@ def plan_geometry(mask_gray: np.ndarray, dst_shape, p) -> tuple[Geometry, np.nda
 # --------------------------------------------------------------------------------------
 # stencils (reference pre_process_kernel_gradient imp.cpp:1920-1964, _lapXY :1966-2018)
 # --------------------------------------------------------------------------------------
-def blended_gradients(D: np.ndarray, S: np.ndarray, E: np.ndarray):
+def bgr2gray_u8(img: np.ndarray) -> np.ndarray:
+    """cv::cvtColor(BGR2GRAY) for 8-bit images: 15-bit fixed point, (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+    (pinned bit-exact against cv2.cvtColor in tests/test_oracle.py)."""
+    b, g, r = (img[:, :, k].astype(np.int64) for k in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def blended_gradients(D: np.ndarray, S: np.ndarray, E: np.ndarray, flags: int = NORMAL_CLONE):
     """computeGradientX/Y (kernel [0,-1,1], BORDER_REFLECT_101) of dst-ROI and src-ROI, then
     arrayProduct with (255-E)/255 and E/255, then add.  float32, two rounded multiplies + one
-    rounded add (NOT an FMA)."""
+    rounded add (NOT an FMA).
+      MIXED_CLONE          per pixel and channel the patch gradient pair is replaced by dst's unless
+                           |gxS - gyS| > |gxD - gyD|   (Cloning::normalClone, OpenCV seamless_cloning_impl.cpp)
+      MONOCHROME_TRANSFER  the patch gradients are those of cvtColor(patch, BGR2GRAY), replicated to 3 channels"""
     f = np.float32
     Df = D.astype(f)
+    if flags == MONOCHROME_TRANSFER:
+        S = np.repeat(bgr2gray_u8(S)[:, :, None], 3, axis=2)
     Sf = S.astype(f)
 
     def gx(a):
@@ -183,8 +200,13 @@ def blended_gradients(D: np.ndarray, S: np.ndarray, E: np.ndarray):
     inv255 = f(1.0 / 255.0)
     m = (E.astype(f) * inv255)[:, :, None]
     mi = ((255 - E).astype(f) * inv255)[:, :, None]
-    vx = (gx(Df) * mi).astype(f) + (gx(Sf) * m).astype(f)
-    vy = (gy(Df) * mi).astype(f) + (gy(Sf) * m).astype(f)
+    gxD, gyD, gxS, gyS = gx(Df), gy(Df), gx(Sf), gy(Sf)
+    if flags == MIXED_CLONE:
+        keep = np.abs(gxS - gyS) > np.abs(gxD - gyD)
+        gxS = np.where(keep, gxS, gxD)
+        gyS = np.where(keep, gyS, gyD)
+    vx = (gxD * mi).astype(f) + (gxS * m).astype(f)
+    vy = (gyD * mi).astype(f) + (gyS * m).astype(f)
     return vx.astype(f), vy.astype(f)
 
 
@@ -294,10 +316,14 @@ def compose_u8(u: np.ndarray) -> np.ndarray:
 # the whole path
 # --------------------------------------------------------------------------------------
 def restate(src, dst, mask, p, flags: int = NORMAL_CLONE, transform: str = "cv") -> Trace:
-    """Restatement of cv::seamlessClone(src, dst, mask, p, blend, NORMAL_CLONE) returning every
-    intermediate.  Never mutates its inputs (the real function overwrites the caller's mask)."""
-    if flags != NORMAL_CLONE:
-        raise OracleError("only NORMAL_CLONE is in scope")
+    """Restatement of cv::seamlessClone(src, dst, mask, p, blend, flags) returning every intermediate;
+    flags = NORMAL_CLONE (the hot path), MIXED_CLONE or MONOCHROME_TRANSFER (the same solver behind a different
+    gradient selection).  Never mutates its inputs (the real function overwrites the caller's mask)."""
+    wide = flags >= NORMAL_CLONE_WIDE
+    if wide:
+        flags -= NORMAL_CLONE_WIDE - NORMAL_CLONE
+    if flags not in (NORMAL_CLONE, MIXED_CLONE, MONOCHROME_TRANSFER):
+        raise OracleError("flags must be NORMAL_CLONE, MIXED_CLONE, MONOCHROME_TRANSFER or their _WIDE variants")
     src = np.asarray(src)
     dst = np.asarray(dst)
     if src.ndim == 2:
@@ -307,7 +333,7 @@ def restate(src, dst, mask, p, flags: int = NORMAL_CLONE, transform: str = "cv")
     mg = normalise_mask(mask, src.shape)
     if mg.shape != src.shape[:2]:
         raise OracleError("mask and src sizes differ")
-    geom, mrz = plan_geometry(mg, dst.shape, p)
+    geom, mrz = plan_geometry(mg, dst.shape, p, wide)
     tr = Trace(geom)
     if geom.empty:
         tr.blend = dst.copy()
@@ -317,7 +343,7 @@ def restate(src, dst, mask, p, flags: int = NORMAL_CLONE, transform: str = "cv")
     S = src[y : y + h, x : x + w]  # OpenCV zeroes S outside the mask; irrelevant to the result
     E = erode3(mrz)[y : y + h, x : x + w]
     tr.eroded = E
-    tr.vx, tr.vy = blended_gradients(D, S, E)
+    tr.vx, tr.vy = blended_gradients(D, S, E, flags)
     tr.rhs = rhs_from_gradients(tr.vx, tr.vy, D)
     tr.den = denominator(w, h)
     spec = np.empty(tr.rhs.shape, np.float64 if transform == "f64" else np.float32)
@@ -333,12 +359,12 @@ def restate(src, dst, mask, p, flags: int = NORMAL_CLONE, transform: str = "cv")
     return tr
 
 
-def cv_reference(src, dst, mask, p):
+def cv_reference(src, dst, mask, p, flags: int = NORMAL_CLONE):
     """The real thing: cv2.seamlessClone with a COPY of the mask (it mutates its mask argument)."""
     import cv2
 
     m = normalise_mask(mask, np.asarray(src).shape).copy()
-    return cv2.seamlessClone(np.ascontiguousarray(src), np.ascontiguousarray(dst), m, (int(p[0]), int(p[1])), cv2.NORMAL_CLONE)
+    return cv2.seamlessClone(np.ascontiguousarray(src), np.ascontiguousarray(dst), m, (int(p[0]), int(p[1])), int(flags))
 
 
 # --------------------------------------------------------------------------------------

@@ -120,14 +120,14 @@ class Context:
         self._check(self.lib.scb_seamless_clone(self.handle, C.byref(vs), C.byref(vd), C.byref(vm), int(p[0]), int(p[1]), C.byref(vb), int(flags), MEM_HOST))
         return blend
 
-    def plan(self, mask, src_hw, dst_hw, p, mem_kind: int = MEM_HOST) -> "Plan":
-        return Plan(self, mask, src_hw, dst_hw, p, mem_kind)
+    def plan(self, mask, src_hw, dst_hw, p, mem_kind: int = MEM_HOST, clone_flags: int = NORMAL_CLONE) -> "Plan":
+        return Plan(self, mask, src_hw, dst_hw, p, mem_kind, clone_flags)
 
 
 class Plan:
     """Everything that depends only on (mask, sizes, p): ROI, eroded mask, DST tables (scb_plan)."""
 
-    def __init__(self, ctx: Context, mask, src_hw, dst_hw, p, mem_kind: int = MEM_HOST):
+    def __init__(self, ctx: Context, mask, src_hw, dst_hw, p, mem_kind: int = MEM_HOST, clone_flags: int = NORMAL_CLONE):
         self.ctx = ctx
         self.lib = ctx.lib
         if mem_kind == MEM_HOST:
@@ -136,7 +136,8 @@ class Plan:
         else:
             vm = mask if isinstance(mask, capi.ScbImage) else capi.tensor_view(mask)
         h = C.c_void_p()
-        ctx._check(self.lib.scb_plan_create(ctx.handle, C.byref(vm), mem_kind, int(src_hw[0]), int(src_hw[1]), int(dst_hw[0]), int(dst_hw[1]), int(p[0]), int(p[1]), C.byref(h)))
+        ctx._check(self.lib.scb_plan_create_ex(ctx.handle, C.byref(vm), mem_kind, int(src_hw[0]), int(src_hw[1]), int(dst_hw[0]), int(dst_hw[1]), int(p[0]), int(p[1]),
+                                               int(clone_flags), C.byref(h)))
         self.handle = h
         g = capi.ScbGeometry()
         ctx._check(self.lib.scb_plan_geometry(self.handle, C.byref(g)))
@@ -211,7 +212,8 @@ def default_context(device: int = 0) -> Context:
 
 
 def seamlessClone(src, dst, mask, p, flags: int = NORMAL_CLONE, device: int = 0) -> np.ndarray:
-    """Drop-in for cv2.seamlessClone(src, dst, mask, p, cv2.NORMAL_CLONE) on numpy arrays."""
+    """Drop-in for cv2.seamlessClone(src, dst, mask, p, flags) on numpy arrays; flags = NORMAL_CLONE (the hot path),
+    MIXED_CLONE, MONOCHROME_TRANSFER or their _WIDE variants (9, 10, 11)."""
     return default_context(device).seamless_clone(src, dst, mask, p, flags)
 
 

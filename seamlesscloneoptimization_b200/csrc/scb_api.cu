@@ -129,6 +129,8 @@ struct scb_plan {
     const float* fx = nullptr;
     const float* fy = nullptr;
     int lowkx = 0, lowky = 0;
+    int mode = SCB_NORMAL_CLONE;        // gradient selection: NORMAL_CLONE, MIXED_CLONE or MONOCHROME_TRANSFER
+    bool wide = false;                  // *_WIDE flags: src (not the mask bounding box) is centred at p
     bool debug = false;
     float *dbg_vx = nullptr, *dbg_vy = nullptr, *dbg_rhs = nullptr, *dbg_spec = nullptr, *dbg_u = nullptr;
 };
@@ -733,8 +735,12 @@ struct PlanInput {
 };
 
 static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
-                      int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in) {
+                      int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in, int clone_flags = SCB_NORMAL_CLONE) {
     *out = nullptr;
+    const bool wide = clone_flags >= SCB_NORMAL_CLONE_WIDE;
+    const int mode = wide ? clone_flags - (SCB_NORMAL_CLONE_WIDE - SCB_NORMAL_CLONE) : clone_flags;
+    if (mode != SCB_NORMAL_CLONE && mode != SCB_MIXED_CLONE && mode != SCB_MONOCHROME_TRANSFER)
+        return fail(c, SCB_ERR_UNSUPPORTED, "seamlessClone: flags must be NORMAL_CLONE, MIXED_CLONE, MONOCHROME_TRANSFER or their _WIDE variants");
     if (!mask || !mask->data) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask is null (pass an all-255 mask for 'no mask')");
     if (mask->channels != 1) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask must be single channel 8-bit (convert colour masks to grey first)");
     if (mask->rows != src_rows || mask->cols != src_cols) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: mask and src sizes differ");
@@ -748,6 +754,8 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
     p->src_cols = src_cols;
     p->dst_rows = dst_rows;
     p->dst_cols = dst_cols;
+    p->mode = mode;
+    p->wide = wide;
     MaskView& mv = in->mv;
     mv.rows = mask->rows;
     mv.cols = mask->cols;
@@ -808,8 +816,13 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
     g.y = miny;
     g.w = maxx - minx + 1;
     g.h = maxy - miny + 1;
-    g.rx = in.px - g.w / 2;  // truncating division on the BBOX size, like cv::seamlessClone
-    g.ry = in.py - g.h / 2;
+    if (p->wide) {  // *_WIDE: p is where the centre of src goes; the ROI keeps its place inside src
+        g.rx = in.px - p->src_cols / 2 + g.x;
+        g.ry = in.py - p->src_rows / 2 + g.y;
+    } else {
+        g.rx = in.px - g.w / 2;  // truncating division on the BBOX size, like cv::seamlessClone
+        g.ry = in.py - g.h / 2;
+    }
     g.nx = g.w - 2;
     g.ny = g.h - 2;
     auto bad = [&](int code, const char* msg) {
@@ -857,6 +870,11 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
 
 extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
                                int dst_rows, int dst_cols, int px, int py, scb_plan** out) {
+    return scb_plan_create_ex(c, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, SCB_NORMAL_CLONE, out);
+}
+
+extern "C" int scb_plan_create_ex(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                                  int dst_rows, int dst_cols, int px, int py, int clone_flags, scb_plan** out) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
     if (!out) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: out is null");
     *out = nullptr;
@@ -864,7 +882,7 @@ extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_m
     Lane* lane = &c->lanes[0];
     scb_plan* p = nullptr;
     PlanInput in;
-    int rc = plan_begin(c, lane, lane->stream, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, 0, &p, &in);
+    int rc = plan_begin(c, lane, lane->stream, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, 0, &p, &in, clone_flags);
     if (rc) return rc;
     cudaError_t e = cudaStreamSynchronize(lane->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1113,6 +1131,7 @@ static bool choose_swap(const scb_plan* p) {
         const char* e = std::getenv("SCB_SWAP");
         return e ? std::atoi(e) : -1;
     }();
+    if (p->mode != SCB_NORMAL_CLONE) return false;  // the mode stencils store the natural layout only
     if (p->ctx->orientation >= 0) return p->ctx->orientation != 0;
     if (forced >= 0) return forced != 0;
     // Measured on B200 (profiles/r1_s3_ab_swap.txt): at 4K the row passes drop from 221 to 186 us with the lines along y, but the
@@ -1132,10 +1151,15 @@ static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0,
     rp.g = G;
     rp.gp = gp;
     rp.y0 = y0;
+    rp.y1 = y1;
     rp.transposed = swap ? 1 : 0;
     rp.gpt = (int)align_up((size_t)p->g.ny, 4);
-    const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
-    SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
+    if (p->mode != SCB_NORMAL_CLONE) {  // MIXED_CLONE / MONOCHROME_TRANSFER: per-pixel float stencil with the mode's gradient selection
+        SCB_LAUNCH(rhs_mode_kernel, dim3((gp + 31) / 32, (y1 - y0 + 7) / 8), dim3(256), 0, p->lane->stream, rp, p->mode);
+    } else {
+        const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
+        SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
+    }
     c->launches++;
     if (p->debug && !swap)  // dense [3][ny][nx] copy for scb_plan_get_intermediate (debug plans keep the natural orientation)
         for (int ch = 0; ch < 3; ++ch)
@@ -1505,7 +1529,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         out_pitch = blend->stride;
     }
     if (p->debug) {
-        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, ms, st, p->dbg_vx, p->dbg_vy);
+        SCB_LAUNCH(gradients_dump_kernel, dim3((g.w + 31) / 32, (g.h + 7) / 8), dim3(256), 0, ms, st, p->dbg_vx, p->dbg_vy, p->mode);
         c->launches++;
     }
     tm.mark(ST_IN);
@@ -1610,10 +1634,9 @@ extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const s
 extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const scb_image* dst, const scb_image* mask,
                                   int px, int py, scb_image* blend, int clone_flags, int mem_kind) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
-    if (clone_flags != SCB_NORMAL_CLONE) return fail(c, SCB_ERR_UNSUPPORTED, "seamlessClone: only NORMAL_CLONE is implemented (no CPU fallback for MIXED_CLONE / MONOCHROME_TRANSFER)");
     if (!src || !dst || !blend) return fail(c, SCB_ERR_INVALID_ARGUMENT, "seamlessClone: null image");
     scb_plan* p = nullptr;
-    int rc = scb_plan_create(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, &p);
+    int rc = scb_plan_create_ex(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p);
     if (rc) return rc;
     rc = scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
     scb_plan_destroy(p);

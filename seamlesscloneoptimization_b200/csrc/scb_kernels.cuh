@@ -102,6 +102,7 @@ struct RhsParams {
     float* g;  // [3][ny][gp]
     int gp;    // row pitch of g in floats, multiple of 4
     int y0;    // first interior row of this launch
+    int y1;          // one past the last interior row of this launch (rhs_mode_kernel)
     int transposed;  // 1: store g as [3][nx][gpt] (lines along y: the solve runs its FFT passes along y, scb_api.cu choose_swap)
     int gpt;         // line pitch of the transposed layout in floats
 };
@@ -252,6 +253,75 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
     }
     SCB_UNROLL
     for (int c = 0; c < 3; ++c) rhs_store4(p, c, x0, y, out[c][0], out[c][1], out[c][2], out[c][3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The other cv::seamlessClone flags: the same solver behind a different gradient selection
+// (Cloning::normalClone in OpenCV's seamless_cloning_impl.cpp).
+//   MIXED_CLONE          per pixel and channel, the patch gradient PAIR is replaced by dst's unless
+//                        |gxS - gyS| > |gxD - gyD|
+//   MONOCHROME_TRANSFER  the patch gradients are those of cvtColor(patch, BGR2GRAY) (15-bit fixed point), all 3 channels
+// One thread per interior pixel, OpenCV's float operations in OpenCV's order.  The selection at (X-1, Y) and (X, Y-1)
+// needs the taps (X-1, Y+1) and (X+1, Y-1) on top of the 5-point cross.
+// ---------------------------------------------------------------------------------------------
+enum { kModeNormal = 1, kModeMixed = 2, kModeMono = 3 };
+
+SCB_D float gray_of(const unsigned char* px) {  // cv::cvtColor(BGR2GRAY), 8-bit: (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+    return (float)((__ldg(px) * 3735 + __ldg(px + 1) * 19235 + __ldg(px + 2) * 9798 + (1 << 14)) >> 15);
+}
+
+// forward differences of both images at (X, Y) towards (Xn, Y) and (X, Yn), after the mode's selection
+SCB_D void mode_gradients(const StencilSrc& s, int mode, int c, int X, int Y, int Xn, int Yn, float& gxD, float& gyD, float& gxS, float& gyS) {
+    const unsigned char* d = s.D + (long long)Y * s.d_pitch + 3 * X + c;
+    const float Dc = (float)__ldg(d);
+    gxD = (float)__ldg(s.D + (long long)Y * s.d_pitch + 3 * Xn + c) - Dc;
+    gyD = (float)__ldg(s.D + (long long)Yn * s.d_pitch + 3 * X + c) - Dc;
+    if (mode == kModeMono) {
+        const float Sc = gray_of(s.S + (long long)Y * s.s_pitch + 3 * X);
+        gxS = gray_of(s.S + (long long)Y * s.s_pitch + 3 * Xn) - Sc;
+        gyS = gray_of(s.S + (long long)Yn * s.s_pitch + 3 * X) - Sc;
+    } else {
+        const float Sc = (float)__ldg(s.S + (long long)Y * s.s_pitch + 3 * X + c);
+        gxS = (float)__ldg(s.S + (long long)Y * s.s_pitch + 3 * Xn + c) - Sc;
+        gyS = (float)__ldg(s.S + (long long)Yn * s.s_pitch + 3 * X + c) - Sc;
+    }
+    if (mode == kModeMixed && !(fabsf(gxS - gyS) > fabsf(gxD - gyD))) {
+        gxS = gxD;
+        gyS = gyD;
+    }
+}
+
+__global__ void __launch_bounds__(256) rhs_mode_kernel(RhsParams p, int mode) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = p.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.gp || y >= p.y1) return;
+    const StencilSrc& s = p.st;
+    float g[3] = {0.f, 0.f, 0.f};
+    if (x < p.nx) {
+        const int X = x + 1, Y = y + 1;
+        const float inv255 = 1.0f / 255.0f;
+        const int ec = __ldg(s.E + (long long)Y * s.e_pitch + X), el = __ldg(s.E + (long long)Y * s.e_pitch + X - 1), eu = __ldg(s.E + (long long)(Y - 1) * s.e_pitch + X);
+        const float mc = __fmul_rn((float)ec, inv255), mic = __fmul_rn((float)(255 - ec), inv255);
+        const float ml = __fmul_rn((float)el, inv255), mil = __fmul_rn((float)(255 - el), inv255);
+        const float mu = __fmul_rn((float)eu, inv255), miu = __fmul_rn((float)(255 - eu), inv255);
+        for (int c = 0; c < 3; ++c) {
+            float gxD, gyD, gxS, gyS;
+            mode_gradients(s, mode, c, X, Y, X + 1, Y + 1, gxD, gyD, gxS, gyS);
+            const float vxc = __fadd_rn(__fmul_rn(gxD, mic), __fmul_rn(gxS, mc));
+            const float vyc = __fadd_rn(__fmul_rn(gyD, mic), __fmul_rn(gyS, mc));
+            mode_gradients(s, mode, c, X - 1, Y, X, Y + 1, gxD, gyD, gxS, gyS);
+            const float vxl = __fadd_rn(__fmul_rn(gxD, mil), __fmul_rn(gxS, ml));
+            mode_gradients(s, mode, c, X, Y - 1, X + 1, Y, gxD, gyD, gxS, gyS);
+            const float vyu = __fadd_rn(__fmul_rn(gyD, miu), __fmul_rn(gyS, mu));
+            const float lap = __fadd_rn(__fsub_rn(vxc, vxl), __fsub_rn(vyc, vyu));
+            float bnd = 0.f;
+            if (X == 1) bnd += (float)__ldg(s.D + (long long)Y * s.d_pitch + 3 * (X - 1) + c);
+            if (X == s.w - 2) bnd += (float)__ldg(s.D + (long long)Y * s.d_pitch + 3 * (X + 1) + c);
+            if (Y == 1) bnd += (float)__ldg(s.D + (long long)(Y - 1) * s.d_pitch + 3 * X + c);
+            if (Y == s.h - 2) bnd += (float)__ldg(s.D + (long long)(Y + 1) * s.d_pitch + 3 * X + c);
+            g[c] = __fsub_rn(lap, bnd);
+        }
+    }
+    for (int c = 0; c < 3; ++c) p.g[((size_t)c * p.ny + y) * p.gp + x] = g[c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -619,7 +689,7 @@ __global__ void __launch_bounds__(256) mask_erode_kernel(MaskView m, int x0, int
 // ---------------------------------------------------------------------------------------------
 // debug: blended gradients over the whole ROI (test hook for the 1e-4 intermediate checks)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gradients_dump_kernel(StencilSrc s, float* vx, float* vy /* [3][h][w] */) {
+__global__ void __launch_bounds__(256) gradients_dump_kernel(StencilSrc s, float* vx, float* vy /* [3][h][w] */, int mode) {
     const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (X >= s.w || Y >= s.h) return;
     const int Xn = (X < s.w - 1) ? X + 1 : X - 1, Yn = (Y < s.h - 1) ? Y + 1 : Y - 1;  // BORDER_REFLECT_101
@@ -627,12 +697,10 @@ __global__ void __launch_bounds__(256) gradients_dump_kernel(StencilSrc s, float
     const float inv255 = 1.0f / 255.0f;
     const float m = __fmul_rn((float)e, inv255), mi = __fmul_rn((float)(255 - e), inv255);
     for (int c = 0; c < 3; ++c) {
-        const float Dc = (float)s.D[(long long)Y * s.d_pitch + 3 * X + c], Dr = (float)s.D[(long long)Y * s.d_pitch + 3 * Xn + c];
-        const float Dd = (float)s.D[(long long)Yn * s.d_pitch + 3 * X + c];
-        const float Sc = (float)s.S[(long long)Y * s.s_pitch + 3 * X + c], Sr = (float)s.S[(long long)Y * s.s_pitch + 3 * Xn + c];
-        const float Sd = (float)s.S[(long long)Yn * s.s_pitch + 3 * X + c];
-        vx[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(Dr - Dc, mi), __fmul_rn(Sr - Sc, m));
-        vy[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(Dd - Dc, mi), __fmul_rn(Sd - Sc, m));
+        float gxD, gyD, gxS, gyS;
+        mode_gradients(s, mode, c, X, Y, Xn, Yn, gxD, gyD, gxS, gyS);
+        vx[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(gxD, mi), __fmul_rn(gxS, m));
+        vy[((size_t)c * s.h + Y) * s.w + X] = __fadd_rn(__fmul_rn(gyD, mi), __fmul_rn(gyS, m));
     }
 }
 

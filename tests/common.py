@@ -25,7 +25,9 @@ def golden_names():
 
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    return {k: z[k] for k in z.files}
+    d = {k: z[k] for k in z.files}
+    d["flags"] = int(d["flags"]) if "flags" in d else so.NORMAL_CLONE  # fixtures older than the flag support are NORMAL_CLONE
+    return d
 
 
 def interior(img, geom):
@@ -41,7 +43,7 @@ def allowed_mismatches(n_bytes: int) -> int:
 def check_against_golden(ctx: scb.Context, name: str, check_float: bool = True):
     z = load_golden(name)
     src, dst, mask, p, geom = z["src"], z["dst"], z["mask"], tuple(int(v) for v in z["p"]), z["geom"]
-    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p, clone_flags=z["flags"])
     g = plan.geometry
     assert [g.x, g.y, g.w, g.h, g.rx, g.ry] == [int(v) for v in geom], "ROI geometry differs from OpenCV's"
     plan.set_debug(True)

@@ -56,7 +56,7 @@ int main(int argc, char** argv) {
     }
     try {
         scb::Mat b2;
-        scb::seamlessClone(src, dst, mask, scb::Point(px, py), b2, scb::MIXED_CLONE);
+        scb::seamlessClone(src, dst, mask, scb::Point(px, py), b2, 4 /* not a cv::seamlessClone flag */);
     } catch (const scb::Exception& e) {
         seen += (e.code == SCB_ERR_UNSUPPORTED);
     }

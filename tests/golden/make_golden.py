@@ -16,11 +16,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import seamless_oracle as so  # noqa: E402
 
 
-def save(name, src, dst, mask, p):
+def save(name, src, dst, mask, p, flags=so.NORMAL_CLONE):
     import cv2
 
-    ref = so.cv_reference(src, dst, mask, p)
-    tr = so.restate(src, dst, mask, p, transform="cv")
+    ref = so.cv_reference(src, dst, mask, p, flags)
+    tr = so.restate(src, dst, mask, p, flags=flags, transform="cv")
     assert np.array_equal(ref, tr.blend), name
     g = tr.geom
     np.savez_compressed(
@@ -29,7 +29,7 @@ def save(name, src, dst, mask, p):
         geom=np.array([g.x, g.y, g.w, g.h, g.rx, g.ry], np.int32),
         blend_roi=ref[g.ry : g.ry + g.h, g.rx : g.rx + g.w],
         eroded=tr.eroded, rhs=tr.rhs, spectrum=tr.spectrum, solved=tr.solved,
-        cv_version=np.array(cv2.__version__),
+        cv_version=np.array(cv2.__version__), flags=np.array(flags, np.int32),
     )
     print(name, g, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
 
@@ -53,6 +53,16 @@ def main():
     src = rng.integers(0, 256, size=(40, 64, 3), dtype=np.uint8)
     dst = rng.integers(0, 256, size=(80, 96, 3), dtype=np.uint8)
     save("noise_saturating", src, dst, so.ellipse_mask(40, 64, 32, 20, 28, 17, 0.0), (48, 40))
+
+    # the other cv::seamlessClone flags (same solver, different gradient selection / ROI placement)
+    rng = np.random.default_rng(23)
+    src = so.smooth_rand(rng, 61, 83, 2.0)
+    dst = so.smooth_rand(rng, 140, 170, 2.0)
+    mask = so.ellipse_mask(61, 83, 36.0, 27.0, 30.0, 20.0, 0.3)
+    save("flags_mixed_ellipse", src, dst, mask, (88, 71), so.MIXED_CLONE)
+    grey = ((mask > 0) * rng.integers(1, 256, size=mask.shape)).astype(np.uint8)
+    save("flags_monochrome_grey_mask", src, dst, grey, (88, 71), so.MONOCHROME_TRANSFER)
+    save("flags_mixed_wide_ellipse", src, dst, mask, (88, 71), so.MIXED_CLONE_WIDE)
 
     ref_dir = "/root/reference/seamlessClone-OpenCV/images"
     if os.path.isdir(ref_dir):

@@ -19,7 +19,7 @@ def test_restatement_bit_exact_vs_golden(name):
     if not HAVE_CV:
         pytest.skip("cv2.dft is needed for the bit-exact transform back end")
     z = common.load_golden(name)
-    tr = so.restate(z["src"], z["dst"], z["mask"], tuple(z["p"]), transform="cv")
+    tr = so.restate(z["src"], z["dst"], z["mask"], tuple(z["p"]), flags=z["flags"], transform="cv")
     g = tr.geom
     assert [g.x, g.y, g.w, g.h, g.rx, g.ry] == list(z["geom"])
     assert np.array_equal(tr.blend[g.ry : g.ry + g.h, g.rx : g.rx + g.w], z["blend_roi"])
@@ -30,7 +30,7 @@ def test_restatement_bit_exact_vs_golden(name):
 @pytest.mark.parametrize("name", common.golden_names())
 def test_float64_back_end_within_tolerance(name):
     z = common.load_golden(name)
-    tr = so.restate(z["src"], z["dst"], z["mask"], tuple(z["p"]), transform="f64")
+    tr = so.restate(z["src"], z["dst"], z["mask"], tuple(z["p"]), flags=z["flags"], transform="f64")
     g = tr.geom
     assert np.array_equal(tr.rhs, z["rhs"])  # integer stencil needs no cv2
     assert so.rel_linf(tr.spectrum, z["spectrum"]) < 1e-5
@@ -86,3 +86,28 @@ def test_generators_are_deterministic():
         assert np.array_equal(x, y)
     jobs = so.make_batch_jobs(5, seed=1)
     assert jobs == so.make_batch_jobs(5, seed=1)
+
+
+@pytest.mark.skipif(not HAVE_CV, reason="needs cv2")
+@pytest.mark.parametrize("flags", [so.MIXED_CLONE, so.MONOCHROME_TRANSFER, so.NORMAL_CLONE_WIDE, so.MIXED_CLONE_WIDE, so.MONOCHROME_TRANSFER_WIDE])
+@pytest.mark.parametrize("grey", [False, True])
+def test_other_clone_flags_bit_exact_vs_cv2_live(flags, grey):
+    """MIXED_CLONE / MONOCHROME_TRANSFER (gradient selection) and the _WIDE placement, pinned against cv2.seamlessClone."""
+    rng = np.random.default_rng(31 + flags)
+    src = so.smooth_rand(rng, 61, 83, 2.0)
+    dst = so.smooth_rand(rng, 140, 170, 2.0)
+    mask = so.ellipse_mask(61, 83, 36.0, 27.0, 30.0, 20.0, 0.3)
+    if grey:
+        mask = ((mask > 0) * rng.integers(1, 256, size=mask.shape)).astype(np.uint8)
+    p = (88, 71)
+    ref = so.cv_reference(src, dst, mask, p, flags)
+    tr = so.restate(src, dst, mask, p, flags=flags, transform="cv")
+    assert np.array_equal(tr.blend, ref)
+
+
+@pytest.mark.skipif(not HAVE_CV, reason="needs cv2")
+def test_gray_conversion_bit_exact_vs_cv2():
+    import cv2
+
+    img = np.random.default_rng(3).integers(0, 256, size=(97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(so.bgr2gray_u8(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))

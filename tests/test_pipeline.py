@@ -162,7 +162,7 @@ def test_error_behaviour(ctx):
         ctx.seamless_clone(src, dst, mask, (2, 2))
     assert e.value.code == capi.SCB_ERR_ROI_OUT_OF_BOUNDS
     with pytest.raises(scb.ScbError) as e:  # no CPU fallback for the other flags
-        ctx.seamless_clone(src, dst, mask, p, scb.MIXED_CLONE)
+        ctx.seamless_clone(src, dst, mask, p, 4)  # not a cv::seamlessClone flag
     assert e.value.code == capi.SCB_ERR_UNSUPPORTED
     with pytest.raises(scb.ScbError) as e:
         ctx.seamless_clone(src, dst, mask[:-1], p)
@@ -526,3 +526,32 @@ def test_tri_orientations_agree_with_oracle(be, w, h, mem, monkeypatch):
         assert int((outs[0] != outs[1]).sum()) <= common.allowed_mismatches(roi_interior(outs[0], ref.geom).size)
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the other cv::seamlessClone flags: same solver, different gradient selection / ROI placement
+@pytest.mark.parametrize("flags", [capi.MIXED_CLONE, capi.MONOCHROME_TRANSFER, capi.NORMAL_CLONE_WIDE, capi.MIXED_CLONE_WIDE, capi.MONOCHROME_TRANSFER_WIDE])
+@pytest.mark.parametrize("seed", [2, 9])
+def test_clone_flags_vs_oracle(ctx, flags, seed):
+    rng = np.random.default_rng(100 + seed)
+    src = so.smooth_rand(rng, 61, 83, 2.0)
+    dst = so.smooth_rand(rng, 140, 170, 2.0)
+    mask = so.ellipse_mask(61, 83, 36.0, 27.0, 30.0, 20.0, 0.3)  # off-centre: the _WIDE placement differs from the plain one
+    if seed == 9:
+        mask = (mask > 0) * rng.integers(1, 256, size=mask.shape).astype(np.uint8)  # grey mask values: float blend
+        mask = mask.astype(np.uint8)
+    p = (88, 71)
+    ref = so.restate(src, dst, mask, p, flags=flags, transform="f64")
+    plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p, clone_flags=flags)
+    g = plan.geometry
+    assert (g.x, g.y, g.w, g.h, g.rx, g.ry) == (ref.geom.x, ref.geom.y, ref.geom.w, ref.geom.h, ref.geom.rx, ref.geom.ry)
+    plan.set_debug(True)
+    blend = plan.execute(src, dst)
+    assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_X).transpose(1, 2, 0), ref.vx)
+    assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_Y).transpose(1, 2, 0), ref.vy)
+    assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs), "RHS not bit-exact"
+    assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
+    assert_matches(blend, ref.blend, g, f"flags {flags}", ref.solved)
+    plan.close()
+    one_shot = ctx.seamless_clone(src, dst, mask, p, flags)
+    assert np.array_equal(one_shot, blend)
