@@ -64,37 +64,45 @@ def ncu_traffic(workload: str, kernel: str):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (NVML, 100 ms period)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (NVML, 20 ms period; one sample is taken
+    synchronously at start and the legs take one right after enqueueing the timed steps, while the GPU is still busy,
+    so that even a few-millisecond region is covered)."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-
-    def run(self):
+        self.nv = self.h = None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
-            }
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, name in names.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-                time.sleep(0.1)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.NAMES.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:  # pragma: no cover
+            pass
+
+    def start(self):
+        self.sample()
+        super().start()
+
+    def run(self):
+        while not self.stop_flag:
+            time.sleep(0.02)
+            self.sample()
 
     def stop(self):
         self.stop_flag = True
@@ -304,6 +312,7 @@ def single_job_leg(env: Env, args):
         sampler.start()
         launches0 = ctx.kernel_launches
         evs = env.timed_steps(stream, device_step, args.steps)
+        sampler.sample()
         env.barrier()
         launches = ctx.kernel_launches - launches0
         step_ms = [a.elapsed_time(b) for a, b in evs]
@@ -508,6 +517,7 @@ def sharded_leg(env: Env, args):
         sampler.start()
         launches0 = ctx.kernel_launches
         evs = env.timed_steps(stream, device_step, args.steps)
+        sampler.sample()
         env.barrier()
         launches = ctx.kernel_launches - launches0
         sampler.stop()

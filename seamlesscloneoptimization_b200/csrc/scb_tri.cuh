@@ -36,8 +36,16 @@ namespace scb {
 
 static constexpr int kTriLowK = 32;  // spectral columns solved in float64 and corrected to OpenCV's float32 denominators
 static constexpr int kTriLowL = 32;  // ... for this many lowest frequencies along y
-static constexpr int kTriCols = 32;  // columns per CTA (lanes of a warp)
+#ifndef SCB_TRI_COLS
+#define SCB_TRI_COLS 16
+#endif
+static constexpr int kTriCols = SCB_TRI_COLS;  // columns per CTA: 16 -> 64-byte rows per segment, twice the CTAs (171 CTAs of 32 columns left 23 of the 148 SMs with two CTAs and the rest with one)
+static_assert(32 % kTriCols == 0 && kTriLowK % kTriCols == 0, "column tiles must pack into warps and split the float64 block evenly");
 static constexpr int kTriSegs = 16;  // segments per column (warps of a CTA)
+#ifndef SCB_TRI_UNROLL
+#define SCB_TRI_UNROLL 8
+#endif
+static constexpr int kTriUnroll = SCB_TRI_UNROLL;  // rows whose loads are in flight together
 
 // Segment length for ny unknowns: at most kTriSegs segments, none shorter than 4 rows unless the column is.
 SCB_HD int tri_seg_len(int ny) {
@@ -117,29 +125,29 @@ template <class T>
 struct TriIo;  // global-memory views of one column: a(y), v/u(y) and the tables
 
 template <class T, class LoadA, class LoadM, class LoadP, class LoadV, class StoreV>
-SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][kTriSegs][32] */, const LoadA& load_a, const LoadM& load_m, const LoadP& load_p,
+SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][kTriSegs][kTriCols] */, const LoadA& load_a, const LoadM& load_m, const LoadP& load_p,
                         const LoadV& load_v, const StoreV& store_v, bool active, int phase, int seg0, int seg1, T* ends /* global [kTriSegs][2][estride] + column, or null */,
                         size_t estride) {
     const int r0 = seg * L;
     const bool mine = seg >= seg0 && seg < seg1 && seg < nseg;
     const int len = mine ? ((n - r0 < L) ? n - r0 : L) : 0;
-    T* wl = sm + (0 * kTriSegs + seg) * 32 + lane;
-    T* wf = sm + (1 * kTriSegs + seg) * 32 + lane;
+    T* wl = sm + (0 * kTriSegs + seg) * kTriCols + lane;
+    T* wf = sm + (1 * kTriSegs + seg) * kTriCols + lane;
     // ---- pass 1 ----
     if (active && len > 0 && phase != 2) {
         T v = load_a(r0), b = load_a(r0 + len - 1);
         store_v(r0, v);
         int d = 1;
-        for (; d + 4 <= len; d += 4) {
-            T av[4], ab[4], mm[4];
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            T av[kTriUnroll], ab[kTriUnroll], mm[kTriUnroll];
             SCB_UNROLL
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTriUnroll; ++i) {
                 av[i] = load_a(r0 + d + i);
                 ab[i] = load_a(r0 + len - 1 - d - i);
                 mm[i] = load_m(d + i - 1);
             }
             SCB_UNROLL
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTriUnroll; ++i) {
                 v = mm[i] * v + av[i];
                 b = mm[i] * b + ab[i];
                 store_v(r0 + d + i, v);
@@ -169,16 +177,16 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
     }
     __syncthreads();
     // ---- reduced system: thread (lane, seg 0) of every column ----
-    T* al = sm + (2 * kTriSegs) * 32 + lane;  // alpha[s] at al[s * 32]
-    T* be = sm + (3 * kTriSegs) * 32 + lane;  // beta[s]
-    T* Js = sm + (4 * kTriSegs) * 32 + lane;
-    T* Ks = sm + (5 * kTriSegs) * 32 + lane;
+    T* al = sm + (2 * kTriSegs) * kTriCols + lane;  // alpha[s] at al[s * kTriCols]
+    T* be = sm + (3 * kTriSegs) * kTriCols + lane;  // beta[s]
+    T* Js = sm + (4 * kTriSegs) * kTriCols + lane;
+    T* Ks = sm + (5 * kTriSegs) * kTriCols + lane;
     if (active && seg == 0) {
         const int lastlen = n - (nseg - 1) * L;
         auto ecoef = [&](int s) { return load_p((s == nseg - 1) ? lastlen : L); };      // sinh(theta) / sinh((len+1) theta)
         auto fcoef = [&](int s) { return load_m(((s == nseg - 1) ? lastlen : L) - 1); };  // sinh(len theta) / sinh((len+1) theta)
         const T* WL = sm + lane;
-        const T* WF = sm + kTriSegs * 32 + lane;
+        const T* WF = sm + kTriSegs * kTriCols + lane;
         // p_s = G + H q_s  (p_s: last row of segment s, q_s: first row of segment s+1);  q_s = J_s + K_s q_(s+1)
         T G = WL[0], H = fcoef(0);
         T* Gs = al;  // alpha/beta slots double as G/H storage until the back substitution
@@ -186,23 +194,23 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
         for (int s = 0; s + 1 < nseg; ++s) {
             const T e1 = ecoef(s + 1), f1 = fcoef(s + 1);
             const T den = T(1) - f1 * H;
-            const T J = (WF[(s + 1) * 32] + f1 * G) / den, K = e1 / den;
-            Js[s * 32] = J;
-            Ks[s * 32] = K;
-            Gs[s * 32] = G;
-            Hs[s * 32] = H;
-            const T Gn = WL[(s + 1) * 32] + e1 * (G + H * J);
+            const T J = (WF[(s + 1) * kTriCols] + f1 * G) / den, K = e1 / den;
+            Js[s * kTriCols] = J;
+            Ks[s * kTriCols] = K;
+            Gs[s * kTriCols] = G;
+            Hs[s * kTriCols] = H;
+            const T Gn = WL[(s + 1) * kTriCols] + e1 * (G + H * J);
             H = f1 + e1 * H * K;
             G = Gn;
         }
         // back substitution: q_(nseg-1) = 0 (Dirichlet boundary below the last segment);  alpha_s = p_(s-1),  beta_s = q_s
         T qn = T(0);
-        be[(nseg - 1) * 32] = T(0);
+        be[(nseg - 1) * kTriCols] = T(0);
         for (int s = nseg - 2; s >= 0; --s) {
-            const T q = Js[s * 32] + Ks[s * 32] * qn;
-            const T pp = Gs[s * 32] + Hs[s * 32] * q;
-            be[s * 32] = q;         // H_s consumed
-            al[(s + 1) * 32] = pp;  // G_(s+1) consumed
+            const T q = Js[s * kTriCols] + Ks[s * kTriCols] * qn;
+            const T pp = Gs[s * kTriCols] + Hs[s * kTriCols] * q;
+            be[s * kTriCols] = q;         // H_s consumed
+            al[(s + 1) * kTriCols] = pp;  // G_(s+1) consumed
             qn = q;
         }
         al[0] = T(0);
@@ -210,19 +218,19 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
     __syncthreads();
     // ---- pass 2 ----
     if (active && len > 0) {
-        const T alpha = al[seg * 32];
-        T u = be[seg * 32];
+        const T alpha = al[seg * kTriCols];
+        T u = be[seg * kTriCols];
         int d = len - 1;
-        for (; d >= 3; d -= 4) {
-            T vv[4], mm[4], pp[4];
+        for (; d >= kTriUnroll - 1; d -= kTriUnroll) {
+            T vv[kTriUnroll], mm[kTriUnroll], pp[kTriUnroll];
             SCB_UNROLL
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTriUnroll; ++i) {
                 vv[i] = load_v(r0 + d - i);
                 mm[i] = load_m(d - i);
                 pp[i] = load_p(d - i);
             }
             SCB_UNROLL
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kTriUnroll; ++i) {
                 u = mm[i] * (u + (pp[i] * alpha + vv[i]));
                 store_v(r0 + d - i, u);
             }
@@ -234,10 +242,10 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
     }
 }
 
-// grid = (ceil((x1 - x0) / 32), 3), block = 32 x kTriSegs
+// grid = (ceil((x1 - x0) / kTriCols), 3), block = kTriCols x kTriSegs
 __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolveParams p) {
-    __shared__ double sm_raw[6 * kTriSegs * 32];
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    __shared__ double sm_raw[6 * kTriSegs * kTriCols];
+    const int lane = threadIdx.x % kTriCols, seg = threadIdx.x / kTriCols;  // a warp holds 32 / kTriCols segments of the same columns
     const int c = blockIdx.y;
     const int kb = p.x0 + (int)blockIdx.x * kTriCols;
     const int k = kb + lane;
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolve
     const int nseg = (n + L - 1) / L;
     const float* A = p.A + (size_t)c * n * p.nx + k;
     float* Ct = p.Ct + (size_t)c * n * p.nx + k;
-    if (kb < kTriLowK) {  // float64 columns (whole CTA: kTriLowK == kTriCols)
+    if (kb < kTriLowK) {  // float64 columns (whole CTA: kTriLowK is a multiple of kTriCols)
         double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
         const double* m = p.tab.m64 + k;
         const double* P = p.tab.p64 + k;
