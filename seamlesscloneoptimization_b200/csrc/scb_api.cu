@@ -1158,7 +1158,10 @@ static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0,
         SCB_LAUNCH(rhs_mode_kernel, dim3((gp + 31) / 32, (y1 - y0 + 7) / 8), dim3(256), 0, p->lane->stream, rp, p->mode);
     } else {
         const int chunks = (gp / 4 + kRhsThreads - 1) / kRhsThreads;
-        SCB_LAUNCH(rhs_kernel, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
+        if (swap)
+            SCB_LAUNCH(rhs_kernel<true>, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
+        else
+            SCB_LAUNCH(rhs_kernel<false>, dim3(chunks, y1 - y0), dim3(kRhsThreads), 0, p->lane->stream, rp);
     }
     c->launches++;
     if (p->debug && !swap)  // dense [3][ny][nx] copy for scb_plan_get_intermediate (debug plans keep the natural orientation)

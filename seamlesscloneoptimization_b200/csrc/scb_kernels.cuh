@@ -108,8 +108,9 @@ struct RhsParams {
 };
 
 // four consecutive pixels x0..x0+3 of row y, channel c
+template <bool TRANSPOSED>
 SCB_D void rhs_store4(const RhsParams& p, int c, int x0, int y, float a, float b, float d, float e) {
-    if (!p.transposed) {
+    if (!TRANSPOSED) {
         *reinterpret_cast<float4*>(p.g + ((size_t)c * p.ny + y) * p.gp + x0) = make_float4(a, b, d, e);
     } else {
         float* o = p.g + ((size_t)c * p.nx + x0) * p.gpt + y;
@@ -136,6 +137,7 @@ SCB_D int byte_of(const unsigned (&w)[N], int i) { return (int)((w[i >> 2] >> (8
 
 static constexpr int kRhsThreads = 128;
 
+template <bool TRANSPOSED>
 __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
     const int y = p.y0 + blockIdx.y;
     const int x0 = 4 * (blockIdx.x * kRhsThreads + threadIdx.x);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
         for (int k = 0; k < 4; ++k) {
             float g[3] = {0.f, 0.f, 0.f};
             if (x0 + k < p.nx) rhs_pixel(s, x0 + k, y, g);
-            if (p.transposed) {
+            if (TRANSPOSED) {
                 if (x0 + k < p.nx)
                     for (int c = 0; c < 3; ++c) p.g[((size_t)c * p.nx + x0 + k) * p.gpt + y] = g[c];
             } else if (x0 + k < p.gp) {
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
                 }
             }
             SCB_UNROLL
-            for (int c = 0; c < 3; ++c) rhs_store4(p, c, x0, y, o[c], o[3 + c], o[6 + c], o[9 + c]);
+            for (int c = 0; c < 3; ++c) rhs_store4<TRANSPOSED>(p, c, x0, y, o[c], o[3 + c], o[6 + c], o[9 + c]);
             return;
         }
     }
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
         }
     }
     SCB_UNROLL
-    for (int c = 0; c < 3; ++c) rhs_store4(p, c, x0, y, out[c][0], out[c][1], out[c][2], out[c][3]);
+    for (int c = 0; c < 3; ++c) rhs_store4<TRANSPOSED>(p, c, x0, y, out[c][0], out[c][1], out[c][2], out[c][3]);
 }
 
 // ---------------------------------------------------------------------------------------------
