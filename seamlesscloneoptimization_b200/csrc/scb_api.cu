@@ -1502,7 +1502,10 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     const int nb_out = swap ? 1 : nb;
     int yb[kMaxBands + 1];
     for (int b = 0; b <= nb; ++b) yb[b] = (b == nb) ? g.ny : (int)(((long long)g.ny * b / nb) & ~3LL);  // multiples of 4: whole quads
-    const bool side_copy = !host && copy_dst && !tm.on;
+    // Small jobs of a batch keep everything on the lane's own stream: the other lanes already fill the GPU, and the event
+    // forks / joins of the side stream cost more host time than such a job's kernels take (the batch path is host-bound).
+    const bool serial = tm.on || (defer_host && !p->use_tc && (size_t)g.nx * g.ny < ((size_t)1 << 18));
+    const bool side_copy = !host && copy_dst && !serial;
     if (host) {
         st = make_stencil(p, w.stD, w.pD, w.stS, w.pS);
         out = w.stO;
@@ -1547,7 +1550,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         }
     }
     tm.mark(ST_RHS);
-    if (tm.on) {  // stage timing serialises the refinement so that every stage has its own event pair
+    if (serial) {  // stage timing serialises the refinement so that every stage has its own event pair
         run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, ms, swap);
         if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, ms);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
@@ -1570,10 +1573,10 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
         run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
-        if (!tm.on) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
+        if (!serial) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
         if (p->use_tri) {
-            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, tm.on ? ms : L->side, swap))) return rc;
+            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, serial ? ms : L->side, swap))) return rc;
         } else
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
@@ -1711,14 +1714,20 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
     if (n_jobs <= 0) return SCB_OK;
     if (mem_kind != SCB_MEM_HOST && mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_clone_batch: bad mem kind");
     SCB_CUDA(c, cudaSetDevice(c->device));
-    static const int kChunk = 64;
+    // jobs are planned in chunks (one sync of the prep stream per chunk); ~8 chunks per call keep the lanes fed while the
+    // next chunk's bounding boxes come back, also when a rank of an 8-GPU batch only holds a few dozen jobs
+    static const int kMaxChunk = 64;
+    int kChunk = (n_jobs + 7) / 8;
+    if (kChunk < 8) kChunk = 8;
+    if (kChunk > kMaxChunk) kChunk = kMaxChunk;
+    if (const char* e = std::getenv("SCB_CHUNK")) kChunk = std::atoi(e) > 0 && std::atoi(e) <= kMaxChunk ? std::atoi(e) : kChunk;
     int rc;
     int want_lanes = kDefaultLanes;
     if (const char* e = std::getenv("SCB_LANES")) want_lanes = std::atoi(e) > 0 ? std::atoi(e) : kDefaultLanes;
     if (want_lanes > n_jobs) want_lanes = n_jobs;
     if (want_lanes < c->n_lanes) want_lanes = c->n_lanes;
     if ((rc = ensure_lanes(c, want_lanes))) return rc;
-    if ((rc = ensure_bbox_slots(c, kChunk))) return rc;
+    if ((rc = ensure_bbox_slots(c, kMaxChunk))) return rc;
     const int L = c->n_lanes;
     if (!c->prep) {  // high priority: the next chunk's bounding boxes must not queue behind the lanes' transform kernels
 #ifdef SCB_EMU

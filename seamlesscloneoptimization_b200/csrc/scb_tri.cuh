@@ -12,12 +12,12 @@
 // Parity with OpenCV.  OpenCV's denominators are float32: fl(fl(fx[k] + fy[l]) - 4), with fx, fy themselves rounded
 // to float32.  M uses beta_k = 4 - fx[k] with OpenCV's float32 fx[k] (exact), and the exact fy[l].  The two differ by
 // ~2.4e-7 absolute, which matters only where the denominator is tiny: at the lowest frequencies (measured against
-// cv2.seamlessClone, /tmp-free restatement in tests/test_tri_model.py: exact tridiagonal solve for k >= 32 leaves the
-// byte-exact fraction at the float64 floor; for all k it drops to 41 % at 4K).  So:
-//   * columns k < kTriLowK (one warp per channel) are solved in float64 (their systems have condition ~ (N/pi k)^2),
-//     from the exact float64 row sums where those exist (k < 8: lowfreq_rows_kernel), and
-//   * tri_lowcorr_kernel adds, for k < kTriLowK and l < kTriLowL, the difference between OpenCV's float32 denominator
-//     and the exact one:  Ct_k += -(2/Ny) sum_l sin_l (1/den32[k][l] - 1/den_exact[k][l]) <sin_l, A_k>   (float64 sums).
+// cv2.seamlessClone; numpy model in tests/test_tri_model.py: an exact tridiagonal solve for k >= 32 leaves the byte-exact
+// fraction at the float64 floor; for all k it drops to 41 % at 4K).  So:
+//   * columns k < kTriLowK are solved in float64 (their systems have condition ~ (N / pi k)^2), and
+//   * tri_lowproj_kernel / tri_lowapply_kernel add, for k < kTriLowK and l < kTriLowL, the difference between OpenCV's float32
+//     denominator and the exact one:  Ct_k += -(2/Ny) sum_l sin_l (<sin_l, a_exact_k> / den32[k][l] - <sin_l, a_fft_k> / den[k][l])
+//     in float64, a_exact = the exact float64 row sums where those exist (k < 8: lowfreq_rows_kernel).
 // That block subsumes the 8 x 8 exact low-frequency corner of the FFT engine.
 //
 // LU factors in closed form.  With beta = 2 cosh(theta), rho = exp(-theta), the pivots of M are
