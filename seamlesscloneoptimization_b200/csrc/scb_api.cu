@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <functional>
 #include <string>
 #include <thread>
@@ -1004,22 +1006,89 @@ static void host_copy_rows(const scb_image* dst, scb_image* blend, const scb_geo
     }
 }
 
+// Persistent helper threads for the host-side copy (creating and joining std::threads per call costs ~50 us, a visible part
+// of a 0.8 ms end-to-end clone).  One pool per process; a call hands out row ranges and waits for them.
+class HostPool {
+  public:
+    static HostPool& get() {
+        static HostPool p;
+        return p;
+    }
+    // runs fn(t) for t = 0 .. n-1: t = 0 on the caller, the rest on the pool; returns when all are done
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 1) {
+            fn(0);
+            return;
+        }
+        std::unique_lock<std::mutex> call(call_mu_);  // one caller at a time
+        ensure(n - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            next_ = 1;
+            total_ = n;
+            pending_ = n - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    HostPool() = default;
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void ensure(int n) {
+        while ((int)threads_.size() < n) threads_.emplace_back([this] { loop(); });
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && next_ < total_); });
+            if (stop_) return;
+            while (next_ < total_) {
+                const int t = next_++;
+                const std::function<void(int)>* fn = fn_;
+                lk.unlock();
+                (*fn)(t);
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+            seen = epoch_;
+        }
+    }
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int next_ = 0, total_ = 0, pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 static void host_copy_outside(const scb_image* dst, scb_image* blend, const scb_geometry& g, int max_threads) {
     const size_t bytes = (size_t)3 * dst->cols * dst->rows;
-    int T = (int)(bytes >> 21);  // one thread per 2 MiB
+    int T = (int)(bytes >> 19);  // one thread per 512 KiB (the pool's threads wake in ~10 us; a 1080p frame is 6 MB)
     if (T > max_threads) T = max_threads;
     if (T <= 1) {
         host_copy_rows(dst, blend, g, 0, dst->rows);
         return;
     }
-    std::vector<std::thread> th;
     const int per = (dst->rows + T - 1) / T;
-    for (int t = 1; t < T; ++t) {
+    HostPool::get().run(T, [&](int t) {
         const int a = t * per, b = (a + per < dst->rows) ? a + per : dst->rows;
-        if (a < b) th.emplace_back(host_copy_rows, dst, blend, std::cref(g), a, b);
-    }
-    host_copy_rows(dst, blend, g, 0, per < dst->rows ? per : dst->rows);
-    for (auto& t : th) t.join();
+        if (a < b) host_copy_rows(dst, blend, g, a, b);
+    });
 }
 
 static int host_threads() {
@@ -1796,16 +1865,12 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
         if (mem_kind == SCB_MEM_HOST) {  // blend = dst outside each ROI interior: a parallel-for over the chunk's jobs
             double a = now();
             const int T = host_threads();
-            std::vector<std::thread> th;
-            auto work = [&](int t) {
+            HostPool::get().run(T, [&](int t) {
                 for (int i = t; i < m; i += T) {
                     scb_job& j = jobs[base + i];
                     if (copy_ok[i] && j.blend.data != j.dst.data) host_copy_rows(&j.dst, &j.blend, geoms[i], 0, j.dst.rows);
                 }
-            };
-            for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto& t : th) t.join();
+            });
             t_phase[3] += now() - a;
         }
     }
