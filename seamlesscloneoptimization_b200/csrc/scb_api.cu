@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
 #include <map>
 #include <mutex>
@@ -88,7 +89,8 @@ struct scb_context {
     int n_lanes = 0;
     cudaStream_t prep = nullptr;  // scb_clone_batch: mask uploads + bounding boxes of the next chunk
     std::string err;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};  // scb_clone_batch plans the next chunk on a helper thread
+    std::mutex err_mu;
     std::map<int, DevLenTab> lentabs;   // keyed by n
     std::map<int, float*> filters;      // keyed by ROI extent
     int* bbox_dev = nullptr;     // [slots][4]
@@ -140,7 +142,12 @@ struct scb_plan {
 static thread_local std::string g_create_error;
 
 static int fail(scb_context* c, int code, const std::string& msg) {
-    if (c) c->err = msg; else g_create_error = msg;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->err_mu);
+        c->err = msg;
+    } else {
+        g_create_error = msg;
+    }
     return code;
 }
 #define SCB_CUDA(c, expr)                                                                               \
@@ -673,7 +680,7 @@ extern "C" int scb_set_orientation(scb_context* c, int orientation) {
 }
 extern "C" void* scb_stream(scb_context* c) { return c ? (void*)c->lanes[0].stream : nullptr; }
 extern "C" const char* scb_last_error(const scb_context* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
-extern "C" uint64_t scb_kernel_launches(const scb_context* c) { return c ? c->launches : 0; }
+extern "C" uint64_t scb_kernel_launches(const scb_context* c) { return c ? c->launches.load() : 0; }
 extern "C" const char* scb_status_string(int s) {
     switch (s) {
         case SCB_OK: return "ok";
@@ -1796,7 +1803,7 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
     if (want_lanes > n_jobs) want_lanes = n_jobs;
     if (want_lanes < c->n_lanes) want_lanes = c->n_lanes;
     if ((rc = ensure_lanes(c, want_lanes))) return rc;
-    if ((rc = ensure_bbox_slots(c, kMaxChunk))) return rc;
+    if ((rc = ensure_bbox_slots(c, 2 * kMaxChunk))) return rc;
     const int L = c->n_lanes;
     if (!c->prep) {  // high priority: the next chunk's bounding boxes must not queue behind the lanes' transform kernels
 #ifdef SCB_EMU
@@ -1809,61 +1816,115 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
     }
     int worst = SCB_OK;
     std::string first_error;
+    std::mutex note_mu;
     auto note = [&](scb_job& j, int status) {
         j.status = status;
-        if (status != SCB_OK && worst == SCB_OK) {
-            worst = status;
-            first_error = c->err;
+        if (status != SCB_OK) {
+            std::lock_guard<std::mutex> lk(note_mu);
+            if (worst == SCB_OK) {
+                worst = status;
+                std::lock_guard<std::mutex> lk2(c->err_mu);
+                first_error = c->err;
+            }
         }
     };
-    std::vector<scb_plan*> plans(kChunk);
-    std::vector<PlanInput> inputs(kChunk);
+    // Two chunk states: while this thread queues the solves of chunk k on the lanes, a helper thread plans chunk k+1
+    // (mask uploads, bounding boxes, the one sync of the prep stream, geometry, erosion, tables) -- the batch path is
+    // host-bound (~3 us per CUDA call, ~20 calls per job), so the two phases are worth overlapping.
+    struct Chunk {
+        std::vector<scb_plan*> plans;
+        std::vector<PlanInput> inputs;
+        std::vector<int> planned;  // plan_finish succeeded
+        int base = 0, m = 0, rc = SCB_OK;
+    } chunks[2];
+    for (auto& ch : chunks) {
+        ch.plans.resize(kChunk);
+        ch.inputs.resize(kChunk);
+        ch.planned.resize(kChunk);
+    }
     std::vector<scb_geometry> geoms(kChunk);
     std::vector<char> copy_ok(kChunk);
     // SCB_BATCH_TRACE=1: host wall time of each phase of the batch (stderr), for tuning
     static const bool trace = std::getenv("SCB_BATCH_TRACE") != nullptr;
     double t_phase[5] = {0, 0, 0, 0, 0};
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    for (int base = 0; base < n_jobs; base += kChunk) {
-        const int m = (n_jobs - base < kChunk) ? n_jobs - base : kChunk;
+    auto plan_chunk = [&](Chunk& ch, int base, int parity) {
+        ch.base = base;
+        ch.m = (n_jobs - base < kChunk) ? n_jobs - base : kChunk;
+        ch.rc = SCB_OK;
+        if (cudaSetDevice(c->device) != cudaSuccess) {
+            ch.rc = fail(c, SCB_ERR_CUDA, "scb_clone_batch: cudaSetDevice failed on the planning thread");
+            ch.m = 0;
+            return;
+        }
         double t0 = now();
-        for (int i = 0; i < m; ++i) {
+        for (int i = 0; i < ch.m; ++i) {
             scb_job& j = jobs[base + i];
-            plans[i] = nullptr;
+            ch.plans[i] = nullptr;
+            ch.planned[i] = 0;
             if (!j.src.data || !j.dst.data || !j.blend.data) {
                 note(j, fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_clone_batch: null image"));
                 continue;
             }
-            note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, i, &plans[i], &inputs[i]));
+            note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, parity * kMaxChunk + i,
+                               &ch.plans[i], &ch.inputs[i]));
         }
         double t1 = now();
-        SCB_CUDA(c, cudaStreamSynchronize(c->prep));
-        SCB_CUDA(c, cudaGetLastError());
+        cudaError_t e = cudaStreamSynchronize(c->prep);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            ch.rc = fail(c, SCB_ERR_CUDA, std::string("scb_clone_batch: ") + cudaGetErrorString(e));
+            for (int i = 0; i < ch.m; ++i)
+                if (ch.plans[i]) {
+                    scb_plan_destroy(ch.plans[i]);
+                    ch.plans[i] = nullptr;
+                }
+            return;
+        }
         double t2 = now();
+        for (int i = 0; i < ch.m; ++i) {
+            if (!ch.plans[i]) continue;
+            const int st = plan_finish(ch.plans[i], ch.inputs[i]);  // destroys the plan on failure
+            if (st != SCB_OK) {
+                ch.plans[i] = nullptr;
+                note(jobs[base + i], st);
+            } else {
+                ch.planned[i] = 1;
+            }
+        }
+        double t3 = now();
         t_phase[0] += t1 - t0;
         t_phase[1] += t2 - t1;
+        t_phase[2] += t3 - t2;
+    };
+    const int n_chunks = (n_jobs + kChunk - 1) / kChunk;
+    plan_chunk(chunks[0], 0, 0);
+    for (int k = 0; k < n_chunks; ++k) {
+        Chunk& ch = chunks[k & 1];
+        if (ch.rc != SCB_OK) return ch.rc;
+        std::thread planner;
+        const bool more = k + 1 < n_chunks;
+#ifdef SCB_EMU
+        if (more) plan_chunk(chunks[(k + 1) & 1], (k + 1) * kChunk, (k + 1) & 1);  // the interpreter runs kernels on the calling thread: no helper
+#else
+        if (more) planner = std::thread(plan_chunk, std::ref(chunks[(k + 1) & 1]), (k + 1) * kChunk, (k + 1) & 1);
+#endif
+        const int base = ch.base, m = ch.m;
+        double b0 = now();
         for (int i = 0; i < m; ++i) {
-            if (!plans[i]) continue;
+            copy_ok[i] = 0;
+            geoms[i] = scb_geometry();
+            if (!ch.plans[i] || !ch.planned[i]) continue;
             scb_job& j = jobs[base + i];
-            double a = now();
-            int st = plan_finish(plans[i], inputs[i]);  // destroys the plan on failure
-            double b = now();
-            t_phase[2] += b - a;
-            scb_geometry gtmp{};
-            if (st == SCB_OK) {
-                StageTimer tm;
-                gtmp = plans[i]->g;
-                st = execute_impl(plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host=*/true);
-                scb_plan_destroy(plans[i]);  // stream-ordered frees: the queued kernels finish first
-            }
-            t_phase[3] += now() - b;
-            plans[i] = nullptr;
-            geoms[i] = st == SCB_OK ? gtmp : scb_geometry();
+            StageTimer tm;
+            geoms[i] = ch.plans[i]->g;
+            const int st = execute_impl(ch.plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host=*/true);
+            scb_plan_destroy(ch.plans[i]);  // stream-ordered frees: the queued kernels finish first
+            ch.plans[i] = nullptr;
             copy_ok[i] = (st == SCB_OK);
             note(j, st);
         }
         if (mem_kind == SCB_MEM_HOST) {  // blend = dst outside each ROI interior: a parallel-for over the chunk's jobs
-            double a = now();
             const int T = host_threads();
             HostPool::get().run(T, [&](int t) {
                 for (int i = t; i < m; i += T) {
@@ -1871,8 +1932,9 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
                     if (copy_ok[i] && j.blend.data != j.dst.data) host_copy_rows(&j.dst, &j.blend, geoms[i], 0, j.dst.rows);
                 }
             });
-            t_phase[3] += now() - a;
         }
+        t_phase[3] += now() - b0;
+        if (planner.joinable()) planner.join();
     }
     {
         double a = now();
