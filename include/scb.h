@@ -163,6 +163,7 @@ typedef struct scb_job {
     scb_image src, dst, mask, blend;
     int32_t px, py;
     int32_t status; /* out */
+    int32_t flags;  /* cv::seamlessClone flags of this job; 0 = SCB_NORMAL_CLONE */
 } scb_job;
 int scb_clone_batch(scb_context* ctx, scb_job* jobs, int n_jobs, int mem_kind);
 

@@ -55,7 +55,7 @@ class ScbGeometry(C.Structure):
 
 
 class ScbJob(C.Structure):
-    _fields_ = [("src", ScbImage), ("dst", ScbImage), ("mask", ScbImage), ("blend", ScbImage), ("px", C.c_int32), ("py", C.c_int32), ("status", C.c_int32)]
+    _fields_ = [("src", ScbImage), ("dst", ScbImage), ("mask", ScbImage), ("blend", ScbImage), ("px", C.c_int32), ("py", C.c_int32), ("status", C.c_int32), ("flags", C.c_int32)]
 
 
 class ScbError(RuntimeError):

@@ -1867,7 +1867,7 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
                 continue;
             }
             note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, parity * kMaxChunk + i,
-                               &ch.plans[i], &ch.inputs[i]));
+                               &ch.plans[i], &ch.inputs[i], j.flags ? j.flags : SCB_NORMAL_CLONE));
         }
         double t1 = now();
         cudaError_t e = cudaStreamSynchronize(c->prep);

@@ -294,9 +294,11 @@ def test_batch_of_independent_jobs(be, ctx):
         src, dst, mask, p = so.materialise_job(j, dst_hw=(140, 200), sigma=2.0)
         blend = np.zeros_like(dst)
         keep.append((src, dst, mask, blend))
-        refs.append(so.restate(src, dst, mask, p, transform="f64"))
+        flags = (0, capi.MIXED_CLONE, capi.MONOCHROME_TRANSFER, capi.NORMAL_CLONE)[k % 4]  # per-job cv::seamlessClone flags; 0 = NORMAL_CLONE
+        refs.append(so.restate(src, dst, mask, p, flags=flags or so.NORMAL_CLONE, transform="f64"))
         arr[k].src, arr[k].dst, arr[k].mask, arr[k].blend = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(blend)
         arr[k].px, arr[k].py = p
+        arr[k].flags = flags
     rc = ctx.lib.scb_clone_batch(ctx.handle, arr, len(jobs), scb.MEM_HOST)
     assert rc == 0
     for k in range(len(jobs)):
