@@ -512,7 +512,10 @@ __global__ void __launch_bounds__(FftCfg<LOG2M>::T) rows_inv_kernel(RowsInvParam
 //   amplifies it at the lowest bins only.  Recomputing the kLowK x kLowK corner exactly removes
 //   > 95 % of the solve's error energy for ~1 % extra work (DESIGN.md "low-frequency refinement").
 // ---------------------------------------------------------------------------------------------
-static constexpr int kLowKDev = 8;
+#ifndef SCB_LOWK
+#define SCB_LOWK 4
+#endif
+static constexpr int kLowKDev = SCB_LOWK;  // == kLowK of scb_tables.h
 static constexpr int kLowThreads = 128;
 
 template <int NACC>

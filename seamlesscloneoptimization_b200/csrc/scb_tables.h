@@ -15,7 +15,10 @@
 
 namespace scb {
 
-static const int kLowK = 8;          // low-frequency corner refined exactly (kLowK x kLowK bins)
+#ifndef SCB_LOWK
+#define SCB_LOWK 4
+#endif
+static const int kLowK = SCB_LOWK;   // lowest frequencies per axis whose row sums are taken exactly (float64)
 static const int kMaxLog2M = 14;     // longest convolution: 16384  ->  n <= 8192 unknowns per line
 static const int kMinLog2M = 5;
 

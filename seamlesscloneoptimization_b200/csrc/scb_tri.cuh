@@ -17,7 +17,7 @@
 //   * columns k < kTriLowK are solved in float64 (their systems have condition ~ (N / pi k)^2), and
 //   * tri_lowproj_kernel / tri_lowapply_kernel add, for k < kTriLowK and l < kTriLowL, the difference between OpenCV's float32
 //     denominator and the exact one:  Ct_k += -(2/Ny) sum_l sin_l (<sin_l, a_exact_k> / den32[k][l] - <sin_l, a_fft_k> / den[k][l])
-//     in float64, a_exact = the exact float64 row sums where those exist (k < 8: lowfreq_rows_kernel).
+//     in float64, a_exact = the exact float64 row sums where those exist (k < kLowK: lowfreq_rows_kernel).
 // That block subsumes the 8 x 8 exact low-frequency corner of the FFT engine.
 //
 // LU factors in closed form.  With beta = 2 cosh(theta), rho = exp(-theta), the pivots of M are
