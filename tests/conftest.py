@@ -26,4 +26,9 @@ def cuda_lib():
 
     if not os.path.exists(ge.LIB):
         ge.build_cuda()
+    else:
+        import torch
+
+        if not torch.cuda.is_available():  # authoring container: keep the library in step with the sources (mtime check);
+            ge.build_cuda()                # on the GPU box the shipped library is used as it is
     return ge.LIB
