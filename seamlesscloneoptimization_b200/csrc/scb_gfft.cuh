@@ -116,6 +116,9 @@ SCB_HD constexpr int gtw_total_c(int log2m) { return gtw_offset16(log2m, 16); }
 #ifndef SCB_NG1_FROM
 #define SCB_NG1_FROM 9
 #endif
+#ifndef SCB_TW_SMEM_LOG2M
+#define SCB_TW_SMEM_LOG2M 0
+#endif
 #ifndef SCB_G1_FROM
 #define SCB_G1_FROM 12
 #endif
@@ -133,7 +136,7 @@ struct GCfg {
     // Twiddle tables live in shared memory when the CTA owns the SM anyway (M >= 4096: 17 KB / 81 KB
     // next to 209 KB / 139 KB of data).  At max carveout L1 is only ~24 KB and every table read would
     // otherwise pay L2 latency (ncu: long-scoreboard was the top stall of the fused passes).
-    static constexpr bool TW_SMEM = false;  // tried for M >= 4096: generic-pointer loads + spills made the column pass 15 % slower
+    static constexpr bool TW_SMEM = (LOG2M == SCB_TW_SMEM_LOG2M);  // experiment switch; see DESIGN.md section 5
     static constexpr int TW_F4 = gtw_total_c(LOG2M);
     static constexpr size_t SMEM = DATA_BYTES + (TW_SMEM ? (size_t)TW_F4 * sizeof(float4) : 0);
 };
@@ -153,12 +156,12 @@ SCB_D void group_sync(int group, int nthreads) {
 }
 
 // twiddles of one butterfly: wre[q] + i wim[q] = W_L^{iq}, q = 1..R-1
-template <int R>
+template <int R, bool SMEM_TABLE = false>
 SCB_D void load_twiddles(const float4* __restrict__ tws, int S, int i, float (&wre)[16], float (&wim)[16]) {
     constexpr int ROWS = gtw_rows(R);
     float4 t[ROWS];
     SCB_UNROLL
-    for (int j = 0; j < ROWS; ++j) t[j] = __ldg(tws + j * S + i);
+    for (int j = 0; j < ROWS; ++j) t[j] = SMEM_TABLE ? tws[j * S + i] : __ldg(tws + j * S + i);
     SCB_UNROLL
     for (int j = 0; j < ROWS; ++j) {
         wre[2 * j + 1] = t[j].x;
@@ -216,7 +219,7 @@ SCB_D void gpass(const float4* __restrict__ tws, int gtid, const In& in, const O
         const int i = b & (S - 1);
         const int base = (b / S) * L + i;
         float wre[16], wim[16];
-        load_twiddles<R>(tws, S, i, wre, wim);
+        load_twiddles<R, GCfg<LOG2M>::TW_SMEM>(tws, S, i, wre, wim);
         P4 v[R];
         SCB_UNROLL
         for (int r = 0; r < R; ++r) v[r] = in(base + r * S);
@@ -245,7 +248,7 @@ SCB_D void gpass_bridge(const float4* __restrict__ tws, int gtid, const Planes& 
     for (int b = gtid; b < C::M / R; b += C::G) {
         const int i = b;  // L == M: a single group of sub-transforms
         float wre[16], wim[16];
-        load_twiddles<R>(tws, S, i, wre, wim);
+        load_twiddles<R, GCfg<LOG2M>::TW_SMEM>(tws, S, i, wre, wim);
         P4 v[R];
         SCB_UNROLL
         for (int r = 0; r < R; ++r) v[r] = in(i + r * S);
