@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Turn what a gpurun call brought back in gpurun_out/ into the tracked summaries under profiles/:
+
+  final_launches.csv   (ncu --metrics gpu__time_duration.sum --clock-control none ... bench.py)   -> profiles/<tag>_launches_cfg2.csv,
+                                                                                                   profiles/kernel_times.json
+  final_prof.ncu-rep   (ncu --set full --clock-control none --import-source on ... bench.py)      -> profiles/<tag>_ncu_full_cfg2.txt,
+                                                                                                   profiles/traffic.json
+  final_bench_*.json, final_pytest_gpu.log, final_parity.txt                                        -> profiles/<tag>_*
+
+  python tools/summarise_profiles.py [tag]        (default tag r1_final; needs `ncu` on PATH to read the .ncu-rep)"""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_shared_mem",
+        "launch__occupancy_limit_registers", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max"]
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def copy(src, dst):
+    if os.path.exists(os.path.join(OUT, src)):
+        shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
+
+
+for w in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+    copy(f"final_bench_{w}.json", f"{tag}_bench_{w}.json")
+copy("final_bench_ref.json", f"{tag}_bench_cfg2_reference.json")
+copy("final_pytest_gpu.log", f"{tag}_pytest_gpu.log")
+copy("final_parity.txt", f"{tag}_parity_vs_cv2.txt")
+copy("final_launches.csv", f"{tag}_launches_cfg2.csv")
+
+launches = os.path.join(PROF, f"{tag}_launches_cfg2.csv")
+if os.path.exists(launches):
+    agg = collections.defaultdict(list)
+    for row in csv.DictReader(l for l in open(launches) if not l.startswith("==")):
+        agg[row["Kernel Name"]].append(float(row["Metric Value"].replace(",", "")) / 1e6)  # ns -> ms
+
+    def full_size(sub):  # the device-resident step launches the full ROI; the banded host path launches smaller pieces
+        v = [max(x) for k, x in agg.items() if sub in k]
+        return max(v) if v else None
+
+    kt = {"cfg2": {"rhs": full_size("rhs_kernel"), "rows_fwd": full_size("rows_fwd"), "rows_inv": full_size("rows_inv"), "cols": full_size("tri_solve_kernel"),
+                   "_note": f"gpu__time_duration.sum (ms) of the full-size launch, profiles/{tag}_launches_cfg2.csv (ncu --metrics gpu__time_duration.sum --clock-control none: "
+                            "cold cache, serialised); cols = tri_solve_kernel alone"}}
+    json.dump(kt, open(os.path.join(PROF, "kernel_times.json"), "w"), indent=1)
+    total = sum(sum(v) for v in agg.values())
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{100 * sum(v) / total:6.2f} %  n={len(v):3d}  mean {1e3 * sum(v) / len(v):8.2f} us  max {1e3 * max(v):8.2f} us  {k[:70]}")
+
+rep = os.path.join(OUT, "final_prof.ncu-rep")
+if os.path.exists(rep) and shutil.which("ncu"):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = [f"# ncu --set full --clock-control none, bench.py cfg2 (ROI 1810x1339), tridiagonal engine; report gpurun_out/final_prof.ncu-rep (not committed)"]
+    seen, traffic = set(), {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if name in seen:
+            continue
+        seen.add(name)
+        out.append("\n" + name)
+        for w in WANT:
+            if w in hdr:
+                out.append(f"  {w:70s} {r[hdr.index(w)]} {units[hdr.index(w)]}")
+        stalls = [(num(r[i]), h) for i, h in enumerate(hdr) if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio") and num(r[i]) is not None]
+        for v, h in sorted(stalls, reverse=True)[:5]:
+            out.append(f"  stall {v:7.3f} {h.split('stalled_')[1].split('_per_issue')[0]}")
+        i, j = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        traffic[name.split("(")[0]] = num(r[i]) * SCALE[units[i]] + num(r[j]) * SCALE[units[j]]
+    open(os.path.join(PROF, f"{tag}_ncu_full_cfg2.txt"), "w").write("\n".join(out) + "\n")
+    pick = lambda sub: next((v for k, v in traffic.items() if sub in k), None)
+    t = {"cfg2": {"rows_fwd": pick("rows_fwd"), "rows_inv": pick("rows_inv"), "cols": pick("tri_solve"), "rhs": pick("rhs_kernel"),
+                  "_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of bench.py cfg2, profiles/{tag}_ncu_full_cfg2.txt "
+                           "(writes mostly stay in the 126 MB L2 during ncu's kernel replay); cols = tri_solve_kernel"}}
+    json.dump(t, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
+
+for w in ("cfg2", "cfg1", "cfg5", "cfg4", "cfg3"):
+    f = os.path.join(PROF, f"{tag}_bench_{w}.json")
+    if os.path.exists(f):
+        d = json.load(open(f))
+        print(w, "Mpix/s", round(d["value"]), "ms", round(d["ms_per_step"], 4), "| e2e Mpix/s", round(d["e2e"]["value"]), "ms", round(d["e2e"]["ms_per_step"], 4),
+              "| cpu", round((d.get("cpu_baseline") or {}).get("value") or 0, 2), "| roofline", (d.get("roofline") or {}).get("frac"), (d.get("roofline_stencil") or {}).get("frac_ncu"))
