@@ -557,3 +557,44 @@ def test_clone_flags_vs_oracle(ctx, flags, seed):
     plan.close()
     one_shot = ctx.seamless_clone(src, dst, mask, p, flags)
     assert np.array_equal(one_shot, blend)
+
+
+def test_sharded_tri_entry_points_validate_their_arguments(be):
+    """scb_plan_tri_* refuse plans of another engine, segment ranges outside the plan's, and host-resident images."""
+    src, dst, mask, p = so.make_config("small", 12)
+    vs, hs = be.to_device(src)
+    vd, hd = be.to_device(dst)
+    vm, hm = be.to_device(mask)
+    vb, hb = be.to_device(dst)
+    ctx = be.context()
+    try:
+        ctx.set_engine(capi.ENGINE_TRI)
+        plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+        seg_len, n_segs = C.c_int(), C.c_int()
+        n32, n64, nw = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        assert ctx.lib.scb_plan_tri_layout(plan.handle, C.byref(seg_len), C.byref(n_segs), C.byref(n32), C.byref(n64), C.byref(nw)) == 0
+        g = plan.geometry
+        assert 1 <= n_segs.value <= 16 and (n_segs.value - 1) * seg_len.value < g.ny <= n_segs.value * seg_len.value
+        e32, h32 = be.dev_buffer(n32.value, np.float32)
+        e64, h64 = be.dev_buffer(n64.value + nw.value, np.float64)
+        wd = e64 + 8 * n64.value
+        assert ctx.lib.scb_plan_tri_forward(plan.handle, C.byref(vs), C.byref(vd), scb.MEM_DEVICE, 0, n_segs.value + 1, e32, e64, wd) == capi.SCB_ERR_INVALID_ARGUMENT
+        assert ctx.lib.scb_plan_tri_forward(plan.handle, C.byref(vs), C.byref(vd), scb.MEM_HOST, 0, n_segs.value, e32, e64, wd) == capi.SCB_ERR_UNSUPPORTED
+        # one "rank" owning every segment == the plain solve
+        ctx._check(ctx.lib.scb_plan_tri_forward(plan.handle, C.byref(vs), C.byref(vd), scb.MEM_DEVICE, 0, n_segs.value, e32, e64, wd))
+        ctx._check(ctx.lib.scb_plan_tri_finish(plan.handle, C.byref(vb), scb.MEM_DEVICE, 0, n_segs.value, e32, e64, wd))
+        ctx.sync()
+        vb1, hb1 = be.to_device(np.zeros_like(dst))
+        plan.execute(vs, vd, vb1, scb.MEM_DEVICE)
+        ctx.sync()
+        assert np.array_equal(be.to_host(hb), be.to_host(hb1))
+        plan.close()
+        ctx.set_engine(capi.ENGINE_FFT)
+        plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+        assert ctx.lib.scb_plan_tri_forward(plan.handle, C.byref(vs), C.byref(vd), scb.MEM_DEVICE, 0, 1, e32, e64, wd) == capi.SCB_ERR_UNSUPPORTED
+        plan.close()
+        assert ctx.lib.scb_set_orientation(ctx.handle, 2) == capi.SCB_ERR_INVALID_ARGUMENT
+        h = C.c_void_p()
+        assert ctx.lib.scb_plan_create_ex(ctx.handle, C.byref(vm), scb.MEM_DEVICE, src.shape[0], src.shape[1], dst.shape[0], dst.shape[1], p[0], p[1], 7, C.byref(h)) == capi.SCB_ERR_UNSUPPORTED
+    finally:
+        ctx.close()
