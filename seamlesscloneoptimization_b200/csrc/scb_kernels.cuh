@@ -12,6 +12,9 @@
 //   cols     : DST-I along y -> / (fx + fy - 4) -> inverse DST-I along y
 //   rows_inv : inverse DST-I along x -> clamp + truncate -> u8
 // so a pixel makes three HBM round trips (7+12 | 12+12 | 12+3 = 58 B per solved RGB pixel).
+// The default engine (SCB_ENGINE_TRI, scb_tri.cuh) keeps rows_fwd / rows_inv and replaces `cols` by a tridiagonal solve of every
+// spectral column on the NATURAL layout A [3][ny][nx] -> Ct [3][ny][nx]; the kernels below then serve the x axis only, and
+// cols_kernel / lowfreq_cols_kernel the FFT-on-both-axes engine and its row/column-sharded entry points.
 //
 // What each piece replaces in the reference (/root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp):
 //   rhs_pixel            pre_process_kernel_gradient :1920-1964 + pre_process_kernel_lapXY :1966-2018
