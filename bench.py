@@ -294,7 +294,10 @@ def roofline_objects(stages, px, workload):
             o["frac_ncu"] = alg / (nd * 1e-3) / 1e9 / peak
         return o
 
-    return obj(dom), obj("rhs")
+    d = obj(dom)
+    d["note"] = ("the FFT row passes are bound by the shared-memory and FMA pipes of the SM, not by HBM (DESIGN.md section 5); the HBM/L2-bound kernels "
+                 "of the path are the stencil (roofline_stencil) and the tridiagonal column solve (roofline_column_solve)")
+    return d, obj("rhs"), obj("cols")
 
 
 def single_job_leg(env: Env, args):
@@ -367,7 +370,7 @@ def single_job_leg(env: Env, args):
     total_ms_max, e2e_ms_max = env.max_over_ranks(sum(step_ms), sum(e2e_ts) * 1e3)
     line = None
     if env.rank == 0:
-        roof, roof_st = roofline_objects(stages, px, args.workload)
+        roof, roof_st, roof_cols = roofline_objects(stages, px, args.workload)
         e2e_call = ("scb_plan_execute(HOST pinned frames, plan reused): ROI H2D + solve + ROI D2H + dst->blend host copy" if stream_plan is not None else
                     "scb_seamless_clone(HOST pinned buffers): mask prep + ROI H2D + solve + ROI D2H + dst->blend host copy")
         line = {
@@ -382,7 +385,7 @@ def single_job_leg(env: Env, args):
                     "ms_per_step": e2e_ms_max / args.steps, "p50_ms": 1e3 * statistics.median(e2e_ts), "p99_ms": 1e3 * percentile(e2e_ts, 0.99), "call": e2e_call},
             "gpu_launches": int(launches),
             "p50_ms_device": statistics.median(step_ms), "p99_ms_device": percentile(step_ms, 0.99),
-            "stages_ms": stages, "roofline": roof, "roofline_stencil": roof_st,
+            "stages_ms": stages, "roofline": roof, "roofline_stencil": roof_st, "roofline_column_solve": roof_cols,
         }
     if stream_plan is not None:
         stream_plan.close()
