@@ -41,7 +41,10 @@ static constexpr int kTriLowL = 32;  // ... for this many lowest frequencies alo
 #endif
 static constexpr int kTriCols = SCB_TRI_COLS;  // columns per CTA: 16 -> 64-byte rows per segment, twice the CTAs (171 CTAs of 32 columns left 23 of the 148 SMs with two CTAs and the rest with one)
 static_assert(32 % kTriCols == 0 && kTriLowK % kTriCols == 0, "column tiles must pack into warps and split the float64 block evenly");
-static constexpr int kTriSegs = 16;  // segments per column (warps of a CTA)
+#ifndef SCB_TRI_SEGS
+#define SCB_TRI_SEGS 16
+#endif
+static constexpr int kTriSegs = SCB_TRI_SEGS;  // segments per column
 #ifndef SCB_TRI_UNROLL
 #define SCB_TRI_UNROLL 8
 #endif
