@@ -17,6 +17,8 @@ def emu_lib():
     """The g++ -DSCB_EMU build of the kernel + driver sources (CI checker; tests/emu/README)."""
     import __graft_entry__ as ge
 
+    if os.environ.get("SCB_EMU_LIBRARY"):  # e.g. the AddressSanitizer build made by tools/asan_emu.sh
+        return os.environ["SCB_EMU_LIBRARY"]
     return ge.build_emu()
 
 
