@@ -7,8 +7,12 @@ set -e
 cd "$(dirname "$0")/.."
 OUT=${ASAN_OUT:-/tmp/scb_asan}
 mkdir -p "$OUT"
-g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -DSCB_EMU -x c++ -Itests/emu -Iseamlesscloneoptimization_b200/csrc -ffp-contract=off \
-    -shared -fPIC -Wno-unknown-pragmas seamlesscloneoptimization_b200/csrc/scb_api.cu -o "$OUT/libscb_emu_asan.so" -lpthread
+LIB="$OUT/libscb_emu_asan.so"
+if [ ! -e "$LIB" ] || [ -n "$(find seamlesscloneoptimization_b200/csrc include tests/emu/emu_cuda.h -newer "$LIB" -type f | head -1)" ]; then
+    # one translation unit with every kernel template instantiated: ~20 minutes with -fsanitize=address -g
+    g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -DSCB_EMU -x c++ -Itests/emu -Iseamlesscloneoptimization_b200/csrc -ffp-contract=off \
+        -shared -fPIC -Wno-unknown-pragmas seamlesscloneoptimization_b200/csrc/scb_api.cu -o "$LIB" -lpthread
+fi
 export LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1   # fibers: swapcontext is only partly supported
 SCB_LIBRARY="$OUT/libscb_emu_asan.so" python tools/sanitize_smoke.py 2>&1 | grep -v "doesn't fully support makecontext"
