@@ -117,6 +117,8 @@ const char* scb_last_error(const scb_context* ctx); /* ctx may be NULL: error of
 const char* scb_status_string(int status);
 uint64_t scb_kernel_launches(const scb_context* ctx); /* kernels this library has launched on ctx so far */
 int scb_device_count(void);
+/* 16 hex digits: hash of the sources the library was built from (the test fixture compares it with the tree and rebuilds a stale library) */
+const char* scb_source_hash(void);
 /* Chooses the DST engine of plans created afterwards (SCB_ENGINE_*).  The reference makes the same choice at
  * compile time: SC_FFT_ENABLE, seamlessClone_imp.h:15 (cuFFT solver vs cuBLAS sine-basis solver). */
 int scb_set_engine(scb_context* ctx, int engine);

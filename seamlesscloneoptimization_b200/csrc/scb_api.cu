@@ -693,6 +693,14 @@ extern "C" const char* scb_status_string(int s) {
     }
     return "unknown status";
 }
+#ifndef SCB_SOURCE_HASH_STR
+#define SCB_SOURCE_HASH_STR "unstamped-build!"
+#endif
+// hash of the sources this library was built from (__graft_entry__.source_hash); the test fixture compares it with the tree
+extern "C" const char* scb_source_hash(void) {
+    static const char stamp[] = "SCB_SOURCE_HASH=" SCB_SOURCE_HASH_STR;
+    return stamp + 16;
+}
 extern "C" int scb_host_alloc(void** out, size_t bytes) {
     if (!out) return SCB_ERR_INVALID_ARGUMENT;
     return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? SCB_OK : SCB_ERR_OUT_OF_MEMORY;

@@ -24,9 +24,17 @@ The reference has no multi-GPU path at all; its single-GPU pipel
 /root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp:2105-2135.
 
 torch is used for buffers, pack/unpack copies and the collective: plumbing around the C ABI calls.
+
+Stream contract: the C-ABI passes run on the Context's own stream (scb_stream), which is NOT torch's current stream unless
+the caller made it so.  Every torch op and collective of this module is therefore issued under
+`torch.cuda.stream(ExternalStream(ctx.stream))`, i.e. on the very stream the passes run on, so the passes, the pack/unpack
+copies and the NCCL calls are ordered by the stream itself whatever stream the caller is on.  (On CPU tensors -- the gloo /
+emulator tests -- everything is synchronous and the guard is a no-op.)  Between scb_plan_tri_forward and scb_plan_tri_finish
+the field lives in the CONTEXT's workspace: run no other plan of the same context in between.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -48,6 +56,8 @@ def split(n: int, parts: int) -> list[int]:
 class ShardedSolve:
     def __init__(self, ctx: Context, plan: Plan, device: torch.device, group=None):
         self.ctx, self.plan, self.device, self.group = ctx, plan, device, group
+        # all torch work of this object is issued on the context's stream (see the module docstring)
+        self._stream = torch.cuda.ExternalStream(ctx.stream, device=device) if device.type == "cuda" else None
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         g = plan.geometry
@@ -121,9 +131,17 @@ class ShardedSolve:
             Ct3[:, ys[r] : ys[r + 1], xs[s] : xs[s + 1]].copy_(recv[s])
 
     # -- the solve ---------------------------------------------------------------------------------
+    def _on_ctx_stream(self):
+        return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
+
     def run(self, src_view, dst_view, blend_view) -> None:
-        """All images device resident (ScbImage views).  On return (stream order) the own interior rows
-        of `blend` are solved; blend must already hold a copy of dst (or alias it)."""
+        """All images device resident (ScbImage views).  On return (order of the context's stream) the own interior rows
+        of `blend` are solved; blend must already hold a copy of dst (or alias it).  Inputs written on another stream
+        must be complete (or ordered by an event) before the call, as for any scb_plan_execute(DEVICE)."""
+        with self._on_ctx_stream():
+            self._run(src_view, dst_view, blend_view)
+
+    def _run(self, src_view, dst_view, blend_view) -> None:
         lib, ph, r = self.ctx.lib, self.plan.handle, self.rank
         chk = self.ctx._check
         if self.tri:
@@ -148,6 +166,10 @@ class ShardedSolve:
         """Make every rank's `blend` (H,W,3 u8 tensor) complete: all-gather the solved interior row slabs."""
         if self.world == 1:
             return
+        with self._on_ctx_stream():
+            self._gather_rows(blend)
+
+    def _gather_rows(self, blend: torch.Tensor) -> None:
         g = self.plan.geometry
         x0, x1 = g.rx + 1, g.rx + g.w - 1
         slabs = [torch.empty((self.ys[s + 1] - self.ys[s], x1 - x0, 3), dtype=torch.uint8, device=self.device) for s in range(self.world)]

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: tens of seconds of CPU oracle work (the 8K comparison against cv2)")
+    config.addinivalue_line("markers", "multigpu: spawns torchrun over >= 2 GPUs (skipped on a 1-GPU box)")
 
 
 @pytest.fixture(scope="session")
@@ -24,13 +26,9 @@ def emu_lib():
 
 @pytest.fixture(scope="session")
 def cuda_lib():
+    """libscb.so, guaranteed to be built from the sources in the tree: the library carries a hash of its sources
+    (scb_source_hash) which is compared with the tree here -- on the GPU box too, where file times mean nothing after
+    the snapshot copy -- and the library is rebuilt when they differ."""
     import __graft_entry__ as ge
 
-    if not os.path.exists(ge.LIB):
-        ge.build_cuda()
-    else:
-        import torch
-
-        if not torch.cuda.is_available():  # authoring container: keep the library in step with the sources (mtime check);
-            ge.build_cuda()                # on the GPU box the shipped library is used as it is
-    return ge.LIB
+    return ge.build_cuda()

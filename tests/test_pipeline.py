@@ -72,18 +72,29 @@ def roi_interior(img, g):
     return img[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
 
 
-def assert_matches(blend, ref_blend, g, what="", u_ref=None):
-    """+-1 LSB everywhere; >= 99.9 % exact.  Truncation makes a pixel whose exact value sits ON an
-    integer flip under any float noise (OpenCV's own included), so pixels whose oracle value lies
-    within the float tolerance of an integer are not counted as mismatches (they still must be +-1)."""
+def cv_blend(src, dst, mask, p, flags=so.NORMAL_CLONE):
+    """The u8 reference of every parity test: cv2.seamlessClone itself on the same inputs (the oracle's transform="cv"
+    restatement is pinned bit-exact against it in tests/test_oracle.py; the float64 restatement is used for the
+    1e-4 checks of the float intermediates only)."""
+    return so.cv_reference(src, dst, mask, p, flags)
+
+
+def assert_matches(blend, ref_blend, g, what="", floor_blend=None, floor_solved=None):
+    """+-1 LSB everywhere and >= 99.9 % of the solved bytes exact, against cv2.seamlessClone.  Every byte counts:
+    pixels whose exact value sits on an integer (where truncation flips under any float noise) are NOT exempt.
+    `floor_blend` (the oracle's float64 restatement) is given by the tests of tiny ROIs only: a 1 x 1 or 2 x 5 system has
+    a rational solution with a small denominator, so whole pixels sit exactly on integers and cv2's own float32 DFT noise
+    decides their bytes; there the bar is the float64 solve's own mismatch count against cv2 plus the number of bytes whose
+    float64 solution lies within 1e-4 of an integer (`floor_solved`), plus the usual allowance."""
     a, b = roi_interior(blend, g), roi_interior(ref_blend, g)
     cmp = so.compare_u8(a, b)
     assert cmp["max_abs"] <= common.U8_MAX_ABS, (what, cmp)
-    diff = a != b
-    if u_ref is not None:
-        on_boundary = np.abs(u_ref - np.rint(u_ref)) < common.FLOAT_REL_TOL * 255.0
-        diff = diff & ~on_boundary
-    assert int(diff.sum()) <= common.allowed_mismatches(a.size), (what, cmp)
+    allowed = common.allowed_mismatches(a.size)
+    if floor_blend is not None:
+        allowed += so.compare_u8(roi_interior(floor_blend, g), b)["n_diff"]
+    if floor_solved is not None:
+        allowed += int((np.abs(floor_solved - np.rint(floor_solved)) < 1e-4).sum())
+    assert cmp["n_diff"] <= allowed, (what, cmp, allowed)
     outside = np.ones(blend.shape[:2], bool)
     outside[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = False
     assert np.array_equal(blend[outside], ref_blend[outside]), what
@@ -110,7 +121,7 @@ def test_configs_vs_oracle(ctx, cfg, seed):
     if plan.engine != capi.ENGINE_TRI:  # the tridiagonal engine never forms the 2-D spectrum
         assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
     assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
-    assert_matches(blend, ref.blend, g, cfg, ref.solved)
+    assert_matches(blend, cv_blend(src, dst, mask, p), g, cfg)
     plan.close()
 
 
@@ -139,7 +150,8 @@ def _run_size(ctx, w, h, seed=0):
     if plan.engine != capi.ENGINE_TRI:  # the tridiagonal engine never forms the 2-D spectrum
         assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
     assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
-    assert_matches(blend, ref.blend, g, f"{w}x{h}", ref.solved)
+    assert_matches(blend, cv_blend(src, dst, mask, p), g, f"{w}x{h}", floor_blend=ref.blend if w * h <= 256 else None,
+                   floor_solved=ref.solved if w * h <= 256 else None)
     plan.close()
 
 
@@ -175,9 +187,8 @@ def test_error_behaviour(ctx):
     with pytest.raises(scb.ScbError):
         ctx.seamless_clone(src.astype(np.float32), dst, mask, p)
     # the context stays usable after errors
-    ref = so.restate(src, dst, mask, p, transform="f64")
     blend = ctx.seamless_clone(src, dst, mask, p)
-    assert so.compare_u8(blend, ref.blend)["max_abs"] <= 1
+    assert so.compare_u8(blend, cv_blend(src, dst, mask, p))["max_abs"] <= 1
 
 
 def test_empty_mask_returns_dst(ctx):
@@ -206,8 +217,7 @@ def test_mask_and_src_variants(ctx):
     assert np.array_equal(ctx.seamless_clone(big_s[2:-2, 3:-3], big_d[1:-1, 5:-5], big_m[:, :-3], p), base)
     # grey src is replicated like OpenCV does
     grey = src[:, :, 1].copy()
-    ref = so.restate(grey, dst, mask, p, transform="f64")
-    assert so.compare_u8(ctx.seamless_clone(grey, dst, mask, p), ref.blend)["max_abs"] <= 1
+    assert_matches(ctx.seamless_clone(grey, dst, mask, p), cv_blend(grey, dst, mask, p), so.restate(grey, dst, mask, p, transform="f64").geom, "grey src")
 
 
 def test_colour_mask_grey_conversion_matches_opencv():
@@ -227,7 +237,7 @@ def test_plan_reuse_streaming(ctx):
         s, d, _, _ = so.make_config("small", 20 + seed)
         ref = so.restate(s, d, mask, p, transform="f64")
         blend = plan.execute(s, d)
-        assert_matches(blend, ref.blend, plan.geometry, f"frame {seed}")
+        assert_matches(blend, cv_blend(s, d, mask, p), plan.geometry, f"frame {seed}")
     plan.close()
 
 
@@ -259,7 +269,7 @@ def test_device_resident_inplace_and_prefilled(be, ctx):
     assert np.array_equal(roi_interior(out2, g), roi_interior(host_blend, g))
     out2[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = 7
     assert (out2 == 7).all()
-    assert_matches(host_blend, ref.blend, g)
+    assert_matches(host_blend, cv_blend(src, dst, mask, p), g)
     plan.close()
 
 
@@ -272,7 +282,7 @@ def test_reference_entry_points(be):
     blended = sc.seamlessClone()
     sc.sync()
     sc.destroy()
-    assert so.compare_u8(blended, ref.blend)["max_abs"] <= 1
+    assert_matches(blended, cv_blend(src, dst, mask, p), ref.geom, "reference entry points")
     lib = capi.load(be.lib_path)
     inst = lib.my_seamlessclone_api_imp_create_instance(0)
     assert inst
@@ -296,6 +306,7 @@ def test_batch_of_independent_jobs(be, ctx):
         keep.append((src, dst, mask, blend))
         flags = (0, capi.MIXED_CLONE, capi.MONOCHROME_TRANSFER, capi.NORMAL_CLONE)[k % 4]  # per-job cv::seamlessClone flags; 0 = NORMAL_CLONE
         refs.append(so.restate(src, dst, mask, p, flags=flags or so.NORMAL_CLONE, transform="f64"))
+        refs[-1].cv = cv_blend(src, dst, mask, p, flags or so.NORMAL_CLONE)
         arr[k].src, arr[k].dst, arr[k].mask, arr[k].blend = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(blend)
         arr[k].px, arr[k].py = p
         arr[k].flags = flags
@@ -304,7 +315,7 @@ def test_batch_of_independent_jobs(be, ctx):
     for k in range(len(jobs)):
         assert arr[k].status == 0
         g = refs[k].geom
-        cmp = so.compare_u8(keep[k][3], refs[k].blend)
+        cmp = so.compare_u8(keep[k][3], refs[k].cv)
         assert cmp["max_abs"] <= 1 and cmp["n_diff"] <= common.allowed_mismatches(3 * g.nx * g.ny)
 
 
@@ -358,27 +369,77 @@ def test_launch_counter(ctx):
 # ---------------------------------------------------------------------------------------------
 # full-size cases: GPU only, against cv2.seamlessClone itself (cv2 is part of the image)
 # ---------------------------------------------------------------------------------------------
+def parity_vs_floor(got_roi, cv_roi, f64_roi, what):
+    """Byte parity against cv2.seamlessClone, judged beside what is attainable: OpenCV's own float32 cv::dft noise flips
+    truncated bytes, so even an exact (float64) solve with OpenCV's float32 denominators differs from cv2 in 100 - floor
+    per cent of the bytes (SURVEY.md hard part 2).  Bar: +-1 LSB everywhere, and >= 99.9 % exact wherever the float64
+    solve itself reaches 99.9 %; elsewhere no more than 0.02 points under that floor.  The floor is computed HERE, from the
+    oracle's float64 restatement and cv2 on the same inputs -- nothing is hard-coded."""
+    cmp = so.compare_u8(got_roi, cv_roi)
+    floor = so.compare_u8(f64_roi, cv_roi)["pct_exact"]
+    print(f"{what}: exact vs cv2 {cmp['pct_exact']:.4f} %  (float64 floor {floor:.4f} %)  max |diff| {cmp['max_abs']}  differing bytes {cmp['n_diff']}")
+    assert cmp["max_abs"] <= common.U8_MAX_ABS, (what, cmp)
+    assert cmp["pct_exact"] >= min(common.U8_MIN_EXACT, floor - 0.02), (what, cmp, floor)
+    return cmp, floor
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["cfg1", "cfg5", "cfg2"])
-def test_full_size_vs_opencv(cuda_lib, cfg):
+@pytest.mark.parametrize("cfg,seed", [("cfg1", 0), ("cfg1", 1), ("cfg5", 0), ("cfg5", 1), ("cfg2", 0), ("cfg2", 1), ("cfg2", 2), ("cfg2", 3)])
+def test_full_size_vs_opencv(cuda_lib, cfg, seed):
     pytest.importorskip("cv2")
-    src, dst, mask, p = so.make_config(cfg, 0)
+    src, dst, mask, p = so.make_config(cfg, seed)
     ref = so.cv_reference(src, dst, mask, p)
+    f64 = so.restate(src, dst, mask, p, transform="f64").blend
     with scb.Context(0, lib_path=cuda_lib) as c:
         blend = c.seamless_clone(src, dst, mask, p)
         plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
         g = plan.geometry
         plan.close()
-    cmp = so.compare_u8(roi_interior(blend, g), roi_interior(ref, g))
-    print(cfg, cmp)
-    assert cmp["max_abs"] <= 1
-    # the oracle's own float32 FFT noise bounds %exact from above: the
-    # float64 solve with OpenCV's denominator reaches 99.97 / 99.99 / 99.89 % at these three shapes
-    floor = {"cfg1": 99.9, "cfg5": 99.9, "cfg2": 99.8}[cfg]
-    assert cmp["pct_exact"] >= floor
+    parity_vs_floor(roi_interior(blend, g), roi_interior(ref, g), roi_interior(f64, g), f"{cfg} seed {seed}")
     outside = np.ones(dst.shape[:2], bool)
     outside[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = False
     assert np.array_equal(blend[outside], dst[outside])
+
+
+@pytest.mark.gpu
+def test_full_size_batch_vs_opencv(cuda_lib):
+    """cfg3 at full size: 32 of the 512 jobs (1080p dst, patches up to 1024x768, full and elliptic masks) through
+    scb_clone_batch, every job against cv2.seamlessClone."""
+    pytest.importorskip("cv2")
+    from seamlesscloneoptimization_b200 import batch
+
+    specs = so.make_batch_jobs(512, seed=0)[::16]
+    jobs = [so.materialise_job(j) for j in specs]
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        blends = batch.clone_batch_host(c, jobs)
+    worst = 100.0
+    for k, ((src, dst, mask, p), blend) in enumerate(zip(jobs, blends)):
+        ref = so.cv_reference(src, dst, mask, p)
+        f64 = so.restate(src, dst, mask, p, transform="f64")
+        g = f64.geom
+        cmp, _ = parity_vs_floor(roi_interior(blend, g), roi_interior(ref, g), roi_interior(f64.blend, g), f"cfg3 job {16 * k}")
+        worst = min(worst, cmp["pct_exact"])
+        outside = np.ones(dst.shape[:2], bool)
+        outside[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1] = False
+        assert np.array_equal(blend[outside], dst[outside])
+    print("cfg3 worst job:", worst)
+
+
+@pytest.mark.gpu
+@pytest.mark.slow
+def test_full_size_cfg4_vs_opencv(cuda_lib):
+    """The 8K solve against cv2.seamlessClone itself (12-18 s of cv2, ~30 s of float64 oracle).  OpenCV's own noise floor is
+    99.3-99.6 % at this size (4093 is prime: cv::dft runs its O(n p) path), so the bar is the in-test floor."""
+    pytest.importorskip("cv2")
+    src, dst, mask, p = so.make_config("cfg4", 0)
+    ref = so.cv_reference(src, dst, mask, p)
+    f64 = so.restate(src, dst, mask, p, transform="f64").blend
+    with scb.Context(0, lib_path=cuda_lib) as c:
+        plan = c.plan(mask, src.shape[:2], dst.shape[:2], p)
+        g = plan.geometry
+        blend = plan.execute(src, dst)
+        plan.close()
+    parity_vs_floor(roi_interior(blend, g), roi_interior(ref, g), roi_interior(f64, g), "cfg4 seed 0")
 
 
 @pytest.mark.gpu
@@ -446,6 +507,8 @@ def test_batch_pipelined_over_lanes_with_a_bad_job(be, ctx):
         blend = np.zeros_like(dst)
         keep.append((src, dst, mask, blend))
         refs.append(None if k == 4 else so.restate(src, dst, mask, p, transform="f64"))
+        if k != 4:
+            refs[-1].cv = cv_blend(src, dst, mask, p)
         arr[k].src, arr[k].dst, arr[k].mask, arr[k].blend = capi.host_view(src), capi.host_view(dst), capi.host_view(mask), capi.host_view(blend)
         arr[k].px, arr[k].py = p
     rc = ctx.lib.scb_clone_batch(ctx.handle, arr, len(jobs), scb.MEM_HOST)
@@ -456,7 +519,7 @@ def test_batch_pipelined_over_lanes_with_a_bad_job(be, ctx):
             continue
         assert arr[k].status == 0
         g = refs[k].geom
-        cmp = so.compare_u8(keep[k][3], refs[k].blend)
+        cmp = so.compare_u8(keep[k][3], refs[k].cv)
         assert cmp["max_abs"] <= 1 and cmp["n_diff"] <= common.allowed_mismatches(3 * g.nx * g.ny), (k, cmp)
     # the context stays usable after a failed batch
     src, dst, mask, p = so.make_config("small", 2)
@@ -503,7 +566,8 @@ def test_tri_orientations_agree_with_oracle(be, w, h, mem, monkeypatch):
     mask = np.full((hs, ws), 255, np.uint8)
     mask[:3, :5] = 0  # not a plain rectangle: part of the ROI keeps dst gradients
     p = (3 + w // 2 + 1, 2 + h // 2 + 1)
-    ref = so.restate(src, dst, mask, p, transform="f64")
+    cvb = cv_blend(src, dst, mask, p)
+    geom = so.restate(src, dst, mask, p, transform="f64").geom
     if mem == "host":
         monkeypatch.setenv("SCB_BANDS", "3")  # banded uploads with the passes along y
     ctx = be.context()
@@ -522,10 +586,10 @@ def test_tri_orientations_agree_with_oracle(be, w, h, mem, monkeypatch):
                 ctx._check(ctx.lib.scb_plan_execute(plan.handle, C.byref(vs), C.byref(vd), C.byref(vb), scb.MEM_DEVICE, scb.EXEC_DEFAULT))
                 ctx.sync()
                 blend = be.to_host(hb)
-            assert_matches(blend, ref.blend, plan.geometry, f"orientation {orientation}", ref.solved)
+            assert_matches(blend, cvb, plan.geometry, f"orientation {orientation}")
             outs.append(blend)
             plan.close()
-        assert int((outs[0] != outs[1]).sum()) <= common.allowed_mismatches(roi_interior(outs[0], ref.geom).size)
+        assert int((outs[0] != outs[1]).sum()) <= common.allowed_mismatches(roi_interior(outs[0], geom).size)
     finally:
         ctx.close()
 
@@ -553,7 +617,7 @@ def test_clone_flags_vs_oracle(ctx, flags, seed):
     assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_Y).transpose(1, 2, 0), ref.vy)
     assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs), "RHS not bit-exact"
     assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
-    assert_matches(blend, ref.blend, g, f"flags {flags}", ref.solved)
+    assert_matches(blend, cv_blend(src, dst, mask, p, flags), g, f"flags {flags}")
     plan.close()
     one_shot = ctx.seamless_clone(src, dst, mask, p, flags)
     assert np.array_equal(one_shot, blend)

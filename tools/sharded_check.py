@@ -6,6 +6,7 @@ full-mask S x S patch, gathers the row slabs and compares with the single-GPU so
 (must be bit-identical: the passes are the same kernels on row/column ranges).  Prints per-rank times.
 """
 import argparse
+import contextlib
 import os
 import sys
 
@@ -21,6 +22,8 @@ from seamlesscloneoptimization_b200 import _capi as capi, sharded, workloads  # 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--engine", default="tri", choices=["tri", "fft"], help="tri: segment scheme (2 all-reduces); fft: transpose scheme (2 all-to-alls)")
+    ap.add_argument("--plain-context", action="store_true", help="Context on its own stream, caller on torch's default stream (the ordering ShardedSolve must provide itself)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -33,15 +36,18 @@ def main():
     mask = np.full((S, S), 255, np.uint8)
     p = ((S + 300) // 2, (S + 200) // 2)
     stream = torch.cuda.Stream(device=dev)
-    ctx = scb.Context(local, stream=stream.cuda_stream)
-    ctx.set_engine(capi.ENGINE_FFT)  # the sharded passes are the FFT engine's: compare like with like
+    ctx = scb.Context(local) if args.plain_context else scb.Context(local, stream=stream.cuda_stream)
+    if args.plain_context:
+        stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    ctx.set_engine(capi.ENGINE_TRI if args.engine == "tri" else capi.ENGINE_FFT)  # single and sharded run the same engine: bit-identical
     d_src, d_dst, d_mask = (torch.from_numpy(a).to(dev) for a in (src, dst, mask))
     torch.cuda.synchronize()
-    with torch.cuda.stream(stream):
+    with (contextlib.nullcontext() if args.plain_context else torch.cuda.stream(stream)):
         plan = scb.Plan(ctx, d_mask, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
         single = torch.empty_like(d_dst)
         plan.execute(d_src, d_dst, single, scb.MEM_DEVICE)
         blend = d_dst.clone()
+        torch.cuda.synchronize()
         solve = sharded.ShardedSolve(ctx, plan, dev)
         vs, vd, vb = capi.tensor_view(d_src), capi.tensor_view(d_dst), capi.tensor_view(blend)
         solve.run(vs, vd, vb)
@@ -56,7 +62,7 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
-    print(f"rank {rank}/{world}: sharded == single: {same}; {ms:.3f} ms per sharded solve of {S}x{S}", flush=True)
+    print(f"rank {rank}/{world}: engine {args.engine}{' (plain context)' if args.plain_context else ''}: sharded == single: {same}; {ms:.3f} ms per sharded solve of {S}x{S}", flush=True)
     ok = torch.tensor([1 if same else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     plan.close()
