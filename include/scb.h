@@ -76,8 +76,12 @@ enum {
  * FFT: the Bluestein shared-memory FFT engine on both axes (also what the sharded entry points run).  TC: dense
  * sine-basis contraction on the tensor cores (tcgen05, 3xTF32, even/odd fold) for line lengths 16..4096 -- opt-in:
  * its FP32 accumulation error (~1e-5 relative at K ~ 900) is inside the 1e-4 bar for float intermediates but
- * costs exactly-matching bytes at some shapes.  The environment variable SCB_ENGINE=tri|tc|fft sets the default. */
-enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2, SCB_ENGINE_TRI = 3 };
+ * costs exactly-matching bytes at some shapes.  The environment variable SCB_ENGINE=tri|tc|fft|i8 sets the default.
+ * I8: the tridiagonal solve along y with, along x, the DST as an EXACT integer contraction on the INT8 tensor cores
+ * (tcgen05.mma.kind::i8 over balanced base-256 digit planes, scb_i8.h): no rounding before the final float, the exact
+ * float64 low-frequency row sums fall out of the same accumulators.  AUTO resolves to I8 for line lengths 64..8192
+ * and to TRI otherwise. */
+enum { SCB_ENGINE_AUTO = 0, SCB_ENGINE_FFT = 1, SCB_ENGINE_TC = 2, SCB_ENGINE_TRI = 3, SCB_ENGINE_I8 = 4 };
 
 /* scb_plan_get_intermediate selectors; all float32, planar [3][rows][cols] */
 enum {

@@ -28,7 +28,7 @@ MEM_HOST = 0
 MEM_DEVICE = 1
 
 EXEC_DEFAULT = 0
-ENGINE_AUTO, ENGINE_FFT, ENGINE_TC, ENGINE_TRI = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_FFT, ENGINE_TC, ENGINE_TRI, ENGINE_I8 = 0, 1, 2, 3, 4
 EXEC_BLEND_PREFILLED = 1
 
 INT_GRADIENT_X, INT_GRADIENT_Y, INT_RHS, INT_SPECTRUM, INT_SOLVED, INT_ERODED_MASK = range(6)

@@ -26,6 +26,7 @@
 #include "scb_kernels3.cuh"
 #include "scb_platform.h"
 #include "scb_tables.h"
+#include "scb_i8.h"
 #include "scb_tc.cuh"
 #include "scb_tri.cuh"
 
@@ -79,12 +80,18 @@ struct DevTriTab {
     void* block = nullptr;
 };
 
+struct DevI8Tab {  // digit planes of the folded sine basis of one line length (scb_i8.h)
+    I8Geom g{};
+    signed char* basis = nullptr;
+};
+
 struct scb_context {
     int device = 0;
     std::map<std::pair<int, int>, DevTriTab> tritabs;  // keyed by ROI (w, h): LU factors of the tridiagonal engine
     int engine = SCB_ENGINE_AUTO;
     int orientation = -1;               // tridiagonal engine: -1 cost model, 0 FFT passes along x, 1 along y (scb_set_orientation)
     std::map<int, DevTcTab> tctabs;     // keyed by n (tensor-core engine: split sine bases + tensor maps)
+    std::map<int, DevI8Tab> i8tabs;     // keyed by n (exact INT8 tensor-core engine: digit planes of the basis)
     Lane lanes[kMaxLanes];
     int n_lanes = 0;
     cudaStream_t prep = nullptr;  // scb_clone_batch: mask uploads + bounding boxes of the next chunk
@@ -93,8 +100,8 @@ struct scb_context {
     std::mutex err_mu;
     std::map<int, DevLenTab> lentabs;   // keyed by n
     std::map<int, float*> filters;      // keyed by ROI extent
-    int* bbox_dev = nullptr;     // [slots][4]
-    int* bbox_pinned = nullptr;  // [0..3] init pattern, then [slots][4] results
+    int* bbox_dev = nullptr;     // [slots][kBboxInts]: min x, min y, max x, max y, "mask has grey values", 3 unused
+    int* bbox_pinned = nullptr;  // [0..kBboxInts) init pattern, then [slots][kBboxInts] results
     int bbox_slots = 0;
     int sm_count = 148;
     int max_smem = 232448;
@@ -127,6 +134,9 @@ struct scb_plan {
     LenTabDev tx{}, ty{};
     bool use_tc = false;                // tensor-core dense engine (scb_tc.cuh) instead of the FFT engine
     bool use_tri = false;               // tridiagonal column solve (scb_tri.cuh) instead of the column FFT pass
+    bool use_i8 = false;                // with use_tri: the passes along x as exact INT8 tensor-core contractions (scb_i8.h) instead of FFTs
+    const DevI8Tab* i8x = nullptr;
+    bool grey_mask = false;             // the mask holds values other than 0 / 255 inside its ring: the right-hand side is not integer valued
     bool swap = false;                  // tridiagonal engine: FFT passes along y and the tridiagonal solve along x (choose_swap)
     TriTabDev tri{};                    // LU factors for the chosen orientation
     const DevTcTab *ttx = nullptr, *tty = nullptr;
@@ -225,6 +235,7 @@ static int ensure_lanes(scb_context* c, int n) {
     return SCB_OK;
 }
 
+static const int kBboxInts = 8;
 static int ensure_bbox_slots(scb_context* c, int slots) {
     if (slots <= c->bbox_slots) return SCB_OK;
     for (int i = 0; i < c->n_lanes; ++i) SCB_CUDA(c, cudaStreamSynchronize(c->lanes[i].stream));
@@ -233,8 +244,9 @@ static int ensure_bbox_slots(scb_context* c, int slots) {
     c->bbox_dev = nullptr;
     c->bbox_pinned = nullptr;
     c->bbox_slots = 0;
-    SCB_CUDA(c, cudaMalloc(&c->bbox_dev, (size_t)slots * 4 * sizeof(int)));
-    SCB_CUDA(c, cudaMallocHost(&c->bbox_pinned, (size_t)(slots + 1) * 4 * sizeof(int)));
+    SCB_CUDA(c, cudaMalloc(&c->bbox_dev, (size_t)slots * kBboxInts * sizeof(int)));
+    SCB_CUDA(c, cudaMallocHost(&c->bbox_pinned, (size_t)(slots + 1) * kBboxInts * sizeof(int)));
+    for (int i = 0; i < kBboxInts; ++i) c->bbox_pinned[i] = 0;
     c->bbox_pinned[0] = INT_MAX;
     c->bbox_pinned[1] = INT_MAX;
     c->bbox_pinned[2] = -1;
@@ -497,16 +509,55 @@ static int wanted_engine(const scb_context* c) {
         if (!e) return (int)SCB_ENGINE_AUTO;
         if (std::strcmp(e, "tc") == 0) return (int)SCB_ENGINE_TC;
         if (std::strcmp(e, "tri") == 0) return (int)SCB_ENGINE_TRI;
+        if (std::strcmp(e, "i8") == 0) return (int)SCB_ENGINE_I8;
         if (std::strcmp(e, "fft") == 0 || std::strcmp(e, "scalar") == 0) return (int)SCB_ENGINE_FFT;
         return (int)SCB_ENGINE_AUTO;
     }();
     return c->engine != SCB_ENGINE_AUTO ? c->engine : env_engine;
 }
 
-// AUTO resolves to the tridiagonal engine: FFT rows, Thomas columns (scb_tri.cuh).
+// AUTO resolves to the tridiagonal solve along y (scb_tri.cuh) with, along x, the exact INT8 tensor-core contraction
+// (scb_i8.h) for line lengths in [kI8MinN, kI8MaxN] and the Bluestein FFT passes otherwise.  TRI forces the FFT passes.
 static bool tri_eligible(const scb_context* c) {
     const int want = wanted_engine(c);
-    return want == SCB_ENGINE_AUTO || want == SCB_ENGINE_TRI;
+    return want == SCB_ENGINE_AUTO || want == SCB_ENGINE_TRI || want == SCB_ENGINE_I8;
+}
+static bool i8_eligible(const scb_context* c, int nx, int mode) {
+    const int want = wanted_engine(c);
+    if (want != SCB_ENGINE_AUTO && want != SCB_ENGINE_I8) return false;
+    static const bool auto_on = [] {  // SCB_I8_AUTO=0 keeps AUTO on the FFT passes (A/B checks)
+        const char* e = std::getenv("SCB_I8_AUTO");
+        return !(e && std::strcmp(e, "0") == 0);
+    }();
+    if (want == SCB_ENGINE_AUTO && !auto_on) return false;
+    (void)mode;
+    const int lo = want == SCB_ENGINE_I8 ? 8 : kI8MinN;  // forced: every length the digit planes can hold (tests); AUTO: where it pays
+    return nx >= lo && nx <= kI8MaxN;
+}
+
+// digit planes of the folded sine basis of one line length, built on the device at plan time, cached in the context
+static int get_i8tab(scb_context* c, int n, const DevI8Tab** out) {
+    auto it = c->i8tabs.find(n);
+    if (it != c->i8tabs.end()) {
+        *out = &it->second;
+        return SCB_OK;
+    }
+    DevI8Tab d;
+    d.g = i8_geometry(n);
+    void* b = nullptr;
+    SCB_CUDA(c, cudaMalloc(&b, i8_basis_bytes(d.g)));
+    d.basis = (signed char*)b;
+    cudaStream_t s = c->lanes[0].stream;
+    if (i8_launch_basis((void*)s, d.g, d.basis) != 0) {
+        cudaFree(b);
+        return fail(c, SCB_ERR_CUDA, "i8_basis_kernel launch failed");
+    }
+    c->launches++;
+    SCB_CUDA(c, cudaStreamSynchronize(s));  // publishes the table to every lane
+    SCB_CUDA(c, cudaGetLastError());
+    auto ins = c->i8tabs.emplace(n, d);
+    *out = &ins.first->second;
+    return SCB_OK;
 }
 
 // LU factors m[d][k] of tridiag(-1, 4 - fx[k], -1), built on the device at plan time, cached per ROI (w, h)
@@ -629,6 +680,7 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if ((e = configure_all()) != cudaSuccess) return bail("cudaFuncSetAttribute (is this an sm_100a device?)", e);
+    if ((e = (cudaError_t)i8_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute of the INT8 tensor-core kernels", e);
     if (ensure_bbox_slots(c, 1) != SCB_OK) {
         g_create_error = c->err;
         for (int i = 0; i < c->n_lanes; ++i) lane_destroy(&c->lanes[i]);
@@ -651,6 +703,7 @@ extern "C" int scb_destroy(scb_context* c) {
     for (auto& kv : c->filters) cudaFree(kv.second);
     for (auto& kv : c->tctabs) cudaFree(kv.second.block);
     for (auto& kv : c->tritabs) cudaFree(kv.second.block);
+    for (auto& kv : c->i8tabs) cudaFree(kv.second.basis);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
     delete c;
@@ -667,7 +720,8 @@ extern "C" int scb_sync(scb_context* c) {
 
 extern "C" int scb_set_engine(scb_context* c, int engine) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
-    if (engine != SCB_ENGINE_AUTO && engine != SCB_ENGINE_FFT && engine != SCB_ENGINE_TC && engine != SCB_ENGINE_TRI) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_engine: unknown engine");
+    if (engine != SCB_ENGINE_AUTO && engine != SCB_ENGINE_FFT && engine != SCB_ENGINE_TC && engine != SCB_ENGINE_TRI && engine != SCB_ENGINE_I8)
+        return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_set_engine: unknown engine");
     c->engine = engine;
     return SCB_OK;
 }
@@ -692,14 +746,6 @@ extern "C" const char* scb_status_string(int s) {
         case SCB_ERR_OUT_OF_MEMORY: return "out of device memory";
     }
     return "unknown status";
-}
-#ifndef SCB_SOURCE_HASH_STR
-#define SCB_SOURCE_HASH_STR "unstamped-build!"
-#endif
-// hash of the sources this library was built from (__graft_entry__.source_hash); the test fixture compares it with the tree
-extern "C" const char* scb_source_hash(void) {
-    static const char stamp[] = "SCB_SOURCE_HASH=" SCB_SOURCE_HASH_STR;
-    return stamp + 16;
 }
 extern "C" int scb_host_alloc(void** out, size_t bytes) {
     if (!out) return SCB_ERR_INVALID_ARGUMENT;
@@ -799,15 +845,15 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
         mv.pitch = mask->stride;
     }
     // bbox of the ring-zeroed mask (OpenCV: copyMakeBorder + boundingRect)
-    int* slot_dev = c->bbox_dev + 4 * slot;
-    cudaMemcpyAsync(slot_dev, c->bbox_pinned, 4 * sizeof(int), cudaMemcpyHostToDevice, prep);
+    int* slot_dev = c->bbox_dev + kBboxInts * slot;
+    cudaMemcpyAsync(slot_dev, c->bbox_pinned, kBboxInts * sizeof(int), cudaMemcpyHostToDevice, prep);
     {
         long long blocks = ((long long)mv.rows + 7) / 8;  // one warp per row, 8 warps per CTA
         if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
         SCB_LAUNCH(mask_bbox_kernel, dim3((unsigned)blocks), dim3(256), 0, prep, mv, slot_dev);
         c->launches++;
     }
-    cudaError_t e = cudaMemcpyAsync(c->bbox_pinned + 4 * (slot + 1), slot_dev, 4 * sizeof(int), cudaMemcpyDeviceToHost, prep);
+    cudaError_t e = cudaMemcpyAsync(c->bbox_pinned + kBboxInts * (slot + 1), slot_dev, kBboxInts * sizeof(int), cudaMemcpyDeviceToHost, prep);
     if (e != cudaSuccess) return bad(SCB_ERR_CUDA, std::string("bbox download: ") + cudaGetErrorString(e));
     *out = p;
     return SCB_OK;
@@ -817,8 +863,9 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
 static int plan_finish(scb_plan* p, const PlanInput& in) {
     scb_context* c = p->ctx;
     Lane* lane = p->lane;
-    const int* r = c->bbox_pinned + 4 * (in.slot + 1);
+    const int* r = c->bbox_pinned + kBboxInts * (in.slot + 1);
     const int minx = r[0], miny = r[1], maxx = r[2], maxy = r[3];
+    p->grey_mask = r[4] != 0;
     auto release_stage = [&]() {
         if (p->mask_stage) scbFreeAsync(p->mask_stage, lane->stream);
         p->mask_stage = nullptr;
@@ -882,6 +929,11 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
         scb_plan_destroy(p);
         return rc;
     }
+    p->use_i8 = p->use_tri && !p->swap && i8_eligible(c, g.nx, p->mode);
+    if (p->use_i8 && (rc = get_i8tab(c, g.nx, &p->i8x))) {
+        scb_plan_destroy(p);
+        return rc;
+    }
     return SCB_OK;
 }
 
@@ -919,7 +971,7 @@ extern "C" int scb_plan_geometry(const scb_plan* p, scb_geometry* out) {
 }
 extern "C" int scb_plan_engine(const scb_plan* p) {
     if (!p) return -1;
-    return p->use_tc ? SCB_ENGINE_TC : (p->use_tri ? SCB_ENGINE_TRI : SCB_ENGINE_FFT);
+    return p->use_tc ? SCB_ENGINE_TC : (p->use_tri ? (p->use_i8 ? SCB_ENGINE_I8 : SCB_ENGINE_TRI) : SCB_ENGINE_FFT);
 }
 extern "C" int scb_plan_lowk(const scb_plan* p, int* lowkx, int* lowky) {
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
@@ -1124,6 +1176,8 @@ struct Workspace {
     double* R = nullptr;
     double* Y64 = nullptr;  // tridiagonal engine: float64 columns k < kTriLowK
     double* W = nullptr;    // tridiagonal engine: low-frequency block coefficients [3][kTriLowL][kTriLowK]
+    signed char* Adig = nullptr;  // INT8 engine: folded digit planes of the lines (forward: right-hand side, inverse: column solution)
+    float* lscale = nullptr;      // INT8 engine: per-line scale of the digit planes
 };
 
 static int carve(scb_plan* p, bool host, Workspace* w) {
@@ -1155,6 +1209,9 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     const size_t oLow = take((size_t)3 * p->lowkx * p->lowky * sizeof(float));
     const size_t oY64 = take(p->use_tri ? (size_t)3 * (p->swap ? g.nx : g.ny) * kTriLowK * sizeof(double) : 0);
     const size_t oW = take(p->use_tri ? (size_t)3 * kTriLowL * kTriLowK * sizeof(double) : 0);
+    const int i8_lines = 3 * g.ny;
+    const size_t oAdig = take(p->use_i8 ? i8_adig_bytes(p->i8x->g, i8_lines, 4) : 0);
+    const size_t oLs = take(p->use_i8 ? (size_t)i8_m_rows(i8_lines) * sizeof(float) : 0);
     size_t oD = 0, oS = 0, oO = 0;
     if (host) {
         oD = take((size_t)w->pD * g.h);
@@ -1170,6 +1227,8 @@ static int carve(scb_plan* p, bool host, Workspace* w) {
     w->lowspec = (float*)(p->lane->ws + oLow);
     w->Y64 = (double*)(p->lane->ws + oY64);
     w->W = (double*)(p->lane->ws + oW);
+    w->Adig = (signed char*)(p->lane->ws + oAdig);
+    w->lscale = (float*)(p->lane->ws + oLs);
     if (host) {
         w->stD = (unsigned char*)(p->lane->ws + oD);
         w->stS = (unsigned char*)(p->lane->ws + oS);
@@ -1298,7 +1357,18 @@ static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int 
     a.natural = natural ? 1 : 0;
     launch_rows_fwd(p->ctx, p->lane->stream, f.log2m, y1 - y0, a);
 }
+// SCB_REFINE=0: the FFT engine divides its own float32 spectrum everywhere (no exact low-frequency corner) -- the "plain
+// float32 FFT" variant of SURVEY.md Appendix A, kept as a measurement switch (tools/parity_report.py).
+static bool refine_off() {
+    static const bool off = [] {
+        const char* e = std::getenv("SCB_REFINE");
+        return e && std::strcmp(e, "0") == 0;
+    }();
+    return off;
+}
+
 static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
+    if (refine_off()) lowspec = nullptr;
     ColsParams b;
     b.ty = p->ty;
     b.nx = p->g.nx;
@@ -1400,6 +1470,100 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
     r.y0 = y0;
     r.transposed = swap ? 1 : 0;
     launch_rows_inv(p->ctx, p->lane->stream, f.log2m, y1 - y0, r);
+}
+
+// ---- exact INT8 tensor-core passes along x (scb_i8.h): digit planes -> tcgen05.mma.kind::i8 -> class sums -> float ----
+// forward: G [3][ny][gp] -> A [3][ny][nx] (= -2 sum g sin, what rows_fwd produces) and the exact float64 row sums R [3][lowkx][ny]
+static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R) {
+    scb_context* c = p->ctx;
+    const scb_geometry& g = p->g;
+    const int lines = 3 * g.ny, da = p->grey_mask ? 4 : 2;
+    I8DigitizeParams d{};
+    d.g = p->i8x->g;
+    d.in = G;
+    d.in_plane = (long long)g.ny * gp;
+    d.in_pitch = gp;
+    d.lpc = g.ny;
+    d.lines = lines;
+    d.m_rows = i8_m_rows(lines);
+    d.a = w.Adig;
+    d.lscale = w.lscale;
+    d.fixed_scale = p->grey_mask ? 65536.0f : 1.0f;  // binary mask: the right-hand side is integer valued (|g| <= 1530), two digits hold its fold exactly
+    d.per_line = 0;
+    if (i8_launch_digitize((void*)p->lane->stream, d, da) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
+    c->launches++;
+    I8GemmParams m{};
+    m.g = p->i8x->g;
+    m.lines = lines;
+    m.lpc = g.ny;
+    m.m_rows = d.m_rows;
+    m.a = w.Adig;
+    m.basis = p->i8x->basis;
+    m.lscale = w.lscale;
+    const double unit = std::ldexp(1.0, 8 * (da - 1) - kI8BasisBits);
+    m.scale = (float)(-2.0 * unit);  // OpenCV: Im of the odd-extension FFT = -2 sum x sin
+    m.out = A;
+    m.out_plane = (long long)g.ny * g.nx;
+    m.out_pitch = g.nx;
+    m.R = R;
+    m.lowk = p->lowkx;
+    m.rscale = unit;
+    if (i8_launch_gemm((void*)p->lane->stream, m, da, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_gemm_kernel (forward) launch failed");
+    c->launches++;
+    return SCB_OK;
+}
+// inverse: Ct [3][ny][nx] -> U [3][ny][nx] (= sum Ct sin / (nx+1))
+static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U) {
+    scb_context* c = p->ctx;
+    const scb_geometry& g = p->g;
+    const int lines = 3 * g.ny;
+    I8DigitizeParams d{};
+    d.g = p->i8x->g;
+    d.in = Ct;
+    d.in_plane = (long long)g.ny * g.nx;
+    d.in_pitch = g.nx;
+    d.lpc = g.ny;
+    d.lines = lines;
+    d.m_rows = i8_m_rows(lines);
+    d.a = w.Adig;
+    d.lscale = w.lscale;
+    d.fixed_scale = 1.0f;
+    d.per_line = 1;  // 30-bit fixed point relative to the line's largest magnitude
+    if (i8_launch_digitize((void*)p->lane->stream, d, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
+    c->launches++;
+    I8GemmParams m{};
+    m.g = p->i8x->g;
+    m.lines = lines;
+    m.lpc = g.ny;
+    m.m_rows = d.m_rows;
+    m.a = w.Adig;
+    m.basis = p->i8x->basis;
+    m.lscale = w.lscale;
+    m.scale = (float)(std::ldexp(1.0, 8 * 3 - kI8BasisBits) / (double)(g.nx + 1));
+    m.out = U;
+    m.out_plane = (long long)g.ny * g.nx;
+    m.out_pitch = g.nx;
+    m.R = nullptr;
+    if (i8_launch_gemm((void*)p->lane->stream, m, 4, 3) != 0) return fail(c, SCB_ERR_CUDA, "i8_gemm_kernel (inverse) launch failed");
+    c->launches++;
+    if (p->debug) cudaMemcpyAsync(p->dbg_u, U, (size_t)3 * g.nx * g.ny * sizeof(float), cudaMemcpyDeviceToDevice, p->lane->stream);
+    return SCB_OK;
+}
+// compose rows [y0, y1): planar float solved field -> interleaved u8 (clamp, truncate)
+static void run_compose(scb_plan* p, const float* U, unsigned char* out, long long out_pitch, int y0, int y1) {
+    if (y1 <= y0) return;
+    const scb_geometry& g = p->g;
+    TcComposeParams cp;
+    cp.u = U + (size_t)y0 * g.nx;
+    cp.plane = (long long)g.ny * g.nx;
+    cp.pitch = g.nx;
+    cp.nx = g.nx;
+    cp.ny = g.ny;
+    cp.out = out + (long long)y0 * out_pitch;
+    cp.out_pitch = out_pitch;
+    cp.u_dump = nullptr;
+    SCB_LAUNCH(tc_compose_kernel, dim3((g.nx + 511) / 512, y1 - y0), dim3(128), 0, p->lane->stream, cp);
+    p->ctx->launches++;
 }
 
 // ---- tensor-core engine: the four passes + compose (scb_tc.cuh) ----
@@ -1630,17 +1794,17 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         for (int b = 0; b < nb; ++b) {
             SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
             run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1], swap);
-            if (b + 1 < nb && !swap) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
+            if (b + 1 < nb && !swap && !p->use_i8) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
         }
     }
     tm.mark(ST_RHS);
     if (serial) {  // stage timing serialises the refinement so that every stage has its own event pair
-        run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, ms, swap);
+        if (!p->use_i8) run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, ms, swap);  // the INT8 pass delivers the exact row sums itself
         if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, ms);
     } else {      // production: the refinement (small CTAs, no smem) co-runs with pass A (1 big CTA per SM)
         SCB_CUDA(c, cudaEventRecord(L->ev_fork, ms));
         SCB_CUDA(c, cudaStreamWaitEvent(L->side, L->ev_fork, 0));
-        run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, L->side, swap);
+        if (!p->use_i8) run_lowfreq_rows(p, st, w.G, gpl, w.R, 0, fr.cnt, L->side, swap);
         if (!p->use_tri) run_lowfreq_cols(p, w.R, w.lowspec, L->side);
         SCB_CUDA(c, cudaEventRecord(L->ev_join, L->side));
         if (side_copy) {  // blend = dst.copy() rides along on the side stream; only the compose pass has to wait for it
@@ -1656,7 +1820,11 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
-        run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
+        if (p->use_i8) {
+            if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R))) return rc;
+        } else {
+            run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
+        }
         if (!serial) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
         if (p->use_tri) {
@@ -1665,11 +1833,18 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
+        if (p->use_i8 && (rc = run_i8_inverse(p, w, w.Ct, w.At))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
         if (nb_out == 1) {
-            run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
+            if (p->use_i8)
+                run_compose(p, w.At, out, out_pitch, 0, g.ny);
+            else
+                run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
         } else {
             for (int b = 0; b < nb; ++b) {
-                run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
+                if (p->use_i8)
+                    run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
+                else
+                    run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
                 SCB_CUDA(c, cudaEventRecord(L->ev_out[b], ms));
                 SCB_CUDA(c, cudaStreamWaitEvent(L->copy, L->ev_out[b], 0));
                 SCB_CUDA(c, cudaMemcpy2DAsync(bInt + (size_t)yb[b] * blend->stride, (size_t)blend->stride, w.stO + (size_t)yb[b] * w.pO, (size_t)w.pO, (size_t)3 * g.nx,

@@ -616,20 +616,23 @@ struct MaskView {
     int rows, cols;
 };
 
-// bbox of non-zero pixels of the ring-zeroed mask.  bbox = {minx, miny, maxx, maxy}, pre-set to
-// {INT_MAX, INT_MAX, -1, -1}.  OpenCV: copyMakeBorder(mask(1..-1), 0) + boundingRect.
+// bbox of non-zero pixels of the ring-zeroed mask.  bbox = {minx, miny, maxx, maxy, grey}, pre-set to
+// {INT_MAX, INT_MAX, -1, -1, 0}; grey = 1 when a pixel inside the ring is neither 0 nor 255 (then the blended right-hand
+// side is not integer valued: the INT8 engine digitises it with 16 fractional bits).  OpenCV: copyMakeBorder(mask(1..-1), 0) + boundingRect.
 // A warp owns whole rows (lanes stride over the columns: coalesced byte loads, no index division).
 __global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
-    int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1;
+    int minx = 0x7fffffff, miny = 0x7fffffff, maxx = -1, maxy = -1, grey = 0;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
     for (int y = 1 + warp; y < m.rows - 1; y += nwarps) {
         const unsigned char* row = m.data + (long long)y * m.pitch;
         int lo = 0x7fffffff, hi = -1;
         for (int x = 1 + lane; x < m.cols - 1; x += 32) {
-            if (__ldg(row + x)) {
+            const unsigned char v = __ldg(row + x);
+            if (v) {
                 lo = min(lo, x);
                 hi = x;  // x grows within the lane
+                grey |= (v != 255);
             }
         }
         if (hi >= 0) {
@@ -644,7 +647,9 @@ __global__ void __launch_bounds__(256) mask_bbox_kernel(MaskView m, int* bbox) {
         miny = min(miny, __shfl_xor_sync(0xffffffffu, miny, off));
         maxx = max(maxx, __shfl_xor_sync(0xffffffffu, maxx, off));
         maxy = max(maxy, __shfl_xor_sync(0xffffffffu, maxy, off));
+        grey |= __shfl_xor_sync(0xffffffffu, grey, off);
     }
+    if (lane == 0 && grey) atomicMax(bbox + 4, 1);
     if (lane == 0 && maxx >= 0) {
         atomicMin(bbox + 0, minx);
         atomicMin(bbox + 1, miny);

@@ -275,6 +275,7 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // PRMT, defa
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline int __float2int_rz(float f) { return (int)f; }
+inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }
 inline unsigned __float2uint_rz(float f) { return (unsigned)f; }
 inline float __int2float_rn(int i) { return (float)i; }
 inline double sinpi(double x) { return std::sin(M_PI * x); }

@@ -53,12 +53,14 @@ def be(request):
     return Backend("cuda", request.getfixturevalue("cuda_lib"))
 
 
-ENGINES = {"tri": capi.ENGINE_TRI, "tc": capi.ENGINE_TC, "fft": capi.ENGINE_FFT}
+ENGINES = {"i8": capi.ENGINE_I8, "tri": capi.ENGINE_TRI, "tc": capi.ENGINE_TC, "fft": capi.ENGINE_FFT}
+NO_SPECTRUM = (capi.ENGINE_TRI, capi.ENGINE_I8)  # the tridiagonal solve along y never forms the 2-D spectrum
 
 
-@pytest.fixture(scope="module", params=["tri", "tc", "fft"])
+@pytest.fixture(scope="module", params=["i8", "tri", "tc", "fft"])
 def ctx(be, request):
-    """Every test runs on every engine: 'tri' = FFT rows + tridiagonal column solve (the default), 'tc' = tensor-core
+    """Every test runs on every engine: 'i8' = exact INT8 tensor-core DST along x + tridiagonal column solve (the default from
+    64-point lines up; forced here for every length), 'tri' = FFT rows + tridiagonal column solve, 'tc' = tensor-core
     dense contraction where eligible (line lengths 16..4096; shorter lines fall back to the FFT engine), 'fft' = the
     Bluestein FFT engine on both axes."""
     c = be.context()
@@ -82,16 +84,18 @@ def cv_blend(src, dst, mask, p, flags=so.NORMAL_CLONE):
 def assert_matches(blend, ref_blend, g, what="", floor_blend=None, floor_solved=None):
     """+-1 LSB everywhere and >= 99.9 % of the solved bytes exact, against cv2.seamlessClone.  Every byte counts:
     pixels whose exact value sits on an integer (where truncation flips under any float noise) are NOT exempt.
-    `floor_blend` (the oracle's float64 restatement) is given by the tests of tiny ROIs only: a 1 x 1 or 2 x 5 system has
-    a rational solution with a small denominator, so whole pixels sit exactly on integers and cv2's own float32 DFT noise
-    decides their bytes; there the bar is the float64 solve's own mismatch count against cv2 plus the number of bytes whose
-    float64 solution lies within 1e-4 of an integer (`floor_solved`), plus the usual allowance."""
+    Where cv2's own float32 cv::dft noise makes 99.9 % unattainable -- long thin ROIs (an 8192-point 1-D Poisson problem
+    amplifies float32 rounding by (N/pi)^2 ~ 7e6: cv2 itself is +-0.5 off there) -- `floor_blend`, the oracle's float64
+    restatement, sets the bar: no more mismatches against cv2 than the float64 solve has, plus 0.02 % (at least 2 bytes).
+    `floor_solved` is given by the tests of tiny ROIs only: a 1 x 1 or 2 x 5 system has a rational solution with a small
+    denominator, so whole pixels sit exactly on integers; bytes whose float64 solution lies within 1e-4 of an integer are
+    added to the allowance there."""
     a, b = roi_interior(blend, g), roi_interior(ref_blend, g)
     cmp = so.compare_u8(a, b)
     assert cmp["max_abs"] <= common.U8_MAX_ABS, (what, cmp)
     allowed = common.allowed_mismatches(a.size)
     if floor_blend is not None:
-        allowed += so.compare_u8(roi_interior(floor_blend, g), b)["n_diff"]
+        allowed = max(allowed, so.compare_u8(roi_interior(floor_blend, g), b)["n_diff"] + max(2, int(2e-4 * a.size)))
     if floor_solved is not None:
         allowed += int((np.abs(floor_solved - np.rint(floor_solved)) < 1e-4).sum())
     assert cmp["n_diff"] <= allowed, (what, cmp, allowed)
@@ -118,7 +122,7 @@ def test_configs_vs_oracle(ctx, cfg, seed):
     assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs)
     assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_X).transpose(1, 2, 0), ref.vx)
     assert np.array_equal(plan.intermediate(capi.INT_GRADIENT_Y).transpose(1, 2, 0), ref.vy)
-    if plan.engine != capi.ENGINE_TRI:  # the tridiagonal engine never forms the 2-D spectrum
+    if plan.engine not in NO_SPECTRUM:
         assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
     assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
     assert_matches(blend, cv_blend(src, dst, mask, p), g, cfg)
@@ -147,11 +151,10 @@ def _run_size(ctx, w, h, seed=0):
     g = plan.geometry
     assert (g.w, g.h, g.rx, g.ry) == (w, h, ref.geom.rx, ref.geom.ry)
     assert np.array_equal(plan.intermediate(capi.INT_RHS).transpose(1, 2, 0), ref.rhs)
-    if plan.engine != capi.ENGINE_TRI:  # the tridiagonal engine never forms the 2-D spectrum
+    if plan.engine not in NO_SPECTRUM:
         assert so.rel_linf(plan.intermediate(capi.INT_SPECTRUM).transpose(2, 1, 0), ref.spectrum) < common.FLOAT_REL_TOL
     assert so.rel_linf(plan.intermediate(capi.INT_SOLVED).transpose(1, 2, 0), ref.solved) < common.FLOAT_REL_TOL
-    assert_matches(blend, cv_blend(src, dst, mask, p), g, f"{w}x{h}", floor_blend=ref.blend if w * h <= 256 else None,
-                   floor_solved=ref.solved if w * h <= 256 else None)
+    assert_matches(blend, cv_blend(src, dst, mask, p), g, f"{w}x{h}", floor_blend=ref.blend, floor_solved=ref.solved if w * h <= 256 else None)
     plan.close()
 
 
@@ -362,7 +365,8 @@ def test_launch_counter(ctx):
     before = ctx.kernel_launches
     plan.execute(src, dst)
     # FFT engine: rhs, lowfreq rows, lowfreq cols, rows fwd, cols, rows inv; tensor-core engine: 4 passes + compose instead of 3
-    assert ctx.kernel_launches - before == {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7}.get(plan.engine, 6)
+    # INT8 engine: rhs, digitise, gemm, 3 x column solve, digitise, gemm, compose
+    assert ctx.kernel_launches - before == {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7, capi.ENGINE_I8: 9}.get(plan.engine, 6)
     plan.close()
 
 
@@ -490,7 +494,7 @@ def test_graph_replay_equals_plain_execute(be, ctx):
         for _ in range(3):  # first call captures, the next two replay
             plan.execute_graph(vs, vd, vb1)
         ctx.sync()
-        assert ctx.kernel_launches - before == 3 * {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7}.get(plan.engine, 6)
+        assert ctx.kernel_launches - before == 3 * {capi.ENGINE_TC: 8, capi.ENGINE_TRI: 7, capi.ENGINE_I8: 9}.get(plan.engine, 6)
         assert np.array_equal(be.to_host(hb0), be.to_host(hb1))
     plan.close()
 
