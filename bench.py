@@ -8,6 +8,9 @@ irregular-mask patch, ROI 1810x1341 -> 2.42 M solved RGB pixels per clone.  One 
 NORMAL_CLONE of the workload (cfg3: one pass over the whole batch of jobs).
 
   N > 1 (torchrun, one rank per GPU)
+    no --workload: the cfg2 headline (every rank its own 4K clone, "weak") PLUS the two workloads that really shard, attached to
+              the printed line under "sharded": cfg3 (512 jobs split over the ranks, strong) and cfg4 (ONE 8K solve row-sharded
+              over the ranks, NCCL, strong), each with the same leg on rank 0 alone for the efficiency
     cfg1/2/5  every rank clones its own independent job of that shape, no collective: "weak"
     cfg3      the 512 jobs are split over the ranks (LPT by solved pixels), no collective: "strong"
     cfg4      ONE solve, rows sharded over the ranks along the segments of the partitioned tridiagonal solve, two small NCCL all-reduces
@@ -54,13 +57,32 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(workload: str, kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+def library_stamp():
+    """Source hash the loaded libscb.so was built from (scb_source_hash)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload, {}).get(kernel)
+        from seamlesscloneoptimization_b200 import _capi
+
+        return (_capi.load().scb_source_hash() or b"").decode()
     except Exception:
         return None
+
+
+def _profile_json(name: str):
+    """profiles/<name>: ncu numbers quoted beside the live ones.  Each file carries the source hash of the library it was
+    captured from ("library_stamp"); numbers of another library state are DROPPED (returned as None), never quoted silently."""
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            d = json.load(f)
+    except Exception:
+        return {}
+    if d.get("library_stamp") != library_stamp():
+        return {}
+    return d
+
+
+def ncu_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    return _profile_json("traffic.json").get(workload, {}).get(kernel)
 
 
 class ClockSampler(threading.Thread):
@@ -122,7 +144,7 @@ def percentile(xs, q):
 
 WORKLOADS = {
     "cfg1": "cfg1: 512x384 full-mask patch into 1920x1080 at ROI origin (800,150)",
-    "cfg2": "cfg2: 3840x2160 dst, 2048x1536 irregular-mask patch (ellipse+disc, ROI 1810x1341), p=(1920,1080)",
+    "cfg2": "cfg2: 3840x2160 dst, 2048x1536 irregular-mask patch (ellipse+disc, ROI 1810x1339), p=(1920,1080)",
     "cfg3": "cfg3: batch of 512 independent 1080p clone jobs, patch sizes U[64,1024]xU[64,768], varied offsets, full/elliptic masks",
     "cfg4": "cfg4: 7680x4320 dst, 4096x4096 full-mask patch (ROI 4094x4094), one solve",
     "cfg5": "cfg5: 1920x1080 dst stream, fixed 1280x720 elliptic mask (ROI 1201x661) and offset, plan + CUDA graph reused",
@@ -147,6 +169,32 @@ def cpu_clone_times(jobs, n_calls: int, threads: int | None):
             cv2.seamlessClone(s, d, m.copy(), p, cv2.NORMAL_CLONE)  # cv2 mutates the mask: always a copy
         ts.append(time.perf_counter() - t0)
     return ts, cv2.getNumThreads(), cv2.__version__
+
+
+def _pool_worker(job):
+    import cv2
+
+    cv2.setNumThreads(1)
+    s, d, m, p = job
+    t0 = time.perf_counter()
+    cv2.seamlessClone(s, d, m.copy(), p, cv2.NORMAL_CLONE)
+    return time.perf_counter() - t0
+
+
+def cpu_pool_throughput(jobs, ncores: int):
+    """cfg3 CPU baseline of BASELINE.md section 2: independent jobs on a multiprocessing pool of single-thread cv2 workers."""
+    import multiprocessing as mp
+
+    px = sum(roi_pixels(m)[0] for _, _, m, _ in jobs)
+    try:
+        with mp.get_context("fork").Pool(min(ncores, len(jobs))) as pool:
+            pool.map(_pool_worker, jobs[: min(ncores, len(jobs))])  # warm-up: imports, page faults
+            t0 = time.perf_counter()
+            pool.map(_pool_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+        return {"value": px / dt / 1e6, "unit": UNIT, "cores": min(ncores, len(jobs)), "jobs": len(jobs), "seconds": dt}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unavailable": str(e)}
 
 
 def roi_pixels(mask):
@@ -201,8 +249,14 @@ def cpu_baseline_leg(args, px_per_pass_hint=None):
         ncores = os.cpu_count() or 1
         calls = 1 if args.workload == "cfg4" else args.cpu_baseline_calls
         ts, nthreads, ver = cpu_clone_times(jobs, calls, ncores)
-        return {"value": px * len(ts) / sum(ts) / 1e6, "unit": UNIT, "cores": nthreads, "kind": "reference", "p50_ms": 1e3 * statistics.median(ts),
-                "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} passes over {what} after 1 warm-up, {nthreads} threads of {ncores} host cores"}
+        out = {"value": px * len(ts) / sum(ts) / 1e6, "unit": UNIT, "cores": nthreads, "kind": "reference", "p50_ms": 1e3 * statistics.median(ts),
+               "sample": f"cv2.seamlessClone (OpenCV {ver} wheel), {len(ts)} passes over {what} after 1 warm-up, {nthreads} threads of {ncores} host cores"}
+        if args.workload != "cfg4":  # the single-thread figure beside the all-threads one (OpenCV scales 1.3-1.9x only)
+            t1, _, _ = cpu_clone_times(jobs, 1 if args.workload == "cfg2" else 2, 1)
+            out["one_thread"] = {"value": px * len(t1) / sum(t1) / 1e6, "unit": UNIT, "cores": 1, "p50_ms": 1e3 * statistics.median(t1)}
+        if args.workload == "cfg3":  # the CPU's best batch throughput: a pool of single-thread workers, one per core
+            out["process_pool"] = cpu_pool_throughput(jobs, ncores)
+        return out
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -224,6 +278,7 @@ class Env:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG", "INFO")  # NCCL's own log (stderr) says which transports / algorithms the communicator of the cfg4 leg uses
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.warmup = max(3, args.warmup)
@@ -268,13 +323,27 @@ class Env:
             self.dist.destroy_process_group()
 
 
+class SoloEnv:
+    """View of an Env as a one-rank world: rank 0 runs a strong-scaling leg ALONE (the other ranks wait at the next barrier),
+    which puts the N = 1 figure of that leg into the same run as the N-rank one."""
+
+    def __init__(self, env: Env):
+        self.torch, self.dist, self.args = env.torch, env.dist, env.args
+        self.rank, self.world, self.local_rank, self.dev, self.flush, self.warmup = 0, 1, env.local_rank, env.dev, env.flush, env.warmup
+        self.pinned, self.timed_steps = env.pinned, env.timed_steps
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        return [float(v) for v in vals]
+
+    sum_over_ranks = max_over_ranks
+
+
 def ncu_duration_ms(workload: str, kernel: str):
     """gpu__time_duration of the kernel's full-size launch from the committed ncu launch list (cold cache, serialised)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "kernel_times.json")) as f:
-            return json.load(f).get(workload, {}).get(kernel)
-    except Exception:
-        return None
+    return _profile_json("kernel_times.json").get(workload, {}).get(kernel)
 
 
 def roofline_objects(stages, px, workload):
@@ -300,8 +369,10 @@ def roofline_objects(stages, px, workload):
     return d, obj("rhs"), obj("cols")
 
 
-def single_job_leg(env: Env, args):
+def single_job_leg(env, args, steps=None):
     """cfg1 / cfg2 / cfg5 (and cfg4 on one GPU): one clone per step; every rank its own independent job."""
+    if steps is not None:
+        args = argparse.Namespace(**{**vars(args), "steps": steps})
     import seamlesscloneoptimization_b200 as scb
     from seamlesscloneoptimization_b200 import _capi as capi
 
@@ -394,8 +465,10 @@ def single_job_leg(env: Env, args):
     return line
 
 
-def batch_leg(env: Env, args):
+def batch_leg(env, args, steps=None):
     """cfg3: the batch of independent jobs, split over the ranks by LPT on solved pixels, no collective."""
+    if steps is not None:
+        args = argparse.Namespace(**{**vars(args), "steps": steps})
     import seamlesscloneoptimization_b200 as scb
     from seamlesscloneoptimization_b200 import _capi as capi
     from seamlesscloneoptimization_b200 import batch
@@ -503,8 +576,11 @@ def batch_leg(env: Env, args):
     return line
 
 
-def sharded_leg(env: Env, args):
-    """cfg4 on N > 1 GPUs: ONE solve, row/column sharded, all-to-all between the passes."""
+def sharded_leg(env, args, steps=None):
+    """cfg4 on N > 1 GPUs: ONE solve, row-sharded along the segments of the tridiagonal solve (or row/column sharded with all-to-all
+    transposes, --sharded-fft).  A warm-up step is checked against the single-GPU solve of the same plan: bit-identical or the leg fails."""
+    if steps is not None:
+        args = argparse.Namespace(**{**vars(args), "steps": steps})
     import seamlesscloneoptimization_b200 as scb
     from seamlesscloneoptimization_b200 import _capi as capi
     from seamlesscloneoptimization_b200 import sharded
@@ -528,19 +604,33 @@ def sharded_leg(env: Env, args):
         def device_step():
             solve.run(vs, vd, vb)
 
+        # parity of the sharded path, on the GPU, in the bench itself: own rows of the sharded result == the single-GPU solve
+        single = torch.empty_like(d_dst)
+        plan.execute(d_src, d_dst, single, scb.MEM_DEVICE)
+        device_step()
+        torch.cuda.synchronize()
+        ya, yb_ = g.ry + 1 + solve.ys[env.rank], g.ry + 1 + solve.ys[env.rank + 1]
+        same = bool(torch.equal(d_blend[ya:yb_, g.rx + 1 : g.rx + 1 + g.nx], single[ya:yb_, g.rx + 1 : g.rx + 1 + g.nx]))
+        same_all, = env.max_over_ranks(0.0 if same else 1.0)
+        if same_all != 0.0:
+            raise SystemExit("bench.py: the sharded solve differs from the single-GPU solve of the same plan")
+        del single
         for _ in range(env.warmup):
             device_step()
         env.barrier()
         sampler = ClockSampler(env.local_rank)
         sampler.start()
         launches0 = ctx.kernel_launches
+        solve.time_collectives = True
         evs = env.timed_steps(stream, device_step, args.steps)
         sampler.sample()
         env.barrier()
         launches = ctx.kernel_launches - launches0
         sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in evs]
-        total_ms_max, = env.max_over_ranks(sum(step_ms))
+        coll_ms = solve.collective_ms()
+        solve.time_collectives = False
+        total_ms_max, coll_ms_max = env.max_over_ranks(sum(step_ms), coll_ms or 0.0)
         # e2e: pinned host inputs -> device -> sharded solve -> own row slab back to the host.  A rank moves only the rows of
         # src / dst its shard reads (own interior rows + the one-row halo of the stencil).
         h_src, h_dst = env.pinned(src), env.pinned(dst)
@@ -581,7 +671,8 @@ def sharded_leg(env: Env, args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS["cfg4"], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
                        "l2": "256 MiB flush write between timed steps", "parallelism": par,
-                       "bytes_exchanged_per_rank_per_step": int(xbytes)},
+                       "bytes_exchanged_per_rank_per_step": int(xbytes), "sharded_equals_single_gpu": True},
+            "collective_ms": coll_ms_max if env.world > 1 else 0.0,
             "clocks": sampler.summary(),
             "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int((s1 - s0) * src.shape[1] * 3 + (t1_ - t0_) * dst.shape[1] * 3), "d2h_bytes_per_step": int(h_rows.numel()),
                     "ms_per_step": e2e_ms_max / args.steps, "call": "pinned H2D of the shard's src+dst rows (rank 0's byte counts), ShardedSolve.run, own row slab D2H"},
@@ -598,7 +689,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="default: cfg2 (and, for --gpus N > 1, the cfg3 + cfg4 strong-scaling legs attached)")
     ap.add_argument("--jobs", type=int, default=512, help="cfg3: jobs in the batch")
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as a CUDA graph (default for cfg5)")
     ap.add_argument("--cpu-baseline-calls", type=int, default=5)
@@ -607,16 +698,49 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
+        if args.workload is None:
+            args.workload = "cfg2"
         run_reference(args, rank)
         return
     env = Env(args)
+    explicit = args.workload is not None
+    if not explicit:
+        args.workload = "cfg2"
     if args.workload == "cfg3":
         line = batch_leg(env, args)
     elif args.workload == "cfg4" and env.world > 1:
         line = sharded_leg(env, args)
     else:
         line = single_job_leg(env, args)
+    if not explicit and env.world > 1:
+        # The headline stays cfg2 (comparable with N = 1).  The workloads that really shard ride along: each runs on all N ranks
+        # and, before that, on rank 0 alone, so the line carries its own strong-scaling efficiency.
+        sh = {}
+        k = max(3, min(args.steps, 5))
+        for name, leg in (("cfg3", batch_leg), ("cfg4", sharded_leg if env.world > 1 else single_job_leg)):
+            sub = argparse.Namespace(**{**vars(args), "workload": name})
+            solo = (batch_leg if name == "cfg3" else single_job_leg)(SoloEnv(env), sub, k) if env.rank == 0 else None
+            env.barrier()
+            full = leg(env, sub, k)
+            env.barrier()
+            if env.rank == 0 and full is not None and solo is not None:
+                sh[name] = {
+                    "workload": WORKLOADS[name], "scaling": "strong", "n_gpus": env.world, "steps": k,
+                    "value": full["value"], "unit": UNIT, "ms_per_step": full["ms_per_step"],
+                    "e2e": {"value": full["e2e"]["value"], "ms_per_step": full["e2e"]["ms_per_step"]},
+                    "n1": {"value": solo["value"], "ms_per_step": solo["ms_per_step"], "e2e_value": solo["e2e"]["value"], "where": "rank 0 alone, same run"},
+                    "efficiency_vs_n1": full["value"] / solo["value"] / env.world,
+                    "e2e_efficiency_vs_n1": full["e2e"]["value"] / solo["e2e"]["value"] / env.world,
+                }
+                if name == "cfg3":
+                    sh[name].update(jobs=full["config"]["jobs"], jobs_per_s=full["jobs_per_s"], e2e_jobs_per_s=full["e2e"]["jobs_per_s"], collective="none (jobs split by LPT)")
+                else:
+                    sh[name].update(bytes_exchanged_per_rank_per_step=full["config"]["bytes_exchanged_per_rank_per_step"], collective_ms=full.get("collective_ms"),
+                                    parallelism=full["config"]["parallelism"], sharded_equals_single_gpu=full["config"]["sharded_equals_single_gpu"])
+        if env.rank == 0 and line is not None:
+            line["sharded"] = sh
     if env.rank == 0 and line is not None:
+        line["library_stamp"] = library_stamp()
         if env.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
         print(json.dumps(line))

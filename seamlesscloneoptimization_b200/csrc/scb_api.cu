@@ -21,6 +21,14 @@
 #include <thread>
 #include <vector>
 
+#if defined(__SSE2__) && !defined(SCB_EMU)
+#include <emmintrin.h>
+#endif
+#if defined(__linux__) && !defined(SCB_EMU)
+#include <pthread.h>
+#include <sched.h>
+#endif
+
 #include "../../include/scb.h"
 #include "scb_kernels.cuh"
 #include "scb_kernels3.cuh"
@@ -85,8 +93,13 @@ struct DevI8Tab {  // digit planes of the folded sine basis of one line length (
     signed char* basis = nullptr;
 };
 
+class HostPool;
+struct scb_context;
+static void host_pool_free(scb_context* c);  // defined next to the class
+
 struct scb_context {
     int device = 0;
+    HostPool* pool = nullptr;           // helper threads of the host-side dst -> blend copy; one pool per context (created on first use)
     std::map<std::pair<int, int>, DevTriTab> tritabs;  // keyed by ROI (w, h): LU factors of the tridiagonal engine
     int engine = SCB_ENGINE_AUTO;
     int orientation = -1;               // tridiagonal engine: -1 cost model, 0 FFT passes along x, 1 along y (scb_set_orientation)
@@ -706,6 +719,7 @@ extern "C" int scb_destroy(scb_context* c) {
     for (auto& kv : c->i8tabs) cudaFree(kv.second.basis);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
+    host_pool_free(c);
     delete c;
     return SCB_OK;
 }
@@ -1054,6 +1068,42 @@ static int check_image(scb_context* c, const scb_image* im, int rows, int cols, 
     return SCB_OK;
 }
 
+// Streaming copy for the host-side dst -> blend copy: non-temporal stores, so the destination lines are not read into the
+// cache first (a plain memcpy of 11 KB image rows costs a read-for-ownership per line: 3 bytes of memory traffic per byte
+// copied instead of 2 -- which is what made eight ranks sharing one host collapse, SCALE_r01).
+static void stream_copy(char* d, const char* s, size_t n) {
+#if defined(__SSE2__) && !defined(SCB_EMU)
+    if (n < 2048) {
+        std::memcpy(d, s, n);
+        return;
+    }
+    const size_t head = (64 - ((uintptr_t)d & 63)) & 63;
+    if (head) {
+        std::memcpy(d, s, head);
+        d += head;
+        s += head;
+        n -= head;
+    }
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        const __m128i a0 = _mm_loadu_si128((const __m128i*)(s + 64 * i)), a1 = _mm_loadu_si128((const __m128i*)(s + 64 * i + 16));
+        const __m128i a2 = _mm_loadu_si128((const __m128i*)(s + 64 * i + 32)), a3 = _mm_loadu_si128((const __m128i*)(s + 64 * i + 48));
+        _mm_stream_si128((__m128i*)(d + 64 * i), a0);
+        _mm_stream_si128((__m128i*)(d + 64 * i + 16), a1);
+        _mm_stream_si128((__m128i*)(d + 64 * i + 32), a2);
+        _mm_stream_si128((__m128i*)(d + 64 * i + 48), a3);
+    }
+    if (n - 64 * blocks) std::memcpy(d + 64 * blocks, s + 64 * blocks, n - 64 * blocks);
+#else
+    std::memcpy(d, s, n);
+#endif
+}
+static void stream_fence() {
+#if defined(__SSE2__) && !defined(SCB_EMU)
+    _mm_sfence();
+#endif
+}
+
 // blend = dst everywhere EXCEPT the ROI interior (which the device result overwrites): disjoint from the
 // D2H target, so it needs no ordering against the download and can run on several host threads while the
 // GPU works.  (OpenCV: dst.copyTo(blend) of the whole frame, then the ROI is overwritten.)
@@ -1061,25 +1111,78 @@ static void host_copy_rows(const scb_image* dst, scb_image* blend, const scb_geo
     const size_t row_bytes = (size_t)3 * dst->cols;
     const int iy0 = g.empty ? dst->rows : g.ry + 1, iy1 = g.empty ? dst->rows : g.ry + g.h - 1;
     const size_t left = (size_t)3 * (g.rx + 1), right0 = (size_t)3 * (g.rx + g.w - 1);
-    for (int y = y0; y < y1; ++y) {
+    const bool dense = (size_t)dst->stride == row_bytes && (size_t)blend->stride == row_bytes;
+    int y = y0;
+    while (y < y1) {
         char* o = (char*)blend->data + (size_t)y * blend->stride;
         const char* i = (const char*)dst->data + (size_t)y * dst->stride;
         if (y < iy0 || y >= iy1) {
-            std::memcpy(o, i, row_bytes);
+            int run = 1;  // dense images: the whole run of rows above / below the ROI interior is one streaming copy
+            if (dense) run = (y < iy0 ? (iy0 < y1 ? iy0 : y1) : y1) - y;
+            stream_copy(o, i, row_bytes * (size_t)run);
+            y += run;
         } else {
-            std::memcpy(o, i, left);
-            std::memcpy(o + right0, i + right0, row_bytes - right0);
+            stream_copy(o, i, left);
+            stream_copy(o + right0, i + right0, row_bytes - right0);
+            ++y;
         }
     }
+    stream_fence();
 }
 
+// How many helper threads a context may use for host-side copies, and which cores they sit on.  One process per GPU is the
+// deployment (torchrun sets LOCAL_RANK / LOCAL_WORLD_SIZE): the ranks of a node share its cores, so a rank takes
+// cores / LOCAL_WORLD_SIZE of them (at most 8: the copy is memory bound long before that) and pins its helpers inside its
+// own slice, instead of every rank starting 8 threads on the same cores.  SCB_HOST_THREADS overrides the count, SCB_PIN=0 the pinning.
+struct HostCpus {
+    std::vector<int> cpus;  // this rank's slice of the cores the process may run on
+    int threads = 1;
+    bool pin = false;
+};
+static const HostCpus& host_cpus() {
+    static const HostCpus hc = [] {
+        HostCpus h;
+        std::vector<int> allowed;
+#if defined(__linux__) && !defined(SCB_EMU)
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0)
+            for (int i = 0; i < CPU_SETSIZE; ++i)
+                if (CPU_ISSET(i, &set)) allowed.push_back(i);
+#endif
+        if (allowed.empty()) {
+            unsigned n = std::thread::hardware_concurrency();
+            for (unsigned i = 0; i < (n ? n : 1); ++i) allowed.push_back((int)i);
+        }
+        int world = 1, rank = 0;
+        if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) world = std::atoi(e) > 0 ? std::atoi(e) : 1;
+        if (const char* e = std::getenv("LOCAL_RANK")) rank = std::atoi(e) >= 0 ? std::atoi(e) : 0;
+        const int per = (int)allowed.size() / world > 0 ? (int)allowed.size() / world : 1;
+        const int first = (rank % world) * per < (int)allowed.size() ? (rank % world) * per : 0;
+        for (int i = 0; i < per && first + i < (int)allowed.size(); ++i) h.cpus.push_back(allowed[first + i]);
+        h.threads = per < 8 ? per : 8;
+        if (const char* e = std::getenv("SCB_HOST_THREADS")) h.threads = std::atoi(e) > 0 ? std::atoi(e) : 1;
+        h.pin = world > 1;
+        if (const char* e = std::getenv("SCB_PIN")) h.pin = std::atoi(e) != 0;
+        return h;
+    }();
+    return hc;
+}
+static int host_threads() { return host_cpus().threads; }
+
 // Persistent helper threads for the host-side copy (creating and joining std::threads per call costs ~50 us, a visible part
-// of a 0.8 ms end-to-end clone).  One pool per process; a call hands out row ranges and waits for them.
+// of a 0.8 ms end-to-end clone).  One pool per CONTEXT: contexts are single-threaded per handle, so calls of
+// different contexts on different threads never wait for one another.
 class HostPool {
   public:
-    static HostPool& get() {
-        static HostPool p;
-        return p;
+    HostPool() = default;
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
     }
     // runs fn(t) for t = 0 .. n-1: t = 0 on the caller, the rest on the pool; returns when all are done
     void run(int n, const std::function<void(int)>& fn) {
@@ -1087,7 +1190,6 @@ class HostPool {
             fn(0);
             return;
         }
-        std::unique_lock<std::mutex> call(call_mu_);  // one caller at a time
         ensure(n - 1);
         {
             std::lock_guard<std::mutex> lk(mu_);
@@ -1105,17 +1207,19 @@ class HostPool {
     }
 
   private:
-    HostPool() = default;
-    ~HostPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
     void ensure(int n) {
-        while ((int)threads_.size() < n) threads_.emplace_back([this] { loop(); });
+        while ((int)threads_.size() < n) {
+            threads_.emplace_back([this] { loop(); });
+#if defined(__linux__) && !defined(SCB_EMU)
+            const HostCpus& hc = host_cpus();
+            if (hc.pin && !hc.cpus.empty()) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                CPU_SET(hc.cpus[threads_.size() % hc.cpus.size()], &set);
+                pthread_setaffinity_np(threads_.back().native_handle(), sizeof(set), &set);
+            }
+#endif
+        }
     }
     void loop() {
         uint64_t seen = 0;
@@ -1134,7 +1238,7 @@ class HostPool {
             seen = epoch_;
         }
     }
-    std::mutex mu_, call_mu_;
+    std::mutex mu_;
     std::condition_variable cv_, done_;
     std::vector<std::thread> threads_;
     const std::function<void(int)>* fn_ = nullptr;
@@ -1142,8 +1246,16 @@ class HostPool {
     uint64_t epoch_ = 0;
     bool stop_ = false;
 };
+static HostPool& pool_of(scb_context* c) {
+    if (!c->pool) c->pool = new HostPool();
+    return *c->pool;
+}
+static void host_pool_free(scb_context* c) {
+    delete c->pool;
+    c->pool = nullptr;
+}
 
-static void host_copy_outside(const scb_image* dst, scb_image* blend, const scb_geometry& g, int max_threads) {
+static void host_copy_outside(scb_context* c, const scb_image* dst, scb_image* blend, const scb_geometry& g, int max_threads) {
     const size_t bytes = (size_t)3 * dst->cols * dst->rows;
     int T = (int)(bytes >> 19);  // one thread per 512 KiB (the pool's threads wake in ~10 us; a 1080p frame is 6 MB)
     if (T > max_threads) T = max_threads;
@@ -1152,19 +1264,10 @@ static void host_copy_outside(const scb_image* dst, scb_image* blend, const scb_
         return;
     }
     const int per = (dst->rows + T - 1) / T;
-    HostPool::get().run(T, [&](int t) {
+    pool_of(c).run(T, [&](int t) {
         const int a = t * per, b = (a + per < dst->rows) ? a + per : dst->rows;
         if (a < b) host_copy_rows(dst, blend, g, a, b);
     });
-}
-
-static int host_threads() {
-    static const int n = [] {
-        unsigned h = std::thread::hardware_concurrency();
-        if (const char* e = std::getenv("SCB_HOST_THREADS")) h = (unsigned)std::atoi(e);
-        return (int)(h < 1 ? 1 : (h > 8 ? 8 : h));
-    }();
-    return n;
 }
 
 struct Workspace {
@@ -1553,16 +1656,15 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
 static void run_compose(scb_plan* p, const float* U, unsigned char* out, long long out_pitch, int y0, int y1) {
     if (y1 <= y0) return;
     const scb_geometry& g = p->g;
-    TcComposeParams cp;
-    cp.u = U + (size_t)y0 * g.nx;
+    I8ComposeParams cp;
+    cp.u = U;
     cp.plane = (long long)g.ny * g.nx;
     cp.pitch = g.nx;
     cp.nx = g.nx;
-    cp.ny = g.ny;
-    cp.out = out + (long long)y0 * out_pitch;
+    cp.out = out;
     cp.out_pitch = out_pitch;
-    cp.u_dump = nullptr;
-    SCB_LAUNCH(tc_compose_kernel, dim3((g.nx + 511) / 512, y1 - y0), dim3(128), 0, p->lane->stream, cp);
+    cp.y0 = y0;
+    i8_launch_compose((void*)p->lane->stream, cp, y1 - y0);
     p->ctx->launches++;
 }
 
@@ -1715,7 +1817,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     if (g.empty) {  // OpenCV: blend = dst
         if (copy_dst) {
             if (host) {
-                if (!defer_host) host_copy_outside(dst, blend, g, host_threads());
+                if (!defer_host) host_copy_outside(c, dst, blend, g, host_threads());
             } else {
                 SCB_CUDA(c, cudaMemcpy2DAsync(blend->data, (size_t)blend->stride, dst->data, (size_t)dst->stride, row_bytes, (size_t)p->dst_rows, cudaMemcpyDeviceToDevice, p->lane->stream));
             }
@@ -1861,7 +1963,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (nb_out == 1) SCB_CUDA(c, cudaMemcpy2DAsync(bInt, (size_t)blend->stride, w.stO, (size_t)w.pO, (size_t)3 * g.nx, (size_t)g.ny, cudaMemcpyDeviceToHost, ms));
         tm.mark(ST_OUT);
         if (!defer_host) {
-            if (copy_dst) host_copy_outside(dst, blend, g, host_threads());
+            if (copy_dst) host_copy_outside(c, dst, blend, g, host_threads());
             SCB_CUDA(c, cudaStreamSynchronize(ms));
             SCB_CUDA(c, cudaGetLastError());
         }
@@ -2109,7 +2211,7 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
         }
         if (mem_kind == SCB_MEM_HOST) {  // blend = dst outside each ROI interior: a parallel-for over the chunk's jobs
             const int T = host_threads();
-            HostPool::get().run(T, [&](int t) {
+            pool_of(c).run(T, [&](int t) {
                 for (int i = t; i < m; i += T) {
                     scb_job& j = jobs[base + i];
                     if (copy_ok[i] && j.blend.data != j.dst.data) host_copy_rows(&j.dst, &j.blend, geoms[i], 0, j.dst.rows);

@@ -101,6 +101,16 @@ struct I8GemmParams {
     double* R;                 // [3][lowk][lpc] exact row sums sum_j x[j] sin(..) for k0 < lowk (forward pass), or null
     int lowk;
     double rscale;             // R = t * rscale * lscale[line]
+    long long* trace;          // tuning aid (SCB_I8_TRACE=1): 8 clock64() stamps per CTA, or null
+};
+
+struct I8ComposeParams {
+    const float* u;       // [3][ny][pitch] solved field
+    long long plane;
+    int pitch, nx;
+    unsigned char* out;   // interior origin pixel of the output rows (any alignment)
+    long long out_pitch;
+    int y0;               // first row of this launch
 };
 
 // host launchers (scb_i8.cu).  `da` = digits of the lines: 2 (integer right-hand side, |x| <= 4095 after folding) or 4.
@@ -110,5 +120,6 @@ int i8_configure();  // cudaFuncSetAttribute of the kernels, once per device con
 int i8_launch_basis(void* stream, const I8Geom& g, signed char* basis);
 int i8_launch_digitize(void* stream, const I8DigitizeParams& p, int da);
 int i8_launch_gemm(void* stream, const I8GemmParams& p, int da, int db);
+int i8_launch_compose(void* stream, const I8ComposeParams& p, int rows);
 
 }  // namespace scb

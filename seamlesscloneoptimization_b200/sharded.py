@@ -131,6 +131,24 @@ class ShardedSolve:
             Ct3[:, ys[r] : ys[r + 1], xs[s] : xs[s + 1]].copy_(recv[s])
 
     # -- the solve ---------------------------------------------------------------------------------
+    # bench hook: with `time_collectives` set, CUDA events bracket the exchange of every run(); collective_ms() averages them
+    time_collectives = False
+
+    def _mark(self, start=None):
+        if not self.time_collectives or self._stream is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(self._stream)
+        if start is None:
+            return e
+        self._spans = getattr(self, "_spans", []) + [(start, e)]
+        return None
+
+    def collective_ms(self):
+        spans = getattr(self, "_spans", [])
+        self._spans = []
+        return sum(a.elapsed_time(b) for a, b in spans) / len(spans) if spans else None
+
     def _on_ctx_stream(self):
         return torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
 
@@ -149,8 +167,10 @@ class ShardedSolve:
             e32, e64, wd = self.ends32.data_ptr(), self.f64.data_ptr(), self.f64.data_ptr() + 8 * self.n64
             chk(lib.scb_plan_tri_forward(ph, C.byref(src_view), C.byref(dst_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
             if self.world > 1:  # every rank filled only its own segments / summed only its own rows: zeros elsewhere
+                ev = self._mark()
                 dist.all_reduce(self.ends32, group=self.group)
                 dist.all_reduce(self.f64, group=self.group)
+                self._mark(ev)
             chk(lib.scb_plan_tri_finish(ph, C.byref(blend_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
             return
         y0, y1, x0, x1 = self.ys[r], self.ys[r + 1], self.xs[r], self.xs[r + 1]
