@@ -164,6 +164,12 @@ int scb_plan_get_intermediate(scb_plan* plan, int which, float* out_host, size_t
 int scb_seamless_clone(scb_context* ctx, const scb_image* src, const scb_image* dst, const scb_image* mask,
                        int px, int py, scb_image* blend, int clone_flags, int mem_kind);
 
+/* scb_seamless_clone keeps the plans of its last few (mask, sizes, p, flags) in the context, keyed by a 64-bit hash of the HOST
+ * mask's bytes: a caller that passes the same mask again (video: fixed mask, new frames) skips the mask upload, the bounding-box
+ * round trip, the erosion and the table lookups.  SCB_PLAN_CACHE=n sets the capacity (default 4, 0 disables).
+ * (Replaces the reference's per-call initMask with its blocking D2H, seamlessClone_imp.cpp:978-1071.) */
+int scb_plan_cache_stats(const scb_context* ctx, uint64_t* hits, uint64_t* misses);
+
 /* ---- batch of independent jobs (all HOST or all DEVICE) ---- */
 typedef struct scb_job {
     scb_image src, dst, mask, blend;

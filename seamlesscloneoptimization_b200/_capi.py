@@ -38,7 +38,7 @@ EXPORTS = [
     "scb_create", "scb_destroy", "scb_sync", "scb_stream", "scb_last_error", "scb_status_string",
     "scb_kernel_launches", "scb_device_count", "scb_source_hash", "scb_set_engine", "scb_set_orientation", "scb_tc_selftest", "scb_host_alloc", "scb_host_free",
     "scb_plan_create", "scb_plan_create_ex", "scb_plan_destroy", "scb_plan_geometry", "scb_plan_engine", "scb_plan_execute", "scb_plan_execute_timed", "scb_plan_execute_graph", "scb_plan_set_debug",
-    "scb_plan_get_intermediate", "scb_seamless_clone", "scb_clone_batch",
+    "scb_plan_get_intermediate", "scb_seamless_clone", "scb_plan_cache_stats", "scb_clone_batch",
     "scb_plan_rows_forward", "scb_plan_cols", "scb_plan_lowfreq_finish", "scb_plan_rows_inverse", "scb_plan_lowk",
     "scb_plan_tri_layout", "scb_plan_tri_forward", "scb_plan_tri_finish",
     "my_seamlessclone_api_imp_create_instance", "my_seamlessclone_api_imp_run",
@@ -108,6 +108,7 @@ def load(path: str | None = None) -> C.CDLL:
         "scb_plan_set_debug": (i, [vp, i]),
         "scb_plan_get_intermediate": (i, [vp, i, vp, sz, P(sz)]),
         "scb_seamless_clone": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i, i, P(ScbImage), i, i]),
+        "scb_plan_cache_stats": (i, [vp, P(C.c_uint64), P(C.c_uint64)]),
         "scb_clone_batch": (i, [vp, P(ScbJob), i, i]),
         "scb_plan_rows_forward": (i, [vp, P(ScbImage), P(ScbImage), i, i, i, vp, vp]),
         "scb_plan_cols": (i, [vp, i, i, vp, vp, vp]),

@@ -29,6 +29,15 @@
 #include <sched.h>
 #endif
 
+#if !defined(SCB_EMU) && !defined(SCB_NO_NVTX)
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost nothing unless a profiler is attached
+#define SCB_NVTX_PUSH(name) nvtxRangePushA(name)
+#define SCB_NVTX_POP() nvtxRangePop()
+#else
+#define SCB_NVTX_PUSH(name) ((void)0)
+#define SCB_NVTX_POP() ((void)0)
+#endif
+
 #include "../../include/scb.h"
 #include "scb_kernels.cuh"
 #include "scb_kernels3.cuh"
@@ -40,18 +49,45 @@
 
 using namespace scb;
 
+// One NVTX range per stage of a clone (the reference has CUDA-event timing only, imp.cu:281-349).  The ranges
+// bracket the ENQUEUE of a stage on the host; Nsight Systems projects them onto the kernels they launched.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { SCB_NVTX_PUSH(name); }
+    ~NvtxRange() { SCB_NVTX_POP(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 #ifdef SCB_EMU
 static inline cudaError_t scbMallocAsync(void** p, size_t n, cudaStream_t) { return emu_malloc(p, n); }
+typedef void* cudaMemPool_t;
+static inline cudaError_t scbMallocPoolAsync(void** p, size_t n, cudaMemPool_t, cudaStream_t) { return emu_malloc(p, n); }
 static inline cudaError_t scbFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
 #else
 static inline cudaError_t scbMallocAsync(void** p, size_t n, cudaStream_t s) { return cudaMallocAsync(p, n, s); }
+static inline cudaError_t scbMallocPoolAsync(void** p, size_t n, cudaMemPool_t pool, cudaStream_t s) {
+    return pool ? cudaMallocFromPoolAsync(p, n, pool, s) : cudaMallocAsync(p, n, s);
+}
 static inline cudaError_t scbFreeAsync(void* p, cudaStream_t s) { return cudaFreeAsync(p, s); }
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// Bookkeeping of one cached table: the context's table caches are bounded (byte budget, LRU) and an entry is only evicted
+// while no live plan references it.
+struct CacheMeta {
+    size_t bytes = 0;
+    int refs = 0;
+    uint64_t last_use = 0;
+};
+
 struct DevLenTab {
     LenTabDev dev{};
     void* block = nullptr;
+    CacheMeta meta;
+};
+struct DevFilter {
+    float* d = nullptr;
+    CacheMeta meta;
 };
 
 // A lane is one in-order pipeline of the context: a stream, the side stream of the low-frequency
@@ -78,6 +114,7 @@ static const int kDefaultLanes = 4;  // SCB_LANES=1..8 overrides (tuning)
 struct DevTcTab {
     TcTabDev dev{};
     void* block = nullptr;
+    CacheMeta meta;
 #ifndef SCB_EMU
     CUtensorMap map;
 #endif
@@ -86,11 +123,13 @@ struct DevTcTab {
 struct DevTriTab {
     TriTabDev dev{};
     void* block = nullptr;
+    CacheMeta meta;
 };
 
 struct DevI8Tab {  // digit planes of the folded sine basis of one line length (scb_i8.h)
     I8Geom g{};
     signed char* basis = nullptr;
+    CacheMeta meta;
 };
 
 class HostPool;
@@ -100,6 +139,7 @@ static void host_pool_free(scb_context* c);  // defined next to the class
 struct scb_context {
     int device = 0;
     HostPool* pool = nullptr;           // helper threads of the host-side dst -> blend copy; one pool per context (created on first use)
+    cudaMemPool_t mem_pool = nullptr;   // private stream-ordered pool of the plans' eroded masks / staged masks (never the device's default pool)
     std::map<std::pair<int, int>, DevTriTab> tritabs;  // keyed by ROI (w, h): LU factors of the tridiagonal engine
     int engine = SCB_ENGINE_AUTO;
     int orientation = -1;               // tridiagonal engine: -1 cost model, 0 FFT passes along x, 1 along y (scb_set_orientation)
@@ -112,7 +152,21 @@ struct scb_context {
     std::atomic<uint64_t> launches{0};  // scb_clone_batch plans the next chunk on a helper thread
     std::mutex err_mu;
     std::map<int, DevLenTab> lentabs;   // keyed by n
-    std::map<int, float*> filters;      // keyed by ROI extent
+    std::map<int, DevFilter> filters;   // keyed by ROI extent
+    std::mutex table_mu;                // the table caches: scb_clone_batch plans on a helper thread while the caller's thread destroys plans
+    size_t table_bytes = 0, table_budget = (size_t)1 << 30;  // SCB_TABLE_BUDGET_MB overrides (a 4K ROI size costs ~10 MB of tables)
+    uint64_t use_clock = 0;
+    // scb_seamless_clone's plan cache: (hash of the mask bytes, sizes, p, flags, engine) -> plan.  A video-style caller that passes
+    // the same mask every frame skips the mask upload, the bounding-box round trip, the erosion and the table lookups.
+    struct CachedPlan {
+        uint64_t hash = 0;
+        int key[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        scb_plan* plan = nullptr;
+        uint64_t last_use = 0;
+    };
+    std::vector<CachedPlan> plan_cache;
+    int plan_cache_cap = 4;  // SCB_PLAN_CACHE=n overrides, 0 disables
+    uint64_t plan_hits = 0, plan_misses = 0;
     int* bbox_dev = nullptr;     // [slots][kBboxInts]: min x, min y, max x, max y, "mask has grey values", 3 unused
     int* bbox_pinned = nullptr;  // [0..kBboxInts) init pattern, then [slots][kBboxInts] results
     int bbox_slots = 0;
@@ -149,6 +203,7 @@ struct scb_plan {
     bool use_tri = false;               // tridiagonal column solve (scb_tri.cuh) instead of the column FFT pass
     bool use_i8 = false;                // with use_tri: the passes along x as exact INT8 tensor-core contractions (scb_i8.h) instead of FFTs
     const DevI8Tab* i8x = nullptr;
+    std::vector<CacheMeta*> table_refs; // cached tables this plan uses (released in scb_plan_destroy)
     bool grey_mask = false;             // the mask holds values other than 0 / 255 inside its ring: the right-hand side is not integer valued
     bool swap = false;                  // tridiagonal engine: FFT passes along y and the tridiagonal solve along x (choose_swap)
     TriTabDev tri{};                    // LU factors for the chosen orientation
@@ -418,10 +473,47 @@ static void launch_rows_inv(scb_context* c, cudaStream_t stream, int log2m, int 
 // ------------------------------------------------------------------------------------------------
 // table caches
 // ------------------------------------------------------------------------------------------------
-static int get_lentab(scb_context* c, int n, LenTabDev* out) {
+// A plan takes a reference on every table it uses; callers hold c->table_mu.
+static void table_ref(scb_context* c, scb_plan* p, CacheMeta* m) {
+    m->last_use = ++c->use_clock;
+    if (p) {  // (a table fetched without a plan -- the self-test -- is only touched, not pinned)
+        m->refs++;
+        p->table_refs.push_back(m);
+    }
+}
+static void table_added(scb_context* c, CacheMeta* m, size_t bytes) {
+    m->bytes = bytes;
+    c->table_bytes += bytes;
+}
+// Evicts least-recently-used tables that no live plan references until the caches fit the budget again (cudaFree waits for
+// the device, so nothing can still be reading them).  Called with c->table_mu held, after an insertion.
+static void evict_tables(scb_context* c) {
+    while (c->table_bytes > c->table_budget) {
+        CacheMeta* best = nullptr;
+        std::function<void()> drop;
+        auto consider = [&](CacheMeta& m, std::function<void()> d) {
+            if (m.refs == 0 && m.bytes > 0 && (!best || m.last_use < best->last_use)) {
+                best = &m;
+                drop = std::move(d);
+            }
+        };
+        for (auto it = c->lentabs.begin(); it != c->lentabs.end(); ++it) consider(it->second.meta, [c, it] { cudaFree(it->second.block); c->lentabs.erase(it); });
+        for (auto it = c->filters.begin(); it != c->filters.end(); ++it) consider(it->second.meta, [c, it] { cudaFree(it->second.d); c->filters.erase(it); });
+        for (auto it = c->tctabs.begin(); it != c->tctabs.end(); ++it) consider(it->second.meta, [c, it] { cudaFree(it->second.block); c->tctabs.erase(it); });
+        for (auto it = c->tritabs.begin(); it != c->tritabs.end(); ++it) consider(it->second.meta, [c, it] { cudaFree(it->second.block); c->tritabs.erase(it); });
+        for (auto it = c->i8tabs.begin(); it != c->i8tabs.end(); ++it) consider(it->second.meta, [c, it] { cudaFree(it->second.basis); c->i8tabs.erase(it); });
+        if (!best) return;  // everything left is in use
+        c->table_bytes -= best->bytes;
+        drop();
+    }
+}
+
+static int get_lentab(scb_context* c, scb_plan* p, int n, LenTabDev* out) {
+    std::lock_guard<std::mutex> lk(c->table_mu);
     auto it = c->lentabs.find(n);
     if (it != c->lentabs.end()) {
         *out = it->second.dev;
+        table_ref(c, p, &it->second.meta);
         return SCB_OK;
     }
     HostLenTab h = build_len_tab(n);
@@ -442,8 +534,14 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     std::memcpy(host.data() + off_sin, h.sinlow.data(), h.sinlow.size() * sizeof(double));
     DevLenTab d;
     SCB_CUDA(c, cudaMalloc(&d.block, total));
-    SCB_CUDA(c, cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->lanes[0].stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));  // `host` dies at scope exit; a blocking sync also publishes the table to every lane
+    {
+        cudaError_t e = cudaMemcpyAsync(d.block, host.data(), total, cudaMemcpyHostToDevice, c->lanes[0].stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->lanes[0].stream);  // `host` dies at scope exit; a blocking sync also publishes the table to every lane
+        if (e != cudaSuccess) {
+            cudaFree(d.block);
+            return fail(c, SCB_ERR_CUDA, std::string("get_lentab: ") + cudaGetErrorString(e));
+        }
+    }
     char* b = (char*)d.block;
     d.dev.n = n;
     d.dev.log2m = h.log2m;
@@ -454,8 +552,11 @@ static int get_lentab(scb_context* c, int n, LenTabDev* out) {
     d.dev.tw = (const float2*)(b + off_tw);
     d.dev.gtw = (const float4*)(b + off_ptw);
     d.dev.sinlow = (const double*)(b + off_sin);
-    c->lentabs[n] = d;
+    auto ins = c->lentabs.emplace(n, d);
+    table_added(c, &ins.first->second.meta, total);
+    table_ref(c, p, &ins.first->second.meta);
     *out = d.dev;
+    evict_tables(c);
     return SCB_OK;
 }
 
@@ -474,10 +575,12 @@ static EncodeTiledFn encode_tiled_fn() {
 #endif
 
 // split sine basis of one line length for the tensor-core engine, built on the device at plan time
-static int get_tctab(scb_context* c, int n, const DevTcTab** out) {
+static int get_tctab(scb_context* c, scb_plan* p, int n, const DevTcTab** out) {
+    std::lock_guard<std::mutex> lk(c->table_mu);
     auto it = c->tctabs.find(n);
     if (it != c->tctabs.end()) {
         *out = &it->second;
+        table_ref(c, p, &it->second.meta);
         return SCB_OK;
     }
     DevTcTab d;
@@ -492,8 +595,14 @@ static int get_tctab(scb_context* c, int n, const DevTcTab** out) {
         SCB_LAUNCH(tc_basis_kernel, dim3((unsigned)blocks), dim3(256), 0, c->lanes[0].stream, d.dev, (float*)d.block);
         c->launches++;
     }
-    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));  // publishes the table to every lane
-    SCB_CUDA(c, cudaGetLastError());
+    {
+        cudaError_t e = cudaStreamSynchronize(c->lanes[0].stream);  // publishes the table to every lane
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFree(d.block);
+            return fail(c, SCB_ERR_CUDA, std::string("get_tctab: ") + cudaGetErrorString(e));
+        }
+    }
 #ifndef SCB_EMU
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) {
@@ -512,7 +621,10 @@ static int get_tctab(scb_context* c, int n, const DevTcTab** out) {
     }
 #endif
     auto ins = c->tctabs.emplace(n, d);
+    table_added(c, &ins.first->second.meta, floats * sizeof(float));
+    table_ref(c, p, &ins.first->second.meta);
     *out = &ins.first->second;
+    evict_tables(c);
     return SCB_OK;
 }
 
@@ -549,10 +661,12 @@ static bool i8_eligible(const scb_context* c, int nx, int mode) {
 }
 
 // digit planes of the folded sine basis of one line length, built on the device at plan time, cached in the context
-static int get_i8tab(scb_context* c, int n, const DevI8Tab** out) {
+static int get_i8tab(scb_context* c, scb_plan* p, int n, const DevI8Tab** out) {
+    std::lock_guard<std::mutex> lk(c->table_mu);
     auto it = c->i8tabs.find(n);
     if (it != c->i8tabs.end()) {
         *out = &it->second;
+        table_ref(c, p, &it->second.meta);
         return SCB_OK;
     }
     DevI8Tab d;
@@ -566,19 +680,30 @@ static int get_i8tab(scb_context* c, int n, const DevI8Tab** out) {
         return fail(c, SCB_ERR_CUDA, "i8_basis_kernel launch failed");
     }
     c->launches++;
-    SCB_CUDA(c, cudaStreamSynchronize(s));  // publishes the table to every lane
-    SCB_CUDA(c, cudaGetLastError());
+    {
+        cudaError_t e = cudaStreamSynchronize(s);  // publishes the table to every lane
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFree(b);
+            return fail(c, SCB_ERR_CUDA, std::string("get_i8tab: ") + cudaGetErrorString(e));
+        }
+    }
     auto ins = c->i8tabs.emplace(n, d);
+    table_added(c, &ins.first->second.meta, i8_basis_bytes(d.g));
+    table_ref(c, p, &ins.first->second.meta);
     *out = &ins.first->second;
+    evict_tables(c);
     return SCB_OK;
 }
 
 // LU factors m[d][k] of tridiag(-1, 4 - fx[k], -1), built on the device at plan time, cached per ROI (w, h)
-static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
+static int get_tritab(scb_context* c, scb_plan* p, int w, int h, TriTabDev* out) {
+    std::lock_guard<std::mutex> lk(c->table_mu);
     const auto key = std::make_pair(w, h);
     auto it = c->tritabs.find(key);
     if (it != c->tritabs.end()) {
         *out = it->second.dev;
+        table_ref(c, p, &it->second.meta);
         return SCB_OK;
     }
     const int nx = w - 2, ny = h - 2;
@@ -595,8 +720,15 @@ static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
     SCB_CUDA(c, cudaMalloc(&d.block, total));
     char* b = (char*)d.block;
     cudaStream_t s = c->lanes[0].stream;
-    SCB_CUDA(c, cudaMemsetAsync(b + off_m64, 0, off_th - off_m64, s));
-    SCB_CUDA(c, cudaMemcpyAsync(b + off_th, th.data(), (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, s));
+    auto drop = [&](cudaError_t e) {  // every failure path frees the block
+        cudaFree(d.block);
+        return fail(c, e == cudaErrorMemoryAllocation ? SCB_ERR_OUT_OF_MEMORY : SCB_ERR_CUDA, std::string("get_tritab: ") + cudaGetErrorString(e));
+    };
+    {
+        cudaError_t e = cudaMemsetAsync(b + off_m64, 0, off_th - off_m64, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b + off_th, th.data(), (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return drop(e);
+    }
     TriTableParams tp;
     tp.theta = (const double*)(b + off_th);
     tp.nx = nx;
@@ -613,8 +745,11 @@ static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
         SCB_LAUNCH(tri_table_kernel, dim3((unsigned)blocks), dim3(256), 0, s, tp);
         c->launches++;
     }
-    SCB_CUDA(c, cudaStreamSynchronize(s));  // `th` dies at scope exit; also publishes the table to every lane
-    SCB_CUDA(c, cudaGetLastError());
+    {
+        cudaError_t e = cudaStreamSynchronize(s);  // `th` dies at scope exit; also publishes the table to every lane
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return drop(e);
+    }
     d.dev.m32 = tp.m32;
     d.dev.p32 = tp.p32;
     d.dev.pm = pm;
@@ -622,8 +757,11 @@ static int get_tritab(scb_context* c, int w, int h, TriTabDev* out) {
     d.dev.m64 = tp.m64;
     d.dev.p64 = tp.p64;
     d.dev.theta = tp.theta;
-    c->tritabs[key] = d;
+    auto ins = c->tritabs.emplace(key, d);
+    table_added(c, &ins.first->second.meta, total);
+    table_ref(c, p, &ins.first->second.meta);
     *out = d.dev;
+    evict_tables(c);
     return SCB_OK;
 }
 
@@ -637,19 +775,32 @@ static bool tc_eligible(const scb_context* c, int nx, int ny) {
     return nx >= kTcMinN && ny >= kTcMinN && nx <= kTcMaxN && ny <= kTcMaxN;
 }
 
-static int get_filter(scb_context* c, int extent, const float** out) {
+static int get_filter(scb_context* c, scb_plan* p, int extent, const float** out) {
+    std::lock_guard<std::mutex> lk(c->table_mu);
     auto it = c->filters.find(extent);
     if (it != c->filters.end()) {
-        *out = it->second;
+        *out = it->second.d;
+        table_ref(c, p, &it->second.meta);
         return SCB_OK;
     }
     std::vector<float> f = build_filter(extent);
     float* d = nullptr;
     SCB_CUDA(c, cudaMalloc(&d, f.size() * sizeof(float)));
-    SCB_CUDA(c, cudaMemcpyAsync(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c->lanes[0].stream));
-    SCB_CUDA(c, cudaStreamSynchronize(c->lanes[0].stream));
-    c->filters[extent] = d;
+    {
+        cudaError_t e = cudaMemcpyAsync(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice, c->lanes[0].stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->lanes[0].stream);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return fail(c, SCB_ERR_CUDA, std::string("get_filter: ") + cudaGetErrorString(e));
+        }
+    }
+    DevFilter df;
+    df.d = d;
+    auto ins = c->filters.emplace(extent, df);
+    table_added(c, &ins.first->second.meta, f.size() * sizeof(float));
+    table_ref(c, p, &ins.first->second.meta);
     *out = d;
+    evict_tables(c);
     return SCB_OK;
 }
 
@@ -679,21 +830,34 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
 #ifndef SCB_EMU
-    {   // plans allocate their eroded mask with cudaMallocAsync: keep freed blocks in the pool across syncs
-        // (the default release threshold of 0 hands them back to the OS at every synchronisation)
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    {   // Plans allocate their eroded mask stream-ordered.  A PRIVATE pool: its release threshold (keep freed blocks across
+        // synchronisations instead of handing them back to the OS every time) is nobody else's business, and scb_destroy
+        // returns the memory.  (Setting the threshold on the device's default pool would change the host application.)
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->mem_pool, &props) == cudaSuccess && c->mem_pool) {
+            unsigned long long keep = 256ull << 20;
+            cudaMemPoolSetAttribute(c->mem_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            c->mem_pool = nullptr;  // fall back to the default pool, untouched
+            cudaGetLastError();
         }
     }
 #endif
     if ((e = lane_create(&c->lanes[0], (cudaStream_t)external_stream)) != cudaSuccess) return bail("stream/event creation", e);
     c->n_lanes = 1;
+    if (const char* e = std::getenv("SCB_PLAN_CACHE")) c->plan_cache_cap = std::atoi(e) > 0 ? std::atoi(e) : 0;
+    if (const char* e = std::getenv("SCB_TABLE_BUDGET_MB")) c->table_budget = (size_t)(std::atoll(e) > 0 ? std::atoll(e) : 1) << 20;
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if ((e = configure_all()) != cudaSuccess) return bail("cudaFuncSetAttribute (is this an sm_100a device?)", e);
     if ((e = (cudaError_t)i8_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute of the INT8 tensor-core kernels", e);
+#ifndef SCB_EMU
+    if ((e = cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess) return bail("cudaFuncSetAttribute(tc_pass_kernel)", e);
+#endif
     if (ensure_bbox_slots(c, 1) != SCB_OK) {
         g_create_error = c->err;
         for (int i = 0; i < c->n_lanes; ++i) lane_destroy(&c->lanes[i]);
@@ -707,19 +871,24 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
 extern "C" int scb_destroy(scb_context* c) {
     if (!c) return SCB_OK;
     cudaSetDevice(c->device);
+    for (auto& cp : c->plan_cache) scb_plan_destroy(cp.plan);
+    c->plan_cache.clear();
     for (int i = 0; i < c->n_lanes; ++i) lane_destroy(&c->lanes[i]);
     if (c->prep) {
         cudaStreamSynchronize(c->prep);
         cudaStreamDestroy(c->prep);
     }
     for (auto& kv : c->lentabs) cudaFree(kv.second.block);
-    for (auto& kv : c->filters) cudaFree(kv.second);
+    for (auto& kv : c->filters) cudaFree(kv.second.d);
     for (auto& kv : c->tctabs) cudaFree(kv.second.block);
     for (auto& kv : c->tritabs) cudaFree(kv.second.block);
     for (auto& kv : c->i8tabs) cudaFree(kv.second.basis);
     if (c->bbox_dev) cudaFree(c->bbox_dev);
     if (c->bbox_pinned) cudaFreeHost(c->bbox_pinned);
     host_pool_free(c);
+#ifndef SCB_EMU
+    if (c->mem_pool) cudaMemPoolDestroy(c->mem_pool);
+#endif
     delete c;
     return SCB_OK;
 }
@@ -792,6 +961,11 @@ extern "C" int scb_plan_destroy(scb_plan* p) {
     cudaSetDevice(p->ctx->device);
     if (p->E) scbFreeAsync(p->E, p->lane->stream);
     if (p->mask_stage) scbFreeAsync(p->mask_stage, p->lane->stream);
+    {
+        std::lock_guard<std::mutex> lk(p->ctx->table_mu);
+        for (CacheMeta* m : p->table_refs) m->refs--;
+        p->table_refs.clear();
+    }
     plan_drop_graph(p);
     plan_free_debug(p);
     delete p;
@@ -813,6 +987,7 @@ struct PlanInput {
 
 static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
                       int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in, int clone_flags = SCB_NORMAL_CLONE) {
+    NvtxRange nvtx_("scb:plan_begin");
     *out = nullptr;
     const bool wide = clone_flags >= SCB_NORMAL_CLONE_WIDE;
     const int mode = wide ? clone_flags - (SCB_NORMAL_CLONE_WIDE - SCB_NORMAL_CLONE) : clone_flags;
@@ -847,7 +1022,7 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
     if (mask_mem_kind == SCB_MEM_HOST) {
         const size_t pitch = align_up((size_t)mask->cols, 16);
         void* m = nullptr;
-        if (scbMallocAsync(&m, pitch * mask->rows, prep) != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
+        if (scbMallocPoolAsync(&m, pitch * mask->rows, c->mem_pool, prep) != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
         p->mask_stage = (unsigned char*)m;
         cudaError_t e = cudaMemcpy2DAsync(m, pitch, mask->data, (size_t)mask->stride, (size_t)mask->cols, (size_t)mask->rows, cudaMemcpyHostToDevice, prep);
         if (e != cudaSuccess) return bad(SCB_ERR_CUDA, std::string("mask upload: ") + cudaGetErrorString(e));
@@ -875,6 +1050,7 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
 
 // Call after the prep stream has been synchronised past plan_begin.  On failure the plan is destroyed.
 static int plan_finish(scb_plan* p, const PlanInput& in) {
+    NvtxRange nvtx_("scb:plan_finish");
     scb_context* c = p->ctx;
     Lane* lane = p->lane;
     const int* r = c->bbox_pinned + kBboxInts * (in.slot + 1);
@@ -918,7 +1094,7 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
     p->e_pitch = (long long)align_up((size_t)g.w, 16);
     {
         void* e = nullptr;
-        cudaError_t ce = scbMallocAsync(&e, (size_t)p->e_pitch * g.h, lane->stream);
+        cudaError_t ce = scbMallocPoolAsync(&e, (size_t)p->e_pitch * g.h, c->mem_pool, lane->stream);
         if (ce != cudaSuccess) return bad(SCB_ERR_OUT_OF_MEMORY, "scb_plan_create: cudaMallocAsync failed");
         p->E = (unsigned char*)e;
     }
@@ -926,25 +1102,25 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
     c->launches++;
     release_stage();  // stream-ordered: freed after the erosion has read it
     int rc;
-    if ((rc = get_lentab(c, g.nx, &p->tx)) || (rc = get_lentab(c, g.ny, &p->ty)) || (rc = get_filter(c, g.w, &p->fx)) || (rc = get_filter(c, g.h, &p->fy))) {
+    if ((rc = get_lentab(c, p, g.nx, &p->tx)) || (rc = get_lentab(c, p, g.ny, &p->ty)) || (rc = get_filter(c, p, g.w, &p->fx)) || (rc = get_filter(c, p, g.h, &p->fy))) {
         scb_plan_destroy(p);
         return rc;
     }
     p->lowkx = p->tx.lowk;
     p->lowky = p->ty.lowk;
     p->use_tc = tc_eligible(c, g.nx, g.ny);
-    if (p->use_tc && ((rc = get_tctab(c, g.nx, &p->ttx)) || (rc = get_tctab(c, g.ny, &p->tty)))) {
+    if (p->use_tc && ((rc = get_tctab(c, p, g.nx, &p->ttx)) || (rc = get_tctab(c, p, g.ny, &p->tty)))) {
         scb_plan_destroy(p);
         return rc;
     }
     p->use_tri = !p->use_tc && tri_eligible(c);
     p->swap = p->use_tri && choose_swap(p);
-    if (p->use_tri && (rc = p->swap ? get_tritab(c, g.h, g.w, &p->tri) : get_tritab(c, g.w, g.h, &p->tri))) {
+    if (p->use_tri && (rc = p->swap ? get_tritab(c, p, g.h, g.w, &p->tri) : get_tritab(c, p, g.w, g.h, &p->tri))) {
         scb_plan_destroy(p);
         return rc;
     }
     p->use_i8 = p->use_tri && !p->swap && i8_eligible(c, g.nx, p->mode);
-    if (p->use_i8 && (rc = get_i8tab(c, g.nx, &p->i8x))) {
+    if (p->use_i8 && (rc = get_i8tab(c, p, g.nx, &p->i8x))) {
         scb_plan_destroy(p);
         return rc;
     }
@@ -1003,7 +1179,7 @@ extern "C" int scb_plan_set_debug(scb_plan* p, int on) {
     p->debug = false;
     if (on && !p->g.empty && p->swap) {  // the intermediates are defined in the natural orientation
         p->swap = false;
-        int rc = get_tritab(c, p->g.w, p->g.h, &p->tri);
+        int rc = get_tritab(c, p, p->g.w, p->g.h, &p->tri);
         if (rc) return rc;
     }
     if (on && !p->g.empty) {
@@ -1256,6 +1432,7 @@ static void host_pool_free(scb_context* c) {
 }
 
 static void host_copy_outside(scb_context* c, const scb_image* dst, scb_image* blend, const scb_geometry& g, int max_threads) {
+    NvtxRange nvtx_("scb:host_copy");
     const size_t bytes = (size_t)3 * dst->cols * dst->rows;
     int T = (int)(bytes >> 19);  // one thread per 512 KiB (the pool's threads wake in ~10 us; a 1080p frame is 6 MB)
     if (T > max_threads) T = max_threads;
@@ -1388,6 +1565,7 @@ static bool choose_swap(const scb_plan* p) {
 }
 
 static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0, int y1, bool swap = false) {
+    NvtxRange nvtx_("scb:rhs");
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
     RhsParams rp;
@@ -1417,6 +1595,7 @@ static void run_rhs(scb_plan* p, const StencilSrc& st, float* G, int gp, int y0,
 }
 
 static void run_lowfreq_rows(scb_plan* p, const StencilSrc& st, const float* G, int gp, double* R, int y0, int y1, cudaStream_t stream, bool swap = false) {
+    NvtxRange nvtx_("scb:lowfreq_rows");
     scb_context* c = p->ctx;
     if (y1 <= y0) return;
     const Frame f = frame_of(p, swap);
@@ -1446,6 +1625,7 @@ static void run_lowfreq_cols(scb_plan* p, const double* R, float* lowspec, cudaS
     c->launches++;
 }
 static void run_rows_fwd(scb_plan* p, const StencilSrc& st, const float* G, int gp, float* At, int y0, int y1, bool natural = false, bool swap = false) {
+    NvtxRange nvtx_("scb:rows_fwd");
     const Frame f = frame_of(p, swap);
     RowsFwdParams a;
     a.st = st;
@@ -1471,6 +1651,7 @@ static bool refine_off() {
 }
 
 static void run_cols(scb_plan* p, const float* At, float* Ct, const float* lowspec, int x0, int x1) {
+    NvtxRange nvtx_("scb:cols");
     if (refine_off()) lowspec = nullptr;
     ColsParams b;
     b.ty = p->ty;
@@ -1541,6 +1722,7 @@ static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaS
 // Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][cnt][len] -> Ct [3][cnt][len]);
 // the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
 static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap) {
+    NvtxRange nvtx_("scb:tri_solve");
     scb_context* c = p->ctx;
     const Frame f = frame_of(p, swap);  // "columns" of the solve = the f.len frequencies of a line, solved across the f.cnt lines
     Lane* L = p->lane;
@@ -1560,6 +1742,7 @@ static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, doub
 }
 
 static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long long out_pitch, int y0, int y1, bool swap = false) {
+    NvtxRange nvtx_("scb:rows_inv");
     const Frame f = frame_of(p, swap);
     RowsInvParams r;
     r.tx = f.tl;
@@ -1578,6 +1761,7 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
 // ---- exact INT8 tensor-core passes along x (scb_i8.h): digit planes -> tcgen05.mma.kind::i8 -> class sums -> float ----
 // forward: G [3][ny][gp] -> A [3][ny][nx] (= -2 sum g sin, what rows_fwd produces) and the exact float64 row sums R [3][lowkx][ny]
 static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R) {
+    NvtxRange nvtx_("scb:rows_fwd_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
     const int lines = 3 * g.ny, da = p->grey_mask ? 4 : 2;
@@ -1617,6 +1801,7 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
 }
 // inverse: Ct [3][ny][nx] -> U [3][ny][nx] (= sum Ct sin / (nx+1))
 static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U) {
+    NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
     const int lines = 3 * g.ny;
@@ -1654,6 +1839,7 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
 }
 // compose rows [y0, y1): planar float solved field -> interleaved u8 (clamp, truncate)
 static void run_compose(scb_plan* p, const float* U, unsigned char* out, long long out_pitch, int y0, int y1) {
+    NvtxRange nvtx_("scb:compose");
     if (y1 <= y0) return;
     const scb_geometry& g = p->g;
     I8ComposeParams cp;
@@ -1669,14 +1855,9 @@ static void run_compose(scb_plan* p, const float* U, unsigned char* out, long lo
 }
 
 // ---- tensor-core engine: the four passes + compose (scb_tc.cuh) ----
+// (the dynamic shared memory attribute of tc_pass_kernel is per DEVICE: it is set in scb_create, after cudaSetDevice)
 static int tc_configure_once(scb_context* c) {
-#ifndef SCB_EMU
-    static bool done = false;
-    if (!done) {
-        SCB_CUDA(c, cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-        done = true;
-    }
-#endif
+    (void)c;
     return SCB_OK;
 }
 
@@ -1801,6 +1982,7 @@ static int tc_solve(scb_plan* p, const Workspace& w, unsigned char* out, long lo
 }
 
 static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, StageTimer& tm, bool defer_host = false) {
+    NvtxRange nvtx_("scb:execute");
     if (!p) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     int rc;
@@ -1998,16 +2180,94 @@ extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const s
     return rc;
 }
 
+// 64-bit hash of a HOST mask (every byte: a mask that differs anywhere must miss), over the context's helper threads.
+// Four independent multiply-xor chains per thread keep the multiplier pipelined (~10 GB/s per thread).
+static uint64_t hash_rows(const scb_image* m, int y0, int y1) {
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    for (int y = y0; y < y1; ++y) {
+        const unsigned char* r = (const unsigned char*)m->data + (size_t)y * m->stride;
+        size_t n = (size_t)m->cols, i = 0;
+        for (; i + 32 <= n; i += 32) {
+            uint64_t w[4];
+            std::memcpy(w, r + i, 32);
+            for (int k = 0; k < 4; ++k) h[k] = ((h[k] ^ w[k]) * K) ^ (h[k] >> 29);
+        }
+        uint64_t tail = 0;
+        for (; i < n; ++i) tail = (tail << 8) | r[i];
+        h[0] = ((h[0] ^ tail ^ (uint64_t)y) * K) ^ (h[0] >> 31);
+    }
+    return ((h[0] * K) ^ h[1]) * K ^ ((h[2] * K) ^ h[3]);
+}
+static uint64_t hash_mask(scb_context* c, const scb_image* m) {
+    const size_t bytes = (size_t)m->rows * m->cols;
+    int T = (int)(bytes >> 18);  // one thread per 256 KiB
+    if (T > host_threads()) T = host_threads();
+    if (T <= 1) return hash_rows(m, 0, m->rows);
+    uint64_t part[16] = {0};
+    if (T > 16) T = 16;
+    const int per = (m->rows + T - 1) / T;
+    pool_of(c).run(T, [&](int t) {
+        const int a = t * per, b = (a + per < m->rows) ? a + per : m->rows;
+        part[t] = a < b ? hash_rows(m, a, b) : 0;
+    });
+    uint64_t h = 0x452821E638D01377ull;
+    for (int t = 0; t < T; ++t) h = ((h ^ part[t]) * 0x9E3779B97F4A7C15ull) ^ (h >> 32);
+    return h;
+}
+
 extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const scb_image* dst, const scb_image* mask,
                                   int px, int py, scb_image* blend, int clone_flags, int mem_kind) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
     if (!src || !dst || !blend) return fail(c, SCB_ERR_INVALID_ARGUMENT, "seamlessClone: null image");
+    const bool cacheable = mem_kind == SCB_MEM_HOST && c->plan_cache_cap > 0 && mask && mask->data && mask->channels == 1 && mask->rows > 0 && mask->cols > 0 &&
+                           mask->stride >= mask->cols;
+    if (!cacheable) {
+        scb_plan* p = nullptr;
+        int rc = scb_plan_create_ex(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p);
+        if (rc) return rc;
+        rc = scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
+        scb_plan_destroy(p);
+        return rc;
+    }
+    // plan cache: everything a plan depends on is in the key (the mask by its hash)
+    scb_context::CachedPlan want;
+    {
+        NvtxRange nvtx_("scb:mask_hash");
+        want.hash = hash_mask(c, mask);
+    }
+    const int key[11] = {mask->rows, mask->cols, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, wanted_engine(c), c->orientation};
+    std::memcpy(want.key, key, sizeof(key));
     scb_plan* p = nullptr;
-    int rc = scb_plan_create_ex(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p);
-    if (rc) return rc;
-    rc = scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
-    scb_plan_destroy(p);
-    return rc;
+    for (auto& cp : c->plan_cache)
+        if (cp.hash == want.hash && std::memcmp(cp.key, want.key, sizeof(key)) == 0) {
+            cp.last_use = ++c->use_clock;
+            p = cp.plan;
+            c->plan_hits++;
+            break;
+        }
+    if (!p) {
+        c->plan_misses++;
+        int rc = scb_plan_create_ex(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p);
+        if (rc) return rc;
+        if ((int)c->plan_cache.size() >= c->plan_cache_cap) {  // evict the least recently used plan
+            size_t lru = 0;
+            for (size_t i = 1; i < c->plan_cache.size(); ++i)
+                if (c->plan_cache[i].last_use < c->plan_cache[lru].last_use) lru = i;
+            scb_plan_destroy(c->plan_cache[lru].plan);
+            c->plan_cache.erase(c->plan_cache.begin() + (long)lru);
+        }
+        want.plan = p;
+        want.last_use = ++c->use_clock;
+        c->plan_cache.push_back(want);
+    }
+    return scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
+}
+extern "C" int scb_plan_cache_stats(const scb_context* c, uint64_t* hits, uint64_t* misses) {
+    if (!c) return SCB_ERR_INVALID_ARGUMENT;
+    if (hits) *hits = c->plan_hits;
+    if (misses) *misses = c->plan_misses;
+    return SCB_OK;
 }
 
 // Replays the plan's device-resident launches (D2D copy of dst, stencil, refinement on the side stream,
@@ -2403,7 +2663,7 @@ extern "C" int scb_tc_selftest(scb_context* c, int n, int lines, int transposed,
     int rc = tc_configure_once(c);
     if (rc) return rc;
     const DevTcTab* tab = nullptr;
-    if ((rc = get_tctab(c, n, &tab))) return rc;
+    if ((rc = get_tctab(c, nullptr, n, &tab))) return rc;
     const int pin = (int)align_up((size_t)n, 4), pl = (int)align_up((size_t)lines, 4);
     std::vector<float> hin((size_t)lines * pin, 0.f);
     unsigned long long seed = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)n << 20) ^ (unsigned long long)lines;
