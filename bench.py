@@ -615,21 +615,37 @@ def sharded_leg(env, args, steps=None):
         if same_all != 0.0:
             raise SystemExit("bench.py: the sharded solve differs from the single-GPU solve of the same plan")
         del single
+        # the exchange's own time: CUDA events around the collective of a few plain (un-captured) runs
+        solve.time_collectives = True
         for _ in range(env.warmup):
             device_step()
+        torch.cuda.synchronize()
+        coll_ms = solve.collective_ms()
+        solve.time_collectives = False
+        # the timed steps replay ONE CUDA graph per solve: the C-ABI passes and the NCCL exchange captured together, no host round trip
+        use_graph = solve.tri and env.world > 1 and not args.no_sharded_graph
+        launches_per_step = 0
+        if use_graph:
+            l0 = ctx.kernel_launches
+            solve.capture(vs, vd, vb)
+            launches_per_step = ctx.kernel_launches - l0
+            graph_step = solve.run_graph
+            for _ in range(2):
+                graph_step()
+            torch.cuda.synchronize()
+            ya, yb_ = g.ry + 1 + solve.ys[env.rank], g.ry + 1 + solve.ys[env.rank + 1]
+        else:
+            graph_step = device_step
         env.barrier()
         sampler = ClockSampler(env.local_rank)
         sampler.start()
         launches0 = ctx.kernel_launches
-        solve.time_collectives = True
-        evs = env.timed_steps(stream, device_step, args.steps)
+        evs = env.timed_steps(stream, graph_step, args.steps)
         sampler.sample()
         env.barrier()
-        launches = ctx.kernel_launches - launches0
+        launches = (ctx.kernel_launches - launches0) or launches_per_step * args.steps  # replayed launches are counted at capture time
         sampler.stop()
         step_ms = [a.elapsed_time(b) for a, b in evs]
-        coll_ms = solve.collective_ms()
-        solve.time_collectives = False
         total_ms_max, coll_ms_max = env.max_over_ranks(sum(step_ms), coll_ms or 0.0)
         # e2e: pinned host inputs -> device -> sharded solve -> own row slab back to the host.  A rank moves only the rows of
         # src / dst its shard reads (own interior rows + the one-row halo of the stencil).
@@ -660,7 +676,7 @@ def sharded_leg(env, args, steps=None):
     line = None
     if env.rank == 0:
         if solve.tri:
-            par = f"rows sharded x{env.world} along the segments of the partitioned tridiagonal solve; 2 small all-reduces (NCCL), no transpose"
+            par = f"rows sharded x{env.world} along the segments of the partitioned tridiagonal solve; ONE packed integer all-reduce (NCCL) of disjoint supports, no transpose"
             xbytes = solve.exchange_bytes
         else:
             par = f"rows/cols sharded x{env.world}, 2 all-to-all (NCCL grouped send/recv)"
@@ -671,7 +687,8 @@ def sharded_leg(env, args, steps=None):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS["cfg4"], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
                        "l2": "256 MiB flush write between timed steps", "parallelism": par,
-                       "bytes_exchanged_per_rank_per_step": int(xbytes), "sharded_equals_single_gpu": True},
+                       "bytes_exchanged_per_rank_per_step": int(xbytes), "sharded_equals_single_gpu": True,
+                       "cuda_graph": bool(use_graph)},
             "collective_ms": coll_ms_max if env.world > 1 else 0.0,
             "clocks": sampler.summary(),
             "e2e": {"value": px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int((s1 - s0) * src.shape[1] * 3 + (t1_ - t0_) * dst.shape[1] * 3), "d2h_bytes_per_step": int(h_rows.numel()),
@@ -694,6 +711,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay the device-resident step as a CUDA graph (default for cfg5)")
     ap.add_argument("--cpu-baseline-calls", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-graph", action="store_true", help="cfg4, N > 1: plain launches instead of one CUDA graph per sharded solve")
     ap.add_argument("--sharded-fft", action="store_true", help="cfg4, N > 1: the FFT engine's transpose scheme (two all-to-alls) instead of the tridiagonal engine's segment scheme")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

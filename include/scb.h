@@ -200,6 +200,11 @@ int scb_plan_lowk(const scb_plan* plan, int* lowkx, int* lowky);
 int scb_plan_tri_layout(const scb_plan* plan, int* seg_len, int* n_segs, size_t* ends32_floats, size_t* ends64_doubles, size_t* w_doubles);
 int scb_plan_tri_forward(scb_plan* plan, const scb_image* src, const scb_image* dst, int mem_kind, int seg0, int seg1, float* ends32_dev, double* ends64_dev, double* w_dev);
 int scb_plan_tri_finish(scb_plan* plan, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev, const double* w_dev);
+/* The same with the low-frequency projections left as `w_slots` consecutive per-rank partials ([w_slots][w_doubles], rank r's
+ * scb_plan_tri_forward writes slot r and the others stay zero): every buffer of the exchange then has DISJOINT supports across
+ * the ranks, so ends32 | ends64 | w can be packed and combined with ONE integer all-reduce (x + 0 is exact for any bit pattern). */
+int scb_plan_tri_finish_slots(scb_plan* plan, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev,
+                              const double* w_dev, int w_slots);
 
 /* ---- the reference's four entry points (seamlessclone_cuda.h:4-63), POD views instead of cv::Mat* ---- */
 void* my_seamlessclone_api_imp_create_instance(int gpu_id);

@@ -40,7 +40,7 @@ EXPORTS = [
     "scb_plan_create", "scb_plan_create_ex", "scb_plan_destroy", "scb_plan_geometry", "scb_plan_engine", "scb_plan_execute", "scb_plan_execute_timed", "scb_plan_execute_graph", "scb_plan_set_debug",
     "scb_plan_get_intermediate", "scb_seamless_clone", "scb_plan_cache_stats", "scb_clone_batch",
     "scb_plan_rows_forward", "scb_plan_cols", "scb_plan_lowfreq_finish", "scb_plan_rows_inverse", "scb_plan_lowk",
-    "scb_plan_tri_layout", "scb_plan_tri_forward", "scb_plan_tri_finish",
+    "scb_plan_tri_layout", "scb_plan_tri_forward", "scb_plan_tri_finish", "scb_plan_tri_finish_slots",
     "my_seamlessclone_api_imp_create_instance", "my_seamlessclone_api_imp_run",
     "my_seamlessclone_api_imp_destroy", "my_seamlessclone_api_imp_sync",
 ]
@@ -118,6 +118,7 @@ def load(path: str | None = None) -> C.CDLL:
         "scb_plan_tri_layout": (i, [vp, P(i), P(i), P(sz), P(sz), P(sz)]),
         "scb_plan_tri_forward": (i, [vp, P(ScbImage), P(ScbImage), i, i, i, vp, vp, vp]),
         "scb_plan_tri_finish": (i, [vp, P(ScbImage), i, i, i, vp, vp, vp]),
+        "scb_plan_tri_finish_slots": (i, [vp, P(ScbImage), i, i, i, vp, vp, vp, i]),
         "my_seamlessclone_api_imp_create_instance": (vp, [i]),
         "my_seamlessclone_api_imp_run": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i, i, i, i, P(ScbImage)]),
         "my_seamlessclone_api_imp_destroy": (None, [vp]),

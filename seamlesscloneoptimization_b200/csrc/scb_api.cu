@@ -109,7 +109,7 @@ struct Lane {
     uint64_t ws_epoch = 0;                    // bumps when the arena moves (captured graphs hold its addresses)
 };
 static const int kMaxLanes = 8;
-static const int kDefaultLanes = 4;  // SCB_LANES=1..8 overrides (tuning)
+static const int kDefaultLanes = 8;  // SCB_LANES=1..8 overrides (tuning; measured with 4 submit threads: profiles/r2_batch_submit_sweep.txt)
 
 struct DevTcTab {
     TcTabDev dev{};
@@ -1682,6 +1682,7 @@ static TriLowParams tri_low_params(scb_plan* p, const Frame& f, const float* A, 
     l.fx = f.fl;
     l.fy = f.fc;
     l.W = W;
+    l.w_slots = 1;
     l.Ct = Ct;
     l.y0 = y0;
     l.y1 = y1;
@@ -1760,7 +1761,9 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
 
 // ---- exact INT8 tensor-core passes along x (scb_i8.h): digit planes -> tcgen05.mma.kind::i8 -> class sums -> float ----
 // forward: G [3][ny][gp] -> A [3][ny][nx] (= -2 sum g sin, what rows_fwd produces) and the exact float64 row sums R [3][lowkx][ny]
-static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R) {
+// Rows [y0, y1) of the ROI interior = lines [3 y0, 3 y1) (channel-interleaved).  The tiles that straddle the ends of the range are
+// computed whole (their foreign lines hold whatever the digit planes hold) but only the lines of the range are stored.
+static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R, int y0, int y1) {
     NvtxRange nvtx_("scb:rows_fwd_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -1777,6 +1780,8 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     d.lscale = w.lscale;
     d.fixed_scale = p->grey_mask ? 65536.0f : 1.0f;  // binary mask: the right-hand side is integer valued (|g| <= 1530), two digits hold its fold exactly
     d.per_line = 0;
+    d.line0 = 3 * y0;
+    d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;  // the pad lines up to the last whole tile are written as zeros
     if (i8_launch_digitize((void*)p->lane->stream, d, da) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
     c->launches++;
     I8GemmParams m{};
@@ -1787,6 +1792,10 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     m.a = w.Adig;
     m.basis = p->i8x->basis;
     m.lscale = w.lscale;
+    m.mt0 = 3 * y0 / kI8M;
+    m.mt1 = (3 * y1 + kI8M - 1) / kI8M;
+    m.line0 = 3 * y0;
+    m.line1 = 3 * y1 < lines ? 3 * y1 : lines;
     const double unit = std::ldexp(1.0, 8 * (da - 1) - kI8BasisBits);
     m.scale = (float)(-2.0 * unit);  // OpenCV: Im of the odd-extension FFT = -2 sum x sin
     m.out = A;
@@ -1800,7 +1809,7 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     return SCB_OK;
 }
 // inverse: Ct [3][ny][nx] -> U [3][ny][nx] (= sum Ct sin / (nx+1))
-static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U) {
+static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1) {
     NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -1817,6 +1826,8 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     d.lscale = w.lscale;
     d.fixed_scale = 1.0f;
     d.per_line = 1;  // 30-bit fixed point relative to the line's largest magnitude
+    d.line0 = 3 * y0;
+    d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;
     if (i8_launch_digitize((void*)p->lane->stream, d, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
     c->launches++;
     I8GemmParams m{};
@@ -1827,6 +1838,10 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     m.a = w.Adig;
     m.basis = p->i8x->basis;
     m.lscale = w.lscale;
+    m.mt0 = 3 * y0 / kI8M;
+    m.mt1 = (3 * y1 + kI8M - 1) / kI8M;
+    m.line0 = 3 * y0;
+    m.line1 = 3 * y1 < lines ? 3 * y1 : lines;
     m.scale = (float)(std::ldexp(1.0, 8 * 3 - kI8BasisBits) / (double)(g.nx + 1));
     m.out = U;
     m.out_plane = (long long)g.ny * g.nx;
@@ -1834,7 +1849,7 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     m.R = nullptr;
     if (i8_launch_gemm((void*)p->lane->stream, m, 4, 3) != 0) return fail(c, SCB_ERR_CUDA, "i8_gemm_kernel (inverse) launch failed");
     c->launches++;
-    if (p->debug) cudaMemcpyAsync(p->dbg_u, U, (size_t)3 * g.nx * g.ny * sizeof(float), cudaMemcpyDeviceToDevice, p->lane->stream);
+    if (p->debug && y1 >= g.ny) cudaMemcpyAsync(p->dbg_u, U, (size_t)3 * g.nx * g.ny * sizeof(float), cudaMemcpyDeviceToDevice, p->lane->stream);
     return SCB_OK;
 }
 // compose rows [y0, y1): planar float solved field -> interleaved u8 (clamp, truncate)
@@ -2033,7 +2048,9 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     const Frame fr = frame_of(p, swap);
     const int nb_out = swap ? 1 : nb;
     int yb[kMaxBands + 1];
-    for (int b = 0; b <= nb; ++b) yb[b] = (b == nb) ? g.ny : (int)(((long long)g.ny * b / nb) & ~3LL);  // multiples of 4: whole quads
+    if (p->use_i8 && nb > g.ny / 128) nb = g.ny / 128 > 0 ? g.ny / 128 : 1;  // INT8 passes: bands of whole 128-row blocks (= 3 x 128-line tiles)
+    const long long bq = p->use_i8 ? 127LL : 3LL;
+    for (int b = 0; b <= nb; ++b) yb[b] = (b == nb) ? g.ny : (int)(((long long)g.ny * b / nb) & ~bq);  // multiples of 4: whole quads
     // Small jobs of a batch keep everything on the lane's own stream: the other lanes already fill the GPU, and the event
     // forks / joins of the side stream cost more host time than such a job's kernels take (the batch path is host-bound).
     const bool serial = tm.on || (defer_host && !p->use_tc && (size_t)g.nx * g.ny < ((size_t)1 << 18));
@@ -2078,7 +2095,13 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         for (int b = 0; b < nb; ++b) {
             SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
             run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1], swap);
-            if (b + 1 < nb && !swap && !p->use_i8) run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);  // the last band's rows follow the refinement fork
+            if (b + 1 < nb && !swap) {  // the last band's rows follow the refinement fork
+                if (p->use_i8) {
+                    if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, yb[b], yb[b + 1]))) return rc;
+                } else {
+                    run_rows_fwd(p, st, w.G, w.gp, w.At, yb[b], yb[b + 1], p->use_tri);
+                }
+            }
         }
     }
     tm.mark(ST_RHS);
@@ -2105,7 +2128,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
         if (p->use_i8) {
-            if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R))) return rc;
+            if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, yb[nb - 1], g.ny))) return rc;
         } else {
             run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
         }
@@ -2117,18 +2140,21 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
-        if (p->use_i8 && (rc = run_i8_inverse(p, w, w.Ct, w.At))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
         if (nb_out == 1) {
-            if (p->use_i8)
+            if (p->use_i8) {
+                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
                 run_compose(p, w.At, out, out_pitch, 0, g.ny);
-            else
+            } else {
                 run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
+            }
         } else {
             for (int b = 0; b < nb; ++b) {
-                if (p->use_i8)
+                if (p->use_i8) {
+                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1]))) return rc;
                     run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
-                else
+                } else {
                     run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
+                }
                 SCB_CUDA(c, cudaEventRecord(L->ev_out[b], ms));
                 SCB_CUDA(c, cudaStreamWaitEvent(L->copy, L->ev_out[b], 0));
                 SCB_CUDA(c, cudaMemcpy2DAsync(bInt + (size_t)yb[b] * blend->stride, (size_t)blend->stride, w.stO + (size_t)yb[b] * w.pO, (size_t)w.pO, (size_t)3 * g.nx,
@@ -2456,19 +2482,42 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
 #endif
         const int base = ch.base, m = ch.m;
         double b0 = now();
-        for (int i = 0; i < m; ++i) {
-            copy_ok[i] = 0;
-            geoms[i] = scb_geometry();
-            if (!ch.plans[i] || !ch.planned[i]) continue;
-            scb_job& j = jobs[base + i];
-            StageTimer tm;
-            geoms[i] = ch.plans[i]->g;
-            const int st = execute_impl(ch.plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host=*/true);
-            scb_plan_destroy(ch.plans[i]);  // stream-ordered frees: the queued kernels finish first
-            ch.plans[i] = nullptr;
-            copy_ok[i] = (st == SCB_OK);
-            note(j, st);
+        // The lanes are fed from several host threads: a job costs ~25 CUDA calls of ~3 us each on one thread, more than its kernels
+        // take on the GPU.  Thread t owns the lanes l with l % T == t, so the jobs of a lane stay in order.  (SCB_SUBMIT_THREADS)
+        auto submit = [&](int t, int T) {
+            if (T > 1 && cudaSetDevice(c->device) != cudaSuccess) return;
+            for (int i = 0; i < m; ++i) {
+                if (((base + i) % L) % T != t) continue;
+                copy_ok[i] = 0;
+                geoms[i] = scb_geometry();
+                if (!ch.plans[i] || !ch.planned[i]) continue;
+                scb_job& j = jobs[base + i];
+                StageTimer tm;
+                geoms[i] = ch.plans[i]->g;
+                const int st = execute_impl(ch.plans[i], &j.src, &j.dst, &j.blend, mem_kind, SCB_EXEC_DEFAULT, tm, /*defer_host=*/true);
+                scb_plan_destroy(ch.plans[i]);  // stream-ordered frees: the queued kernels finish first
+                ch.plans[i] = nullptr;
+                copy_ok[i] = (st == SCB_OK);
+                note(j, st);
+            }
+        };
+#ifdef SCB_EMU
+        submit(0, 1);  // the interpreter runs kernels on the calling thread
+#else
+        {
+            static const int want = [] {
+                const char* e = std::getenv("SCB_SUBMIT_THREADS");
+                return e ? std::atoi(e) : 4;
+            }();
+            int T = want < 1 ? 1 : want;
+            if (T > L) T = L;
+            if (T > host_threads()) T = host_threads();
+            if (T <= 1)
+                submit(0, 1);
+            else
+                pool_of(c).run(T, [&](int t) { submit(t, T); });
         }
+#endif
         if (mem_kind == SCB_MEM_HOST) {  // blend = dst outside each ROI interior: a parallel-for over the chunk's jobs
             const int T = host_threads();
             pool_of(c).run(T, [&](int t) {
@@ -2612,8 +2661,12 @@ extern "C" int scb_plan_tri_forward(scb_plan* p, const scb_image* src, const scb
     SCB_CUDA(c, cudaMemsetAsync(ends64_dev, 0, n64 * sizeof(double), ms));
     SCB_CUDA(c, cudaMemsetAsync(w_dev, 0, nw * sizeof(double), ms));
     run_rhs(p, st, w.G, w.gp, y0, y1);
-    run_lowfreq_rows(p, st, w.G, w.gp, w.R, y0, y1, ms);
-    run_rows_fwd(p, st, w.G, w.gp, w.At, y0, y1, /*natural=*/true);
+    if (p->use_i8) {  // the INT8 pass delivers the exact low-frequency row sums itself
+        if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, y0, y1))) return rc;
+    } else {
+        run_lowfreq_rows(p, st, w.G, w.gp, w.R, y0, y1, ms);
+        run_rows_fwd(p, st, w.G, w.gp, w.At, y0, y1, /*natural=*/true);
+    }
     const Frame f = frame_of(p, false);
     launch_tri_low(p, false, tri_low_params(p, f, w.At, w.Ct, w.R, w.Y64, w_dev, y0, y1), ms);
     TriSolveParams t = tri_solve_params(p, f, w.At, w.Ct, w.Y64);
@@ -2628,7 +2681,12 @@ extern "C" int scb_plan_tri_forward(scb_plan* p, const scb_image* src, const scb
 }
 
 extern "C" int scb_plan_tri_finish(scb_plan* p, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev, const double* w_dev) {
-    if (!p || !ends32_dev || !ends64_dev || !w_dev) return SCB_ERR_INVALID_ARGUMENT;
+    return scb_plan_tri_finish_slots(p, blend, mem_kind, seg0, seg1, ends32_dev, ends64_dev, w_dev, 1);
+}
+
+extern "C" int scb_plan_tri_finish_slots(scb_plan* p, scb_image* blend, int mem_kind, int seg0, int seg1, const float* ends32_dev, const double* ends64_dev,
+                                         const double* w_dev, int w_slots) {
+    if (!p || !ends32_dev || !ends64_dev || !w_dev || w_slots < 1) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     if (mem_kind != SCB_MEM_DEVICE) return fail(c, SCB_ERR_UNSUPPORTED, "sharded solve: images must be device resident");
     int rc, y0, y1;
@@ -2646,9 +2704,16 @@ extern "C" int scb_plan_tri_finish(scb_plan* p, scb_image* blend, int mem_kind, 
     t.ends32 = const_cast<float*>(ends32_dev);
     t.ends64 = const_cast<double*>(ends64_dev);
     if (seg1 > seg0) launch_tri_solve(p, t);
-    launch_tri_low(p, true, tri_low_params(p, f, w.At, w.Ct, w.R, w.Y64, const_cast<double*>(w_dev), y0, y1), p->lane->stream);
+    TriLowParams la = tri_low_params(p, f, w.At, w.Ct, w.R, w.Y64, const_cast<double*>(w_dev), y0, y1);
+    la.w_slots = w_slots;
+    launch_tri_low(p, true, la, p->lane->stream);
     unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
-    run_rows_inv(p, w.Ct, bInt, blend->stride, y0, y1);
+    if (p->use_i8) {
+        if ((rc = run_i8_inverse(p, w, w.Ct, w.At, y0, y1))) return rc;
+        run_compose(p, w.At, bInt, blend->stride, y0, y1);
+    } else {
+        run_rows_inv(p, w.Ct, bInt, blend->stride, y0, y1);
+    }
     SCB_CUDA(c, cudaGetLastError());
     return SCB_OK;
 }

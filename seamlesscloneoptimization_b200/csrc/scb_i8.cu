@@ -90,12 +90,12 @@ template <int DA>
 __global__ void __launch_bounds__(kI8DigThreads) i8_digitize_kernel(I8DigitizeParams p) {
     __shared__ float red[kI8DigThreads / 32];
     const int t = threadIdx.x;
-    const int line = blockIdx.x;
+    const int line = p.line0 + blockIdx.x;
     const int n = p.g.n, h = n >> 1;
     const bool real = line < p.lines;
     const float* x = nullptr;
     if (real) {
-        const int c = line / p.lpc, r = line - c * p.lpc;
+        const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
         x = p.in + (size_t)c * p.in_plane + (size_t)r * p.in_pitch;
     }
     // The line is read ONCE: thread t keeps the elements j0 .. j0+3 and their mirror images for its first chunk (lines up to
@@ -223,8 +223,8 @@ SCB_HD int i8_plane_count(int i, int db) {
 
 // epilogue of one output element, shared by the tensor-core kernel and the emulator kernel
 SCB_D void i8_store(const I8GemmParams& p, int line, int par, int ki, int w0, int w1, int w2, int w3, float ls) {
-    if (line >= p.lines || ki >= p.g.nout[par]) return;
-    const int c = line / p.lpc, r = line - c * p.lpc;
+    if (line < p.line0 || line >= p.line1 || ki >= p.g.nout[par]) return;
+    const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
     const int k0 = 2 * ki + par;
     p.out[(size_t)c * p.out_plane + (size_t)r * p.out_pitch + k0] = i8_combine(w0, w1, w2, w3) * (p.scale * ls);
     if (p.R && k0 < p.lowk) p.R[((size_t)c * p.lowk + k0) * p.lpc + r] = i8_combine_exact(w0, w1, w2, w3) * (p.rscale * (double)ls);
@@ -238,7 +238,7 @@ SCB_D void i8_store(const I8GemmParams& p, int line, int par, int ki, int w0, in
 // ---------------------------------------------------------------------------------------------
 template <int DA, int DB>
 __global__ void i8_gemm_kernel(I8GemmParams p) {
-    const int line = blockIdx.x * kI8M + threadIdx.x;
+    const int line = (p.mt0 + blockIdx.x) * kI8M + threadIdx.x;
     if (line >= p.lines) return;
     const int par = blockIdx.y / p.g.nsb, sb = blockIdx.y % p.g.nsb;
     const float ls = p.lscale[line];
@@ -263,7 +263,8 @@ __global__ void i8_gemm_kernel(I8GemmParams p) {
 template <int DA, int DB>
 static int i8_launch_gemm_t(void* stream, const I8GemmParams& p) {
     (void)stream;
-    SCB_LAUNCH((i8_gemm_kernel<DA, DB>), dim3((p.lines + kI8M - 1) / kI8M, 2 * p.g.nsb), dim3(kI8M), 0, stream, p);
+    if (p.mt1 <= p.mt0) return 0;
+    SCB_LAUNCH((i8_gemm_kernel<DA, DB>), dim3(p.mt1 - p.mt0, 2 * p.g.nsb), dim3(kI8M), 0, stream, p);
     return 0;
 }
 int i8_configure() { return 0; }
@@ -410,7 +411,7 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const int par = blockIdx.y / groups, sb0 = (blockIdx.y % groups) * NSUB;
     const int kpar = p.g.kpar[par];
     const int num_kb = (kpar + KB - 1) / KB;
-    const int m0 = blockIdx.x * kI8M;
+    const int m0 = (p.mt0 + (int)blockIdx.x) * kI8M;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
@@ -532,8 +533,8 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             i8_tmem_wait_ld();
             SCB_UNROLL
             for (int i = 0; i < 16; ++i) tile[(size_t)lane * OP + col + i] = i8_combine(w0[i], w1[i], w2[i], w3[i]) * sc;
-            if (p.R && col == 0 && sb0 == 0 && line < p.lines) {  // exact float64 row sums of the lowest frequencies
-                const int c = line / p.lpc, r = line - c * p.lpc;
+            if (p.R && col == 0 && sb0 == 0 && line >= p.line0 && line < p.line1) {  // exact float64 row sums of the lowest frequencies
+                const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
                 SCB_UNROLL
                 for (int i = 0; i < (kI8LowK + 1) / 2; ++i) {
                     const int k0 = 2 * i + par;
@@ -546,18 +547,18 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         // parity's CTA fills the gaps)
         {
             int ln = m0 + 32 * q;
-            int c = ln / p.lpc, rr = ln - c * p.lpc;
-            for (int r = 0; r < 32 && ln < p.lines; ++r, ++ln) {
+            int rr = ln / 3, c = ln - 3 * rr;
+            for (int r = 0; r < 32 && ln < p.line1; ++r, ++ln) {
                 float* o = p.out + (size_t)c * p.out_plane + (size_t)rr * p.out_pitch;
                 const float* trow = tile + (size_t)r * OP + col0;
                 SCB_UNROLL
                 for (int j = lane; j < COLS; j += 32) {
                     const int ki = sb0 * kI8P + col0 + j;
-                    if (ki < nout) o[2 * ki + par] = trow[j];
+                    if (ki < nout && ln >= p.line0) o[2 * ki + par] = trow[j];
                 }
-                if (++rr == p.lpc) {
-                    rr = 0;
-                    ++c;
+                if (++c == 3) {
+                    c = 0;
+                    ++rr;
                 }
             }
         }
@@ -615,7 +616,7 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * S + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = (p.lines + kI8M - 1) / kI8M;                 // line tiles
+    const int mt = p.mt1 - p.mt0;                               // line tiles of this launch
     const int mtu = (mt + CL - 1) / CL;                         // scheduling units per group (pairs of line tiles when CL = 2)
     const int nsbr0 = (p.g.nout[0] + kI8P - 1) / kI8P, nsbr1 = (p.g.nout[1] + kI8P - 1) / kI8P;
     const int units = (nsbr0 + nsbr1) * mtu;
@@ -652,7 +653,7 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
         const int g = unit / mtu, mu = unit - g * mtu;
         par = g >= nsbr0 ? 1 : 0;
         sb = par ? g - nsbr0 : g;
-        m0 = (mu * CL + (int)cta_rank) * kI8M;
+        m0 = (p.mt0 + mu * CL + (int)cta_rank) * kI8M;
     };
 
     if (warp == 0) {
@@ -758,8 +759,8 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 i8_tmem_wait_ld();
                 SCB_UNROLL
                 for (int i = 0; i < 16; ++i) tile[(size_t)lane * OP + col + i] = i8_combine(w0[i], w1[i], w2[i], w3[i]) * sc;
-                if (p.R && col == 0 && sb == 0 && line < p.lines) {
-                    const int c = line / p.lpc, r = line - c * p.lpc;
+                if (p.R && col == 0 && sb == 0 && line >= p.line0 && line < p.line1) {
+                    const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
                     SCB_UNROLL
                     for (int i = 0; i < (kI8LowK + 1) / 2; ++i) {
                         const int k0 = 2 * i + par;
@@ -773,13 +774,13 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty(b)) : "memory");
             {
                 int ln = m0 + 32 * q;
-                int c = ln / p.lpc, rr = ln - c * p.lpc;
+                int rr = ln / 3, c = ln - 3 * rr;
                 const int ki = sb * kI8P + col0 + lane;
-                for (int r = 0; r < 32 && ln < p.lines; ++r, ++ln) {
-                    if (ki < nout) p.out[(size_t)c * p.out_plane + (size_t)rr * p.out_pitch + 2 * ki + par] = tile[(size_t)r * OP + col0 + lane];
-                    if (++rr == p.lpc) {
-                        rr = 0;
-                        ++c;
+                for (int r = 0; r < 32 && ln < p.line1; ++r, ++ln) {
+                    if (ki < nout && ln >= p.line0) p.out[(size_t)c * p.out_plane + (size_t)rr * p.out_pitch + 2 * ki + par] = tile[(size_t)r * OP + col0 + lane];
+                    if (++c == 3) {
+                        c = 0;
+                        ++rr;
                     }
                 }
             }
@@ -830,7 +831,8 @@ static int i8_launch_gemm_t5(void* stream, const I8GemmParams& p) {
     int rc;
     if ((rc = i8_make_map(&amap, p.a, (size_t)2 * DA * p.m_rows, p.g.kpad, kI8M, KB))) return rc;
     if ((rc = i8_make_map(&bmap, p.basis, i8_basis_rows(p.g), p.g.kpad, DB * kI8P / CL, KB))) return rc;  // CL = 2: each CTA loads half the rows
-    const int mt = (p.lines + kI8M - 1) / kI8M;
+    const int mt = p.mt1 - p.mt0;
+    if (mt <= 0) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mt + CL - 1) / CL * CL, 2 * (p.g.nsb / NSUB));
     cfg.blockDim = dim3(kI8Threads);
@@ -877,7 +879,8 @@ static int i8_launch_gemm_p(void* stream, const I8GemmParams& p) {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }();
-    const int mt = (p.lines + kI8M - 1) / kI8M;
+    const int mt = p.mt1 - p.mt0;
+    if (mt <= 0) return 0;
     const int units = ((p.g.nout[0] + kI8P - 1) / kI8P + (p.g.nout[1] + kI8P - 1) / kI8P) * ((mt + CL - 1) / CL);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kI8Threads);
@@ -988,7 +991,8 @@ int i8_launch_compose(void* stream, const I8ComposeParams& p, int rows) {
 }
 
 int i8_launch_digitize(void* stream, const I8DigitizeParams& p, int da) {
-    const dim3 grid(p.m_rows), block(kI8DigThreads);
+    if (p.line1 <= p.line0) return 0;
+    const dim3 grid(p.line1 - p.line0), block(kI8DigThreads);
     if (da == 2)
         SCB_LAUNCH(i8_digitize_kernel<2>, grid, block, 0, (cudaStream_t)stream, p);
     else

@@ -80,8 +80,9 @@ struct I8DigitizeParams {
     long long in_plane;
     int in_pitch;
     int lpc;                // lines per channel
-    int lines;              // 3 * lpc
+    int lines;              // 3 * lpc; line = 3 * row + channel (channel-interleaved, so a band of image rows is a contiguous line range)
     int m_rows;             // i8_m_rows(lines)
+    int line0, line1;       // lines of this launch (HOST calls digitise band by band); [lines, m_rows) are written as zeros
     signed char* a;         // digit planes
     float* lscale;          // [m_rows] per-line scale the epilogue multiplies by
     float fixed_scale;      // per_line == 0: x is multiplied by this before rounding (1: integer input, 65536: 16 fractional bits)
@@ -91,6 +92,8 @@ struct I8DigitizeParams {
 struct I8GemmParams {
     I8Geom g;
     int lines, lpc, m_rows;
+    int mt0, mt1;              // 128-line tiles of this launch
+    int line0, line1;          // only lines in [line0, line1) are stored (a row shard's first / last tile straddles its neighbours' lines)
     const signed char* a;      // digit planes of the lines          (emulator build reads them directly; the GPU kernel goes through TMA)
     const signed char* basis;  // digit planes of the basis
     const float* lscale;       // [m_rows]

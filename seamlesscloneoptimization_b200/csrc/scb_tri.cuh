@@ -303,6 +303,8 @@ struct TriLowParams {
     const float* fx;       // OpenCV filter_X (nx)
     const float* fy;       // OpenCV filter_Y (ny)
     double* W;             // [3][kTriLowL][kTriLowK], zeroed before tri_lowproj_kernel
+    int w_slots;           // tri_lowapply_kernel: W is the SUM of this many consecutive [3][kTriLowL][kTriLowK] blocks (row-sharded solves: one
+                           // partial per rank, exchanged with a single integer all-reduce of disjoint slots); 0 or 1 = just W
     float* Ct;             // [3][ny][nx]
     int y0, y1;            // rows of this launch (row-sharded solves: the own rows; W then holds a partial sum)
 };
@@ -368,7 +370,12 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowP
     const int L = n < kTriLowL ? n : kTriLowL;
     double w[kTriLowL];
     SCB_UNROLL
-    for (int l = 0; l < kTriLowL; ++l) w[l] = (l < L) ? p.W[((size_t)c * kTriLowL + l) * kTriLowK + k] : 0.0;
+    for (int l = 0; l < kTriLowL; ++l) {
+        double sum = 0.0;
+        if (l < L)
+            for (int sl = 0; sl < (p.w_slots > 1 ? p.w_slots : 1); ++sl) sum += p.W[(size_t)sl * 3 * kTriLowL * kTriLowK + ((size_t)c * kTriLowL + l) * kTriLowK + k];
+        w[l] = sum;
+    }
     const int yb = p.y0 + blockIdx.x * kTriLowRows;
     for (int y = yb + warp; y < yb + kTriLowRows && y < p.y1; y += kTriLowWarps) {
         double sum = p.Y64[((size_t)c * n + y) * kTriLowK + k];

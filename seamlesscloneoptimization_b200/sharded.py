@@ -65,7 +65,7 @@ class ShardedSolve:
             raise capi.ScbError(capi.SCB_ERR_INVALID_ARGUMENT, "sharded solve: empty plan")
         self.nx, self.ny = int(g.nx), int(g.ny)
         self.ys, self.xs = split(self.ny, self.world), split(self.nx, self.world)
-        self.tri = plan.engine == capi.ENGINE_TRI
+        self.tri = plan.engine in (capi.ENGINE_TRI, capi.ENGINE_I8)
         if self.tri:
             seg_len, n_segs = C.c_int(), C.c_int()
             n32, n64, nw = C.c_size_t(), C.c_size_t(), C.c_size_t()
@@ -73,10 +73,17 @@ class ShardedSolve:
             self.seg_len, self.n_segs = seg_len.value, n_segs.value
             self.segs = split(self.n_segs, self.world)  # rank r owns segments [segs[r], segs[r+1])
             self.ys = [min(self.ny, s * self.seg_len) for s in self.segs]
-            self.ends32 = torch.zeros(n32.value, dtype=torch.float32, device=device)
-            self.f64 = torch.zeros(n64.value + nw.value, dtype=torch.float64, device=device)  # ends64 | w: one all-reduce
-            self.n64 = n64.value
-            self.exchange_bytes = 4 * n32.value + 8 * (n64.value + nw.value)
+            # ONE exchange buffer: ends32 | ends64 | one W slot per rank.  Every rank fills only its own segments and its own W
+            # slot, the rest is zero, so the supports are disjoint and a single integer all-reduce(SUM) combines them exactly
+            # (x + 0 == x for any bit pattern; the W partials are summed by the kernel that consumes them).
+            self.n32, self.n64, self.nw = n32.value, n64.value, nw.value
+            n32p = (self.n32 + 1) // 2 * 2  # keep the float64 part 8-byte aligned
+            self.pack = torch.zeros((4 * n32p + 8 * (self.n64 + self.nw * self.world)) // 8, dtype=torch.int64, device=device)
+            self._e32 = self.pack.data_ptr()
+            self._e64 = self._e32 + 4 * n32p
+            self._w0 = self._e64 + 8 * self.n64
+            self.exchange_bytes = self.pack.numel() * 8
+            self.graph = None
             return
         lkx, lky = C.c_int(), C.c_int()
         ctx._check(ctx.lib.scb_plan_lowk(plan.handle, C.byref(lkx), C.byref(lky)))
@@ -164,14 +171,14 @@ class ShardedSolve:
         chk = self.ctx._check
         if self.tri:
             s0, s1 = self.segs[r], self.segs[r + 1]
-            e32, e64, wd = self.ends32.data_ptr(), self.f64.data_ptr(), self.f64.data_ptr() + 8 * self.n64
-            chk(lib.scb_plan_tri_forward(ph, C.byref(src_view), C.byref(dst_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
-            if self.world > 1:  # every rank filled only its own segments / summed only its own rows: zeros elsewhere
+            if self.world > 1:
+                self.pack.zero_()  # the other ranks' parts of the previous solve
+            chk(lib.scb_plan_tri_forward(ph, C.byref(src_view), C.byref(dst_view), capi.MEM_DEVICE, s0, s1, self._e32, self._e64, self._w0 + 8 * self.nw * r))
+            if self.world > 1:
                 ev = self._mark()
-                dist.all_reduce(self.ends32, group=self.group)
-                dist.all_reduce(self.f64, group=self.group)
+                dist.all_reduce(self.pack, group=self.group)
                 self._mark(ev)
-            chk(lib.scb_plan_tri_finish(ph, C.byref(blend_view), capi.MEM_DEVICE, s0, s1, e32, e64, wd))
+            chk(lib.scb_plan_tri_finish_slots(ph, C.byref(blend_view), capi.MEM_DEVICE, s0, s1, self._e32, self._e64, self._w0, self.world))
             return
         y0, y1, x0, x1 = self.ys[r], self.ys[r + 1], self.xs[r], self.xs[r + 1]
         self.lowrows.zero_()
@@ -181,6 +188,21 @@ class ShardedSolve:
         chk(lib.scb_plan_cols(ph, x0, x1, self.At.data_ptr(), self.Ct.data_ptr(), self.lowspec.data_ptr()))
         self.exchange_cols_to_rows()
         chk(lib.scb_plan_rows_inverse(ph, self.Ct.data_ptr(), C.byref(blend_view), capi.MEM_DEVICE, y0, y1))
+
+    def capture(self, src_view, dst_view, blend_view) -> None:
+        """Captures one whole sharded solve -- the C-ABI passes AND the NCCL exchange between them -- into a CUDA graph on the
+        context's stream; run_graph() then replays it with a single launch and no host round trip per phase.  Call after at least
+        one plain run() (workspace growth, NCCL connection set-up and table builds cannot be captured)."""
+        if self._stream is None:
+            raise capi.ScbError(capi.SCB_ERR_UNSUPPORTED, "CUDA graphs need a CUDA device")
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self._stream):
+            self._run(src_view, dst_view, blend_view)
+        self.graph = g
+
+    def run_graph(self) -> None:
+        self.graph.replay()
 
     def gather_rows(self, blend: torch.Tensor) -> None:
         """Make every rank's `blend` (H,W,3 u8 tensor) complete: all-gather the solved interior row slabs."""

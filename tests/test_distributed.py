@@ -48,7 +48,7 @@ def _worker(rank, world, port, lib_path, out_dir, engine):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("engine", [capi.ENGINE_TRI, capi.ENGINE_FFT], ids=["tri-segments", "fft-transpose"])
+@pytest.mark.parametrize("engine", [capi.ENGINE_I8, capi.ENGINE_TRI, capi.ENGINE_FFT], ids=["i8-segments", "tri-segments", "fft-transpose"])
 def test_sharded_solve_over_gloo(tmp_path, emu_lib, world, engine):
     """tri: row shards = segment groups of the partitioned Thomas solve, two small all-reduces;  fft: two all-to-all transposes."""
     port = _free_port()

@@ -631,6 +631,31 @@ def test_banded_host_transfers_equal_single_shot(be, ctx, monkeypatch):
     plan.close()
 
 
+def test_banded_host_transfers_int8_engine(be, monkeypatch):
+    """The INT8 passes run band by band too (bands of whole 128-row blocks = 3 x 128-line tiles of the channel-interleaved line
+    order): a tall thin ROI, two and three bands against the single-shot call."""
+    w, h = 40, 420
+    rng = np.random.default_rng(5)
+    src = so.smooth_rand(rng, h + 2, w + 2, 2.0)
+    dst = so.smooth_rand(rng, h + 9, w + 11, 2.0)
+    mask = np.full((h + 2, w + 2), 255, np.uint8)
+    p = (5 + w // 2 + 1, 3 + h // 2 + 1)
+    ctx = be.context()
+    try:
+        ctx.set_engine(capi.ENGINE_I8)
+        plan = ctx.plan(mask, src.shape[:2], dst.shape[:2], p)
+        assert plan.engine == capi.ENGINE_I8
+        monkeypatch.setenv("SCB_BANDS", "1")
+        ref = plan.execute(src, dst)
+        for nb in (2, 3):
+            monkeypatch.setenv("SCB_BANDS", str(nb))
+            assert np.array_equal(plan.execute(src, dst), ref), nb
+        assert_matches(ref, cv_blend(src, dst, mask, p), plan.geometry, "tall thin ROI", floor_blend=so.restate(src, dst, mask, p, transform="f64").blend)
+        plan.close()
+    finally:
+        ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # tridiagonal engine: both orientations (FFT passes along x or along y) give the same image
 @pytest.mark.parametrize("w,h", [(10, 18), (44, 45), (131, 20), (20, 259), (66, 140)])

@@ -54,6 +54,16 @@ def main():
         solve.gather_rows(blend)
         torch.cuda.synchronize()
         same = bool(torch.equal(blend, single))
+        if args.engine == "tri":  # the same solve replayed as ONE CUDA graph (passes + NCCL exchange captured together)
+            blend2 = d_dst.clone()
+            vb2 = capi.tensor_view(blend2)
+            torch.cuda.synchronize()
+            solve.capture(vs, vd, vb2)
+            solve.run_graph()
+            solve.run_graph()
+            solve.gather_rows(blend2)
+            torch.cuda.synchronize()
+            same = same and bool(torch.equal(blend2, single))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         e0.record(stream)
