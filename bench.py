@@ -197,6 +197,24 @@ def cpu_pool_throughput(jobs, ncores: int):
         return {"value": None, "unavailable": str(e)}
 
 
+def parity_vs_cv2(src, dst, mask, p, roi, got_interior):
+    """The bytes this run produced against cv2.seamlessClone on the same inputs (the reference arithmetic itself, run on the host as part
+    of the CPU-baseline leg).  north_star: +-1 LSB and >= 99.9 % exact; cv2's own float32 cv::dft noise caps the attainable figure below
+    that at the larger shapes (the float64-solve floor is computed in tests/test_pipeline.py::test_full_size_vs_opencv)."""
+    try:
+        import cv2
+
+        rx, ry, w, h = roi
+        ref = cv2.seamlessClone(src, dst, mask.copy(), p, cv2.NORMAL_CLONE)[ry + 1 : ry + h - 1, rx + 1 : rx + w - 1]
+        d = np.abs(ref.astype(np.int16) - got_interior.astype(np.int16))
+        return {"against": f"cv2.seamlessClone {cv2.__version__}, same inputs", "pct_exact": 100.0 * float((d == 0).mean()), "max_abs_diff": int(d.max()),
+                "differing_bytes": int((d != 0).sum()), "solved_bytes": int(d.size),
+                "note": "attainable ceiling = what an exact float64 solve with OpenCV's float32 denominators reaches against cv2 (cfg1 99.93, cfg2 99.85, cfg5 99.98 %, "
+                        "seed 0; computed live in tests/test_pipeline.py::test_full_size_vs_opencv): cv2's own float32 cv::dft rounding flips truncated bytes"}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": str(e)}
+
+
 def roi_pixels(mask):
     ys, xs = np.nonzero(mask[1:-1, 1:-1])
     w, h = int(xs.max() - xs.min() + 1), int(ys.max() - ys.min() + 1)
@@ -278,7 +296,6 @@ class Env:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            os.environ.setdefault("NCCL_DEBUG", "INFO")  # NCCL's own log (stderr) says which transports / algorithms the communicator of the cfg4 leg uses
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.warmup = max(3, args.warmup)
@@ -346,14 +363,37 @@ def ncu_duration_ms(workload: str, kernel: str):
     return _profile_json("kernel_times.json").get(workload, {}).get(kernel)
 
 
-def roofline_objects(stages, px, workload):
+def measured_tensor_peak():
+    """Dense int8 tensor peak for the roofline of the INT8 contraction kernels.  MEASURED_PEAKS.json holds the measured bf16 cuBLAS rate
+    (burst); on B200 the dense int8 MMA rate is exactly twice the bf16 one (same data path, K = 32 instead of 16 per instruction), so the
+    int8 denominator is 2 x that measurement -- stated in peak_kind."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return 2.0 * float(json.load(f)["bf16_tflops"]), "2 x measured bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on B200"
+    except Exception:
+        return 2.0 * 1590.0, "2 x fallback bf16 (B200_PROFILING.md)"
+
+
+def i8_tensor_ops(g, inverse: bool):
+    """int8 multiply-adds x 2 that one INT8 pass issues on the tensor pipe: 3 ny lines, per parity kpar x nout folded products,
+    7 digit-plane products forward (2 digits of the integer right-hand side x 4 basis digits, classes 0..3 kept), 9 inverse (4 x 3)."""
+    n = int(g.nx)
+    kpar, nout = (n // 2 + (n & 1), n // 2), ((n + 1) // 2, n // 2)
+    return 2.0 * 3 * int(g.ny) * sum(k * o for k, o in zip(kpar, nout)) * (9 if inverse else 7)
+
+
+def roofline_objects(stages, px, workload, g=None):
     peak, peak_kind = measured_peak_gbs()
-    dom = max(("rows_fwd", "cols", "rows_inv"), key=lambda k: stages.get(k, 0.0))
+    i8 = "i8_gemm_inv" in stages
+    names = dict(KERNEL_NAMES)
+    if i8:
+        names.update({"rows_fwd": "i8_digitize_kernel<2> + i8_gemm_pkernel<2,4> (INT8 tensor-core DST)", "rows_inv": "i8_digitize_kernel<4> + i8_gemm_pkernel<4,3> + i8_compose_kernel",
+                      "cols": "tri_solve_kernel + tri_low*_kernel (tridiagonal solve along y)"})
 
     def obj(k):
         alg = ALG_BYTES[k] * px
         ach = alg / (stages[k] * 1e-3) / 1e9 if stages.get(k) else None
-        o = {"bound": "hbm", "kernel": KERNEL_NAMES[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+        o = {"bound": "hbm", "kernel": names[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
              "frac": (ach / peak) if ach else None, "algorithmic_bytes_per_launch": alg, "duration_ms": stages.get(k),
              "duration_source": "live CUDA-event pair around the stage on the library's stream (includes the launch gap: several microseconds on a ~10 us kernel)",
              "traffic": ncu_traffic(workload, k)}
@@ -363,6 +403,32 @@ def roofline_objects(stages, px, workload):
             o["frac_ncu"] = alg / (nd * 1e-3) / 1e9 / peak
         return o
 
+    def tensor_obj(k, inverse):
+        tpeak, tkind = measured_tensor_peak()
+        ops = i8_tensor_ops(g, inverse)
+        ach = ops / (stages[k] * 1e-3) / 1e12 if stages.get(k) else None
+        o = {"bound": "tensor", "kernel": "i8_gemm_pkernel<4,3> (inverse DST along x)" if inverse else "i8_gemm_pkernel<2,4> (forward DST along x)",
+             "achieved": ach, "peak": tpeak, "peak_kind": tkind, "unit": "TOP/s (int8)", "frac": (ach / tpeak) if ach else None,
+             "algorithmic_ops_per_launch": ops, "duration_ms": stages.get(k),
+             "duration_source": "live CUDA-event pair around the kernel on the library's stream",
+             "traffic": ncu_traffic(workload, k),
+             "hbm_view": {"algorithmic_bytes_per_launch": (15 if inverse else 24) * px,
+                          "achieved_GBps": (15 if inverse else 24) * px / (stages[k] * 1e-3) / 1e9 if stages.get(k) else None, "peak_GBps": peak}}
+        nd = ncu_duration_ms(workload, k)
+        if nd:
+            o["ncu_duration_ms"] = nd
+            o["frac_ncu"] = ops / (nd * 1e-3) / 1e12 / tpeak
+        return o
+
+    if i8:  # the dominant kernel is one of the two INT8 contractions: tensor-pipe bound, reported against the int8 tensor peak
+        dom = max(("i8_gemm_fwd", "i8_gemm_inv"), key=lambda k: stages.get(k, 0.0))
+        d = tensor_obj(dom, dom == "i8_gemm_inv")
+        d["other_pass"] = tensor_obj("i8_gemm_fwd" if dom == "i8_gemm_inv" else "i8_gemm_inv", dom != "i8_gemm_inv")
+        d["note"] = ("the DST along x is an exact integer contraction on the INT8 tensor cores (tcgen05.mma.kind::i8 over base-256 digit planes, "
+                     "DESIGN.md section 5); its operand stream (digit planes re-read per 64-output tile) keeps the tensor pipe ~45 % busy; "
+                     "the HBM/L2-bound kernels of the path are the stencil (roofline_stencil) and the tridiagonal column solve (roofline_column_solve)")
+        return d, obj("rhs"), obj("cols")
+    dom = max(("rows_fwd", "cols", "rows_inv"), key=lambda k: stages.get(k, 0.0))
     d = obj(dom)
     d["note"] = ("the FFT row passes are bound by the shared-memory and FMA pipes of the SM, not by HBM (DESIGN.md section 5); the HBM/L2-bound kernels "
                  "of the path are the stencil (roofline_stencil) and the tridiagonal column solve (roofline_column_solve)")
@@ -437,11 +503,12 @@ def single_job_leg(env, args, steps=None):
         e2e_ts.append(time.perf_counter() - t0)
     env.barrier()
     assert np.array_equal(h_blend.numpy(), d_blend.cpu().numpy()), "host and device paths disagree"
+    result_interior = h_blend.numpy()[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1].copy() if env.rank == 0 else None
 
     total_ms_max, e2e_ms_max = env.max_over_ranks(sum(step_ms), sum(e2e_ts) * 1e3)
     line = None
     if env.rank == 0:
-        roof, roof_st, roof_cols = roofline_objects(stages, px, args.workload)
+        roof, roof_st, roof_cols = roofline_objects(stages, px, args.workload, g)
         e2e_call = ("scb_plan_execute(HOST pinned frames, plan reused): ROI H2D + solve + ROI D2H + dst->blend host copy" if stream_plan is not None else
                     "scb_seamless_clone(HOST pinned buffers): mask prep + ROI H2D + solve + ROI D2H + dst->blend host copy")
         line = {
@@ -449,7 +516,9 @@ def single_job_leg(env, args, steps=None):
             "warmup": env.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "solved_pixels_per_step": px, "roi": [g.w, g.h], "fft_len": [1 << g.log2m_x, 1 << g.log2m_y],
-                       "l2": "256 MiB flush write between timed steps", "jobs_per_step_per_gpu": 1, "cuda_graph": bool(use_graph)},
+                       "l2": "256 MiB flush write between timed steps", "jobs_per_step_per_gpu": 1, "cuda_graph": bool(use_graph),
+                       "engine": {capi.ENGINE_I8: "i8: INT8 tensor-core DST along x + tridiagonal solve along y", capi.ENGINE_TRI: "tri: FFT along x + tridiagonal solve along y",
+                                  capi.ENGINE_FFT: "fft", capi.ENGINE_TC: "tc"}.get(plan.engine, str(plan.engine))},
             "clocks": sampler.summary(),
             "e2e": {"value": env.world * px * args.steps / (e2e_ms_max * 1e-3) / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int((0 if stream_plan is not None else mask.size) + 2 * 3 * g.w * g.h), "d2h_bytes_per_step": int(3 * g.nx * g.ny),
@@ -457,6 +526,7 @@ def single_job_leg(env, args, steps=None):
             "gpu_launches": int(launches),
             "p50_ms_device": statistics.median(step_ms), "p99_ms_device": percentile(step_ms, 0.99),
             "stages_ms": stages, "roofline": roof, "roofline_stencil": roof_st, "roofline_column_solve": roof_cols,
+            "_parity_inputs": (src, dst, mask, p, (int(g.rx), int(g.ry), int(g.w), int(g.h)), result_interior),
         }
     if stream_plan is not None:
         stream_plan.close()
@@ -695,6 +765,8 @@ def sharded_leg(env, args, steps=None):
                     "ms_per_step": e2e_ms_max / args.steps, "call": "pinned H2D of the shard's src+dst rows (rank 0's byte counts), ShardedSolve.run, own row slab D2H"},
             "gpu_launches": int(launches), "p50_ms_device": statistics.median(step_ms),
         }
+    solve.graph = None  # the captured NCCL kernels go before the communicator does
+    torch.cuda.synchronize()
     plan.close()
     ctx.close()
     return line
@@ -754,13 +826,17 @@ def main():
                     sh[name].update(jobs=full["config"]["jobs"], jobs_per_s=full["jobs_per_s"], e2e_jobs_per_s=full["e2e"]["jobs_per_s"], collective="none (jobs split by LPT)")
                 else:
                     sh[name].update(bytes_exchanged_per_rank_per_step=full["config"]["bytes_exchanged_per_rank_per_step"], collective_ms=full.get("collective_ms"),
-                                    parallelism=full["config"]["parallelism"], sharded_equals_single_gpu=full["config"]["sharded_equals_single_gpu"])
+                                    parallelism=full["config"]["parallelism"], sharded_equals_single_gpu=full["config"]["sharded_equals_single_gpu"],
+                                    cuda_graph=full["config"]["cuda_graph"], p50_ms_device=full["p50_ms_device"])
         if env.rank == 0 and line is not None:
             line["sharded"] = sh
     if env.rank == 0 and line is not None:
         line["library_stamp"] = library_stamp()
+        pin = line.pop("_parity_inputs", None)
         if env.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
+            if pin is not None and args.workload != "cfg4":
+                line["parity"] = parity_vs_cv2(*pin)
         print(json.dumps(line))
     env.close()
 

@@ -153,6 +153,10 @@ int scb_plan_execute(scb_plan* plan, const scb_image* src, const scb_image* dst,
  * stage_ms[7] = { input copies, RHS stencil, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
  * (The reference times its whole run() with one event pair: seamlessClone_imp.cu:281-349.) */
 int scb_plan_execute_timed(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms);
+/* The same, plus the kernels of the INT8 tensor-core passes on their own event pairs:
+ * i8_ms[5] = { digitise forward, GEMM forward, digitise inverse, GEMM inverse, compose } (zeros on another engine). */
+int scb_plan_execute_timed_i8(scb_plan* plan, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms,
+                              float* i8_ms);
 /* DEVICE-resident execute replayed as one CUDA graph launch (captured on first use; re-captured when a
  * pointer, stride or the workspace changes): the per-frame call of a fixed-mask stream (BASELINE cfg5).
  * Replaces the reference's ~47 launches and 2 host syncs per frame (seamlessClone_imp.cpp:2105-2135). */

@@ -37,7 +37,7 @@ INT_GRADIENT_X, INT_GRADIENT_Y, INT_RHS, INT_SPECTRUM, INT_SOLVED, INT_ERODED_MA
 EXPORTS = [
     "scb_create", "scb_destroy", "scb_sync", "scb_stream", "scb_last_error", "scb_status_string",
     "scb_kernel_launches", "scb_device_count", "scb_source_hash", "scb_set_engine", "scb_set_orientation", "scb_tc_selftest", "scb_host_alloc", "scb_host_free",
-    "scb_plan_create", "scb_plan_create_ex", "scb_plan_destroy", "scb_plan_geometry", "scb_plan_engine", "scb_plan_execute", "scb_plan_execute_timed", "scb_plan_execute_graph", "scb_plan_set_debug",
+    "scb_plan_create", "scb_plan_create_ex", "scb_plan_destroy", "scb_plan_geometry", "scb_plan_engine", "scb_plan_execute", "scb_plan_execute_timed", "scb_plan_execute_timed_i8", "scb_plan_execute_graph", "scb_plan_set_debug",
     "scb_plan_get_intermediate", "scb_seamless_clone", "scb_plan_cache_stats", "scb_clone_batch",
     "scb_plan_rows_forward", "scb_plan_cols", "scb_plan_lowfreq_finish", "scb_plan_rows_inverse", "scb_plan_lowk",
     "scb_plan_tri_layout", "scb_plan_tri_forward", "scb_plan_tri_finish", "scb_plan_tri_finish_slots",
@@ -104,6 +104,7 @@ def load(path: str | None = None) -> C.CDLL:
         "scb_plan_geometry": (i, [vp, P(ScbGeometry)]),
         "scb_plan_execute": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i, i]),
         "scb_plan_execute_timed": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i, i, P(C.c_float)]),
+        "scb_plan_execute_timed_i8": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i, i, P(C.c_float), P(C.c_float)]),
         "scb_plan_execute_graph": (i, [vp, P(ScbImage), P(ScbImage), P(ScbImage), i]),
         "scb_plan_set_debug": (i, [vp, i]),
         "scb_plan_get_intermediate": (i, [vp, i, vp, sz, P(sz)]),

@@ -164,6 +164,7 @@ class Plan:
         return blend
 
     STAGES = ("copy_in", "rhs", "lowfreq", "rows_fwd", "cols", "rows_inv", "copy_out")
+    I8_KERNELS = ("i8_digitize_fwd", "i8_gemm_fwd", "i8_digitize_inv", "i8_gemm_inv", "i8_compose")
 
     def execute_timed(self, src, dst, blend, mem_kind: int = MEM_HOST, flags: int = EXEC_DEFAULT) -> dict:
         """execute() with CUDA events between the stages; returns {stage: ms} (syncs the stream)."""
@@ -171,9 +172,12 @@ class Plan:
             vs, vd, vb = capi.host_view(_bgr(src, "src")), capi.host_view(_bgr(dst, "dst")), capi.host_view(blend)
         else:
             vs, vd, vb = (x if isinstance(x, capi.ScbImage) else capi.tensor_view(x) for x in (src, dst, blend))
-        ms = (C.c_float * 7)()
-        self.ctx._check(self.lib.scb_plan_execute_timed(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags, ms))
-        return dict(zip(self.STAGES, (float(v) for v in ms)))
+        ms, i8 = (C.c_float * 7)(), (C.c_float * 5)()
+        self.ctx._check(self.lib.scb_plan_execute_timed_i8(self.handle, C.byref(vs), C.byref(vd), C.byref(vb), mem_kind, flags, ms, i8))
+        out = dict(zip(self.STAGES, (float(v) for v in ms)))
+        if self.engine == capi.ENGINE_I8:  # the kernels of the INT8 passes on their own event pairs
+            out.update(zip(self.I8_KERNELS, (float(v) for v in i8)))
+        return out
 
     def set_debug(self, on: bool = True):
         self.ctx._check(self.lib.scb_plan_set_debug(self.handle, int(on)))

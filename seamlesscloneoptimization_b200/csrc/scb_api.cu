@@ -1759,11 +1759,24 @@ static void run_rows_inv(scb_plan* p, const float* Ct, unsigned char* out, long 
     launch_rows_inv(p->ctx, p->lane->stream, f.log2m, y1 - y0, r);
 }
 
+// stage boundaries recorded by scb_plan_execute_timed
+enum { ST_BEGIN = 0, ST_IN, ST_RHS, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_X_DIGF, ST_X_DIGI, ST_X_GEMMI, ST_COUNT };
+static const int kStages = ST_OUT;  // stage_ms has ST_OUT entries; the ST_X_* events split the INT8 passes into their kernels
+
+struct StageTimer {
+    cudaEvent_t ev[ST_COUNT];
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    void mark(int i) {
+        if (on) cudaEventRecord(ev[i], stream);
+    }
+};
+
 // ---- exact INT8 tensor-core passes along x (scb_i8.h): digit planes -> tcgen05.mma.kind::i8 -> class sums -> float ----
 // forward: G [3][ny][gp] -> A [3][ny][nx] (= -2 sum g sin, what rows_fwd produces) and the exact float64 row sums R [3][lowkx][ny]
 // Rows [y0, y1) of the ROI interior = lines [3 y0, 3 y1) (channel-interleaved).  The tiles that straddle the ends of the range are
 // computed whole (their foreign lines hold whatever the digit planes hold) but only the lines of the range are stored.
-static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R, int y0, int y1) {
+static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R, int y0, int y1, StageTimer* tm = nullptr) {
     NvtxRange nvtx_("scb:rows_fwd_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -1784,6 +1797,7 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;  // the pad lines up to the last whole tile are written as zeros
     if (i8_launch_digitize((void*)p->lane->stream, d, da) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
     c->launches++;
+    if (tm) tm->mark(ST_X_DIGF);
     I8GemmParams m{};
     m.g = p->i8x->g;
     m.lines = lines;
@@ -1809,7 +1823,7 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     return SCB_OK;
 }
 // inverse: Ct [3][ny][nx] -> U [3][ny][nx] (= sum Ct sin / (nx+1))
-static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1) {
+static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1, StageTimer* tm = nullptr) {
     NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -1830,6 +1844,7 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;
     if (i8_launch_digitize((void*)p->lane->stream, d, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
     c->launches++;
+    if (tm) tm->mark(ST_X_DIGI);
     I8GemmParams m{};
     m.g = p->i8x->g;
     m.lines = lines;
@@ -1849,6 +1864,7 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     m.R = nullptr;
     if (i8_launch_gemm((void*)p->lane->stream, m, 4, 3) != 0) return fail(c, SCB_ERR_CUDA, "i8_gemm_kernel (inverse) launch failed");
     c->launches++;
+    if (tm) tm->mark(ST_X_GEMMI);
     if (p->debug && y1 >= g.ny) cudaMemcpyAsync(p->dbg_u, U, (size_t)3 * g.nx * g.ny * sizeof(float), cudaMemcpyDeviceToDevice, p->lane->stream);
     return SCB_OK;
 }
@@ -1888,20 +1904,7 @@ static void launch_tc_pass(scb_plan* p, const DevTcTab* tab, const TcPassParams&
     p->ctx->launches++;
 }
 
-struct StageTimer;
 static int tc_solve(scb_plan* p, const Workspace& w, unsigned char* out, long long out_pitch, StageTimer& tm);
-
-// stage boundaries recorded by scb_plan_execute_timed
-enum { ST_BEGIN = 0, ST_IN, ST_RHS, ST_LOW, ST_ROWS_FWD, ST_COLS, ST_ROWS_INV, ST_OUT, ST_COUNT };
-
-struct StageTimer {
-    cudaEvent_t ev[ST_COUNT];
-    bool on = false;
-    cudaStream_t stream = nullptr;
-    void mark(int i) {
-        if (on) cudaEventRecord(ev[i], stream);
-    }
-};
 
 // defer_host: batch mode -- leave the trailing stream sync AND the host-side dst->blend copy to the caller
 static int tc_solve(scb_plan* p, const Workspace& w, unsigned char* out, long long out_pitch, StageTimer& tm) {
@@ -2128,7 +2131,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if ((rc = tc_solve(p, w, out, out_pitch, tm))) return rc;
     } else {
         if (p->use_i8) {
-            if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, yb[nb - 1], g.ny))) return rc;
+            if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, yb[nb - 1], g.ny, &tm))) return rc;
         } else {
             run_rows_fwd(p, st, w.G, gpl, w.At, swap ? 0 : yb[nb - 1], fr.cnt, p->use_tri, swap);
         }
@@ -2142,7 +2145,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if (nb_out == 1) {
             if (p->use_i8) {
-                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
+                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
                 run_compose(p, w.At, out, out_pitch, 0, g.ny);
             } else {
                 run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
@@ -2189,6 +2192,13 @@ extern "C" int scb_plan_execute(scb_plan* p, const scb_image* src, const scb_ima
 // Same as scb_plan_execute, with CUDA events between the stages on the context stream; returns after a
 // stream sync.  stage_ms[7] = { input copies, RHS stencil, low-frequency refinement, rows forward, columns, rows inverse, output copy }.
 extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms) {
+    return scb_plan_execute_timed_i8(p, src, dst, blend, mem_kind, exec_flags, stage_ms, nullptr);
+}
+
+// The same, plus the kernels of the INT8 passes on their own: i8_ms[5] = { digitise forward, GEMM forward, digitise inverse, GEMM inverse,
+// compose } (zeros for plans on another engine).  rows forward = i8_ms[0] + i8_ms[1], rows inverse = i8_ms[2] + i8_ms[3] + i8_ms[4].
+extern "C" int scb_plan_execute_timed_i8(scb_plan* p, const scb_image* src, const scb_image* dst, scb_image* blend, int mem_kind, int exec_flags, float* stage_ms,
+                                         float* i8_ms) {
     if (!p || !stage_ms) return SCB_ERR_INVALID_ARGUMENT;
     scb_context* c = p->ctx;
     SCB_CUDA(c, cudaSetDevice(c->device));
@@ -2196,11 +2206,20 @@ extern "C" int scb_plan_execute_timed(scb_plan* p, const scb_image* src, const s
     tm.on = true;
     tm.stream = p->lane->stream;
     for (int i = 0; i < ST_COUNT; ++i) SCB_CUDA(c, cudaEventCreate(&tm.ev[i]));
-    for (int i = 0; i < ST_COUNT - 1; ++i) stage_ms[i] = 0.f;
+    for (int i = 0; i < kStages; ++i) stage_ms[i] = 0.f;
+    if (i8_ms)
+        for (int i = 0; i < 5; ++i) i8_ms[i] = 0.f;
     int rc = execute_impl(p, src, dst, blend, mem_kind, exec_flags, tm);
     if (rc == SCB_OK && !p->g.empty) {
         cudaStreamSynchronize(p->lane->stream);
-        for (int i = 0; i < ST_COUNT - 1; ++i) cudaEventElapsedTime(&stage_ms[i], tm.ev[i], tm.ev[i + 1]);
+        for (int i = 0; i < kStages; ++i) cudaEventElapsedTime(&stage_ms[i], tm.ev[i], tm.ev[i + 1]);
+        if (i8_ms && p->use_i8) {
+            cudaEventElapsedTime(&i8_ms[0], tm.ev[ST_LOW], tm.ev[ST_X_DIGF]);
+            cudaEventElapsedTime(&i8_ms[1], tm.ev[ST_X_DIGF], tm.ev[ST_ROWS_FWD]);
+            cudaEventElapsedTime(&i8_ms[2], tm.ev[ST_COLS], tm.ev[ST_X_DIGI]);
+            cudaEventElapsedTime(&i8_ms[3], tm.ev[ST_X_DIGI], tm.ev[ST_X_GEMMI]);
+            cudaEventElapsedTime(&i8_ms[4], tm.ev[ST_X_GEMMI], tm.ev[ST_ROWS_INV]);
+        }
     }
     for (int i = 0; i < ST_COUNT; ++i) cudaEventDestroy(tm.ev[i]);
     return rc;

@@ -28,7 +28,7 @@ def test_sharded_solve_equals_single_gpu_over_nccl(cuda_lib, engine, plain):
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tools", "sharded_check.py"), "--size", "1100", "--engine", engine] + (["--plain-context"] if plain else [])
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0, "sharded result differs from the single-GPU result (or the run failed)"
     assert r.stdout.count("sharded == single: True") == 2

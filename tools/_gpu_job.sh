@@ -1,10 +1,8 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_pipeline.py -m gpu -q -x -k "banded or batch or golden or int8" 2>&1 | tail -5 > gpurun_out/r2_l_pytest_gpu.log
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_l_bench_cfg2.json 2> gpurun_out/r2_l_bench_cfg2.err
-SCB_PLAN_CACHE=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_l_bench_cfg2_nocache.json 2> gpurun_out/r2_l_bench_cfg2_nocache.err
-timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_l_bench_cfg4.json 2> gpurun_out/r2_l_bench_cfg4.err
-for t in 1 2 4 8; do for l in 4 8; do
-SCB_SUBMIT_THREADS=$t SCB_LANES=$l timeout 300 python bench.py --workload cfg3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_l_bench_cfg3_t${t}_l${l}.json 2> gpurun_out/r2_l_bench_cfg3_t${t}_l${l}.err
-done; done
+nvidia-smi -L > gpurun_out/r2_m_gpus.txt
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q -x -s 2>&1 | tail -30 > gpurun_out/r2_m_pytest_multigpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_m_bench_n2.json 2> gpurun_out/r2_m_bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload cfg4 --steps 10 --warmup 3 --no-sharded-graph > gpurun_out/r2_m_bench_cfg4_n2_nograph.json 2> gpurun_out/r2_m_bench_cfg4_n2_nograph.err
+tail -5 gpurun_out/r2_m_bench_n2.err

@@ -73,6 +73,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
     print(f"rank {rank}/{world}: engine {args.engine}{' (plain context)' if args.plain_context else ''}: sharded == single: {same}; {ms:.3f} ms per sharded solve of {S}x{S}", flush=True)
+    solve.graph = None  # the captured NCCL kernels go before the communicator does
+    torch.cuda.synchronize()
     ok = torch.tensor([1 if same else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     plan.close()
