@@ -9,10 +9,12 @@ from oracle import seamless_oracle as so
 
 
 @pytest.mark.gpu
-def test_cpp_seamless_clone(tmp_path, cuda_lib):
+@pytest.mark.parametrize("which", ["scb_mat", "cv_mat_overload"])
+def test_cpp_seamless_clone(tmp_path, cuda_lib, which):
+    """scb::seamlessClone on scb::Mat, and the cv::Mat overload (compiled against the mock <opencv2/core.hpp>: no OpenCV headers here)."""
     import __graft_entry__ as ge
 
-    exe = ge.build_cpp_test()
+    exe = ge.build_cpp_test() if which == "scb_mat" else ge.build_cvmat_test()
     assert exe and os.path.exists(exe)
     src, dst, mask, p = so.make_config("small", 21)
     ref = so.restate(src, dst, mask, p, transform="f64")
@@ -32,4 +34,6 @@ def test_cpp_api_compiles_against_the_header(cuda_lib):
     import __graft_entry__ as ge
 
     exe = ge.build_cpp_test(force=True)
+    assert exe and os.path.exists(exe)
+    exe = ge.build_cvmat_test(force=True)  # the cv::Mat overload (SCB_WITH_OPENCV) against the mock <opencv2/core.hpp>
     assert exe and os.path.exists(exe)

@@ -5,18 +5,22 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from tests import common
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cli_and_compare_report(tmp_path, emu_lib):
+@pytest.mark.parametrize("backend", ["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_cli_and_compare_report(tmp_path, request, backend):
+    """Runs twice: against the emulator build on CPU and against libscb.so on a B200 (-m gpu)."""
+    lib = request.getfixturevalue("emu_lib" if backend == "emu" else "cuda_lib")
     z = common.load_golden("small_ellipse")
     for k in ("src", "dst", "mask"):
         np.save(tmp_path / f"{k}.npy", z[k])
     px, py = (int(v) for v in z["p"])
-    env = dict(os.environ, SCB_LIBRARY=emu_lib)
+    env = dict(os.environ, SCB_LIBRARY=lib)
     out = tmp_path / "blend.npy"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "seamless_clone_cli.py"), str(tmp_path / "src.npy"), str(tmp_path / "dst.npy"),
                         str(tmp_path / "mask.npy"), str(px), str(py), "--out", str(out)], env=env, capture_output=True, text=True, cwd=ROOT)
