@@ -700,7 +700,7 @@ def sharded_leg(env, args, steps=None):
             solve.capture(vs, vd, vb)
             launches_per_step = ctx.kernel_launches - l0
             graph_step = solve.run_graph
-            for _ in range(2):
+            for _ in range(6):
                 graph_step()
             torch.cuda.synchronize()
             ya, yb_ = g.ry + 1 + solve.ys[env.rank], g.ry + 1 + solve.ys[env.rank + 1]

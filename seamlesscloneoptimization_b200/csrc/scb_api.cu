@@ -1774,6 +1774,40 @@ struct StageTimer {
 
 // ---- exact INT8 tensor-core passes along x (scb_i8.h): digit planes -> tcgen05.mma.kind::i8 -> class sums -> float ----
 // forward: G [3][ny][gp] -> A [3][ny][nx] (= -2 sum g sin, what rows_fwd produces) and the exact float64 row sums R [3][lowkx][ny]
+// NORMAL_CLONE on the INT8 engine: the stencil writes the folded digit planes itself (rhs_fold_kernel) -- no float right-hand side,
+// no digitise launch.  SCB_I8_FUSE=0 keeps the two-kernel path (A/B checks); debug plans need G and keep it too.
+static bool i8_fused_rhs(const scb_plan* p) {
+    static const bool off = [] {
+        const char* e = std::getenv("SCB_I8_FUSE");
+        return e && std::strcmp(e, "0") == 0;
+    }();
+    return p->use_i8 && p->mode == SCB_NORMAL_CLONE && !p->debug && !off;
+}
+static void run_rhs_fold(scb_plan* p, const StencilSrc& st, const Workspace& w, int y0, int y1) {
+    NvtxRange nvtx_("scb:rhs_fold");
+    const scb_geometry& g = p->g;
+    RhsFoldParams f;
+    f.st = st;
+    f.nx = g.nx;
+    f.ny = g.ny;
+    f.kpar0 = p->i8x->g.kpar[0];
+    f.kpad = p->i8x->g.kpad;
+    f.lines = 3 * g.ny;
+    f.m_rows = i8_m_rows(f.lines);
+    f.planes = w.Adig;
+    f.lscale = w.lscale;
+    f.scale = p->grey_mask ? 65536.0f : 1.0f;
+    f.y0 = y0;
+    const int rows = (y1 >= g.ny ? (f.m_rows + 2) / 3 : y1) - y0;  // the last range also writes the zero pad lines up to the last whole tile
+    if (rows <= 0) return;
+    const dim3 grid((f.kpad / 4 + kRhsThreads - 1) / kRhsThreads, rows);
+    if (p->grey_mask)
+        SCB_LAUNCH(rhs_fold_kernel<4>, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
+    else
+        SCB_LAUNCH(rhs_fold_kernel<2>, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
+    p->ctx->launches++;
+}
+
 // Rows [y0, y1) of the ROI interior = lines [3 y0, 3 y1) (channel-interleaved).  The tiles that straddle the ends of the range are
 // computed whole (their foreign lines hold whatever the digit planes hold) but only the lines of the range are stored.
 static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int gp, float* A, double* R, int y0, int y1, StageTimer* tm = nullptr) {
@@ -1795,8 +1829,10 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     d.per_line = 0;
     d.line0 = 3 * y0;
     d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;  // the pad lines up to the last whole tile are written as zeros
-    if (i8_launch_digitize((void*)p->lane->stream, d, da) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
-    c->launches++;
+    if (!i8_fused_rhs(p)) {  // (fused: rhs_fold_kernel has written the digit planes already)
+        if (i8_launch_digitize((void*)p->lane->stream, d, da) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
+        c->launches++;
+    }
     if (tm) tm->mark(ST_X_DIGF);
     I8GemmParams m{};
     m.g = p->i8x->g;
@@ -2092,12 +2128,19 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
     }
     tm.mark(ST_IN);
     const int gpl = swap ? (int)align_up((size_t)g.ny, 4) : w.gp;  // pitch of a line of G in the solve's frame
+    const bool fused = i8_fused_rhs(p);
     if (nb == 1) {
-        run_rhs(p, st, w.G, w.gp, 0, g.ny, swap);
+        if (fused)
+            run_rhs_fold(p, st, w, 0, g.ny);
+        else
+            run_rhs(p, st, w.G, w.gp, 0, g.ny, swap);
     } else {
         for (int b = 0; b < nb; ++b) {
             SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_band[b], 0));
-            run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1], swap);
+            if (fused)
+                run_rhs_fold(p, st, w, yb[b], yb[b + 1]);
+            else
+                run_rhs(p, st, w.G, w.gp, yb[b], yb[b + 1], swap);
             if (b + 1 < nb && !swap) {  // the last band's rows follow the refinement fork
                 if (p->use_i8) {
                     if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, yb[b], yb[b + 1]))) return rc;
@@ -2679,7 +2722,10 @@ extern "C" int scb_plan_tri_forward(scb_plan* p, const scb_image* src, const scb
     SCB_CUDA(c, cudaMemsetAsync(ends32_dev, 0, n32 * sizeof(float), ms));
     SCB_CUDA(c, cudaMemsetAsync(ends64_dev, 0, n64 * sizeof(double), ms));
     SCB_CUDA(c, cudaMemsetAsync(w_dev, 0, nw * sizeof(double), ms));
-    run_rhs(p, st, w.G, w.gp, y0, y1);
+    if (i8_fused_rhs(p))
+        run_rhs_fold(p, st, w, y0, y1);
+    else
+        run_rhs(p, st, w.G, w.gp, y0, y1);
     if (p->use_i8) {  // the INT8 pass delivers the exact low-frequency row sums itself
         if ((rc = run_i8_forward(p, w, w.G, w.gp, w.At, w.R, y0, y1))) return rc;
     } else {

@@ -260,6 +260,209 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_kernel(RhsParams p) {
     for (int c = 0; c < 3; ++c) rhs_store4<TRANSPOSED>(p, c, x0, y, out[c][0], out[c][1], out[c][2], out[c][3]);
 }
 
+// The same four-pixel stencil as rhs_kernel's vector path, as a function: the right-hand side of pixels x0 .. x0+3 of row y, all three
+// channels.  Requires x0 + 8 <= nx (the word loads cover pixels x0 .. x0+5).  Used by rhs_fold_kernel below.
+SCB_D void rhs_quad(const StencilSrc& s, int x0, int y, float (&out)[3][4]) {
+    const int X = x0 + 1, Y = y + 1;
+    // row Y from column X-1 (20 bytes cover X-1 .. X+4), rows Y-1 / Y+1 from column X (12 bytes cover X .. X+3)
+    unsigned dm[5], du[3], dd[3], sm[5], su[3], sd[3], em[2], eu[1];
+    load_unaligned_words<2>(s.E + (long long)Y * s.e_pitch + (X - 1), em);
+    load_unaligned_words<1>(s.E + (long long)(Y - 1) * s.e_pitch + X, eu);
+    {
+        // Fast path (almost every thread): the nine mask taps of the four pixels are all 0 or all 255 and no
+        // pixel touches the ROI border, so g is the 5-point Laplacian of ONE image, a 1-D stencil over its
+        // interleaved bytes (taps at -3, +3, -pitch, +pitch bytes).  Only that image is read, and the twelve
+        // values are formed two at a time in packed 16-bit lanes (biased by 2048 so that no borrow crosses a
+        // lane) and converted with the 2^23 trick: ~35 instructions per pixel instead of ~140, which is what
+        // lets the kernel run at HBM speed.  The results are small exact integers, hence bit-identical to
+        // the float path below.
+        const unsigned m_and = em[0] & eu[0] & (em[1] | 0xffffff00u), m_or = em[0] | eu[0] | (em[1] & 0xffu);
+        const bool all_src = (m_and == 0xffffffffu), all_dst = (m_or == 0u);
+        if ((all_src || all_dst) && x0 > 0 && Y > 1 && Y < s.h - 2) {
+            const unsigned char* img = all_src ? s.S : s.D;
+            const long long pitch = all_src ? s.s_pitch : s.d_pitch;
+            unsigned m[5], u[3], d[3];
+            load_unaligned_words<5>(img + (long long)Y * pitch + 3 * (X - 1), m);
+            load_unaligned_words<3>(img + (long long)(Y - 1) * pitch + 3 * X, u);
+            load_unaligned_words<3>(img + (long long)(Y + 1) * pitch + 3 * X, d);
+            float o[12];
+            SCB_UNROLL
+            for (int j = 0; j < 3; ++j) {
+                const unsigned l = m[j];                                        // bytes e-3
+                const unsigned c = __funnelshift_r(m[j], m[j + 1], 24);         // bytes e
+                const unsigned r = __funnelshift_r(m[j + 1], m[j + 2], 16);     // bytes e+3
+                SCB_UNROLL
+                for (int half = 0; half < 2; ++half) {
+                    const unsigned sel = half ? 0x4342u : 0x4140u;  // two bytes -> two 16-bit lanes
+                    unsigned t = 0x08000800u + __byte_perm(l, 0u, sel) + __byte_perm(r, 0u, sel) + __byte_perm(u[j], 0u, sel) + __byte_perm(d[j], 0u, sel);
+                    t -= 4u * __byte_perm(c, 0u, sel);
+                    o[4 * j + 2 * half + 0] = __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7610u)) - 8390656.0f;  // (2^23 + 2048 + v) - (2^23 + 2048)
+                    o[4 * j + 2 * half + 1] = __uint_as_float(__byte_perm(t, 0x4b000000u, 0x7632u)) - 8390656.0f;
+                }
+            }
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                out[c][0] = o[c];
+                out[c][1] = o[3 + c];
+                out[c][2] = o[6 + c];
+                out[c][3] = o[9 + c];
+            }
+            return;
+        }
+    }
+    load_unaligned_words<5>(s.D + (long long)Y * s.d_pitch + 3 * (X - 1), dm);
+    load_unaligned_words<3>(s.D + (long long)(Y - 1) * s.d_pitch + 3 * X, du);
+    load_unaligned_words<3>(s.D + (long long)(Y + 1) * s.d_pitch + 3 * X, dd);
+    load_unaligned_words<5>(s.S + (long long)Y * s.s_pitch + 3 * (X - 1), sm);
+    load_unaligned_words<3>(s.S + (long long)(Y - 1) * s.s_pitch + 3 * X, su);
+    load_unaligned_words<3>(s.S + (long long)(Y + 1) * s.s_pitch + 3 * X, sd);
+    SCB_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const int el = byte_of(em, k), ec = byte_of(em, k + 1), eup = byte_of(eu, k);
+        const bool binary = ((el == 0) | (el == 255)) & ((ec == 0) | (ec == 255)) & ((eup == 0) | (eup == 255));
+        const int Xk = X + k;
+        if (binary) {
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const int Dl = byte_of(dm, 3 * k + c), Dc = byte_of(dm, 3 * k + 3 + c), Dr = byte_of(dm, 3 * k + 6 + c);
+                const int Du = byte_of(du, 3 * k + c), Dd = byte_of(dd, 3 * k + c);
+                const int Sl = byte_of(sm, 3 * k + c), Sc = byte_of(sm, 3 * k + 3 + c), Sr = byte_of(sm, 3 * k + 6 + c);
+                const int Su = byte_of(su, 3 * k + c), Sd = byte_of(sd, 3 * k + c);
+                int lap = (ec ? (Sr - Sc) + (Sd - Sc) : (Dr - Dc) + (Dd - Dc)) - (el ? (Sc - Sl) : (Dc - Dl)) - (eup ? (Sc - Su) : (Dc - Du));
+                if (Xk == 1) lap -= Dl;
+                if (Xk == s.w - 2) lap -= Dr;
+                if (Y == 1) lap -= Du;
+                if (Y == s.h - 2) lap -= Dd;
+                out[c][k] = (float)lap;
+            }
+        } else {  // grey mask values: OpenCV's float arithmetic, operation by operation
+            const float inv255 = 1.0f / 255.0f;
+            const float mc = __fmul_rn((float)ec, inv255), mic = __fmul_rn((float)(255 - ec), inv255);
+            const float ml = __fmul_rn((float)el, inv255), mil = __fmul_rn((float)(255 - el), inv255);
+            const float mu = __fmul_rn((float)eup, inv255), miu = __fmul_rn((float)(255 - eup), inv255);
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c) {
+                const float Dl = (float)byte_of(dm, 3 * k + c), Dc = (float)byte_of(dm, 3 * k + 3 + c), Dr = (float)byte_of(dm, 3 * k + 6 + c);
+                const float Du = (float)byte_of(du, 3 * k + c), Dd = (float)byte_of(dd, 3 * k + c);
+                const float Sl = (float)byte_of(sm, 3 * k + c), Sc = (float)byte_of(sm, 3 * k + 3 + c), Sr = (float)byte_of(sm, 3 * k + 6 + c);
+                const float Su = (float)byte_of(su, 3 * k + c), Sd = (float)byte_of(sd, 3 * k + c);
+                const float vxc = __fadd_rn(__fmul_rn(Dr - Dc, mic), __fmul_rn(Sr - Sc, mc));
+                const float vxl = __fadd_rn(__fmul_rn(Dc - Dl, mil), __fmul_rn(Sc - Sl, ml));
+                const float vyc = __fadd_rn(__fmul_rn(Dd - Dc, mic), __fmul_rn(Sd - Sc, mc));
+                const float vyu = __fadd_rn(__fmul_rn(Dc - Du, miu), __fmul_rn(Sc - Su, mu));
+                const float lap = __fadd_rn(__fsub_rn(vxc, vxl), __fsub_rn(vyc, vyu));
+                float bnd = 0.f;
+                if (Xk == 1) bnd += Dl;
+                if (Xk == s.w - 2) bnd += Dr;
+                if (Y == 1) bnd += Du;
+                if (Y == s.h - 2) bnd += Dd;
+                out[c][k] = __fsub_rn(lap, bnd);
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Stencil fused with the fold + digit split of the INT8 DST engine (scb_i8.h): instead of the float right-hand side G, the kernel
+// writes the balanced base-256 digit planes of  f0 = g[j] + g[n-1-j],  f1 = g[j] - g[n-1-j]  directly -- what i8_digitize_kernel would
+// produce from G, bit for bit -- so G (12 B per pixel written, then read again) never exists and one launch disappears.
+// A thread owns the folded elements j0 .. j0+3 of one row: the four pixels at x = j0 and their mirror images at x = n-4-j0.
+//   planes[(par * DA + i) * m_rows + line][j],  line = 3 y + channel  (the engine's channel-interleaved line order)
+// DA = 2: integer right-hand side (binary mask); DA = 4: 16 fractional bits (grey mask values).  Rows y >= ny are the zero pad lines.
+// grid = (ceil(kpad / 4 / 128), rows), block = 128
+// ---------------------------------------------------------------------------------------------
+struct RhsFoldParams {
+    StencilSrc st;
+    int nx, ny;
+    int kpar0, kpad;     // folded length (parity 0) and row pitch of the digit planes
+    int m_rows, lines;   // padded / real line count (lines = 3 ny)
+    signed char* planes;
+    float* lscale;       // [m_rows] per-line scale of the digit planes (1 or 2^-16)
+    float scale;         // 1 (DA = 2) or 65536 (DA = 4)
+    int y0;
+};
+
+template <int ND>
+SCB_D void fold_digits(int v, int (&d)[ND]) {  // balanced base-256 digits, most significant first (== i8_digits of scb_i8.cu)
+    SCB_UNROLL
+    for (int i = ND - 1; i > 0; --i) {
+        const int lo = ((v + 128) & 255) - 128;
+        d[i] = lo;
+        v = (v - lo) >> 8;
+    }
+    d[0] = v;
+}
+
+template <int DA>
+__global__ void __launch_bounds__(kRhsThreads) rhs_fold_kernel(RhsFoldParams p) {
+    const int y = p.y0 + blockIdx.y;
+    const int j0 = 4 * (blockIdx.x * kRhsThreads + threadIdx.x);
+    if (j0 >= p.kpad) return;
+    const int n = p.nx, h = n >> 1;
+    float a[3][4], b[3][4];  // g at j0+e, and at its mirror n-1-(j0+e)
+    SCB_UNROLL
+    for (int c = 0; c < 3; ++c)
+        SCB_UNROLL
+        for (int e = 0; e < 4; ++e) a[c][e] = b[c][e] = 0.f;
+    bool mid[4] = {false, false, false, false};  // the middle element of an odd line: f0 = g[h], f1 = 0
+    if (y < p.ny && j0 < p.kpar0) {
+        if (j0 >= 4 && j0 + 3 < h && j0 + 8 <= n) {
+            float m[3][4];
+            rhs_quad(p.st, j0, y, a);
+            rhs_quad(p.st, n - 4 - j0, y, m);
+            SCB_UNROLL
+            for (int c = 0; c < 3; ++c)
+                SCB_UNROLL
+                for (int e = 0; e < 4; ++e) b[c][e] = m[c][3 - e];
+        } else {  // the ends of the row and the thread that straddles the middle: pixel by pixel
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                float g[3] = {0.f, 0.f, 0.f}, gm[3] = {0.f, 0.f, 0.f};
+                if (j < h) {
+                    rhs_pixel(p.st, j, y, g);
+                    rhs_pixel(p.st, n - 1 - j, y, gm);
+                } else if (j == h && (n & 1)) {
+                    rhs_pixel(p.st, h, y, g);
+                    mid[e] = true;
+                }
+                for (int c = 0; c < 3; ++c) {
+                    a[c][e] = g[c];
+                    b[c][e] = gm[c];
+                }
+            }
+        }
+    }
+    SCB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        const int line = 3 * y + c;
+        if (line >= p.m_rows) continue;
+        if (j0 == 0) p.lscale[line] = 1.0f / p.scale;
+        unsigned w[2][DA];
+        SCB_UNROLL
+        for (int q = 0; q < 2; ++q)
+            SCB_UNROLL
+            for (int i = 0; i < DA; ++i) w[q][i] = 0u;
+        SCB_UNROLL
+        for (int e = 0; e < 4; ++e) {
+            const int va = __float2int_rn(a[c][e] * p.scale), vb = __float2int_rn(b[c][e] * p.scale);
+            int d0[DA], d1[DA];
+            fold_digits<DA>(va + vb, d0);
+            fold_digits<DA>(mid[e] ? 0 : va - vb, d1);
+            SCB_UNROLL
+            for (int i = 0; i < DA; ++i) {
+                w[0][i] |= (unsigned)(d0[i] & 255) << (8 * e);
+                w[1][i] |= (unsigned)(d1[i] & 255) << (8 * e);
+            }
+        }
+        SCB_UNROLL
+        for (int q = 0; q < 2; ++q)
+            SCB_UNROLL
+            for (int i = 0; i < DA; ++i)
+                *reinterpret_cast<unsigned*>(p.planes + ((size_t)(q * DA + i) * p.m_rows + line) * p.kpad + j0) = w[q][i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The other cv::seamlessClone flags: the same solver behind a different gradient selection
 // (Cloning::normalClone in OpenCV's seamless_cloning_impl.cpp).

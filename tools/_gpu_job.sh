@@ -1,6 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_multigpu.py -m gpu -q -x 2>&1 | tail -8 > gpurun_out/r2_n_pytest_multigpu.log
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_n_bench_cfg2.json 2> gpurun_out/r2_n_bench_cfg2.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_n_bench_cfg2_reference.json 2> gpurun_out/r2_n_bench_cfg2_reference.err
+nvidia-smi -L | wc -l > gpurun_out/r2_o_ngpus.txt
+nproc >> gpurun_out/r2_o_ngpus.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_o_bench_n8.json 2> gpurun_out/r2_o_bench_n8.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r2_o_bench_n4.json 2> gpurun_out/r2_o_bench_n4.err
