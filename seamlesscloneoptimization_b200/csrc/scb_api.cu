@@ -1859,7 +1859,17 @@ static int run_i8_forward(scb_plan* p, const Workspace& w, const float* G, int g
     return SCB_OK;
 }
 // inverse: Ct [3][ny][nx] -> U [3][ny][nx] (= sum Ct sin / (nx+1))
-static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1, StageTimer* tm = nullptr) {
+// With `out8` the pass is also the compose: its epilogue clamps, truncates and stores the interleaved bytes (no float field, no compose
+// launch).  Debug plans (which dump the float field) and SCB_I8_FUSE=0 keep the separate compose kernel.
+static bool i8_fused_compose(const scb_plan* p) {
+    static const bool off = [] {
+        const char* e = std::getenv("SCB_I8_FUSE");
+        return e && std::strcmp(e, "0") == 0;
+    }();
+    return p->use_i8 && !p->debug && !off;
+}
+static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1, StageTimer* tm = nullptr, unsigned char* out8 = nullptr,
+                          long long out8_pitch = 0) {
     NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -1897,6 +1907,8 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     m.out = U;
     m.out_plane = (long long)g.ny * g.nx;
     m.out_pitch = g.nx;
+    m.out_u8 = out8;
+    m.out_u8_pitch = out8_pitch;
     m.R = nullptr;
     if (i8_launch_gemm((void*)p->lane->stream, m, 4, 3) != 0) return fail(c, SCB_ERR_CUDA, "i8_gemm_kernel (inverse) launch failed");
     c->launches++;
@@ -2188,16 +2200,18 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (side_copy) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_copy, 0));
         if (nb_out == 1) {
             if (p->use_i8) {
-                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
-                run_compose(p, w.At, out, out_pitch, 0, g.ny);
+                const bool fc = i8_fused_compose(p);
+                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm, fc ? out : nullptr, out_pitch))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
+                if (!fc) run_compose(p, w.At, out, out_pitch, 0, g.ny);
             } else {
                 run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
             }
         } else {
             for (int b = 0; b < nb; ++b) {
                 if (p->use_i8) {
-                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1]))) return rc;
-                    run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
+                    const bool fc = i8_fused_compose(p);
+                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1], nullptr, fc ? out : nullptr, out_pitch))) return rc;
+                    if (!fc) run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
                 } else {
                     run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);
                 }
@@ -2774,8 +2788,9 @@ extern "C" int scb_plan_tri_finish_slots(scb_plan* p, scb_image* blend, int mem_
     launch_tri_low(p, true, la, p->lane->stream);
     unsigned char* bInt = (unsigned char*)blend->data + (size_t)(g.ry + 1) * blend->stride + (size_t)3 * (g.rx + 1);
     if (p->use_i8) {
-        if ((rc = run_i8_inverse(p, w, w.Ct, w.At, y0, y1))) return rc;
-        run_compose(p, w.At, bInt, blend->stride, y0, y1);
+        const bool fc = i8_fused_compose(p);
+        if ((rc = run_i8_inverse(p, w, w.Ct, w.At, y0, y1, nullptr, fc ? bInt : nullptr, blend->stride))) return rc;
+        if (!fc) run_compose(p, w.At, bInt, blend->stride, y0, y1);
     } else {
         run_rows_inv(p, w.Ct, bInt, blend->stride, y0, y1);
     }

@@ -215,6 +215,9 @@ __global__ void __launch_bounds__(128) i8_compose_kernel(I8ComposeParams p) {
     }
 }
 
+// v < 0 -> 0, v > 255 -> 255, else truncate toward zero (OpenCV's static_cast<uchar> after the clamp; reference post_processing, imp.cpp:2078-2103)
+SCB_D unsigned char i8_to_u8(float v) { return v < 0.f ? (unsigned char)0 : (v > 255.f ? (unsigned char)255 : (unsigned char)__float2int_rz(v)); }
+
 // which basis planes digit i of the lines multiplies: planes 0 .. cnt-1, landing in classes i .. i+cnt-1
 SCB_HD int i8_plane_count(int i, int db) {
     const int left = kI8Classes - i;
@@ -226,7 +229,11 @@ SCB_D void i8_store(const I8GemmParams& p, int line, int par, int ki, int w0, in
     if (line < p.line0 || line >= p.line1 || ki >= p.g.nout[par]) return;
     const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
     const int k0 = 2 * ki + par;
-    p.out[(size_t)c * p.out_plane + (size_t)r * p.out_pitch + k0] = i8_combine(w0, w1, w2, w3) * (p.scale * ls);
+    const float v = i8_combine(w0, w1, w2, w3) * (p.scale * ls);
+    if (p.out_u8)
+        p.out_u8[(long long)r * p.out_u8_pitch + 3 * k0 + c] = i8_to_u8(v);
+    else
+        p.out[(size_t)c * p.out_plane + (size_t)r * p.out_pitch + k0] = v;
     if (p.R && k0 < p.lowk) p.R[((size_t)c * p.lowk + k0) * p.lpc + r] = i8_combine_exact(w0, w1, w2, w3) * (p.rscale * (double)ls);
 }
 
@@ -554,7 +561,12 @@ i8_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 SCB_UNROLL
                 for (int j = lane; j < COLS; j += 32) {
                     const int ki = sb0 * kI8P + col0 + j;
-                    if (ki < nout && ln >= p.line0) o[2 * ki + par] = trow[j];
+                    if (ki < nout && ln >= p.line0) {
+                        if (p.out_u8)
+                            p.out_u8[(long long)rr * p.out_u8_pitch + 3 * (2 * ki + par) + c] = i8_to_u8(trow[j]);
+                        else
+                            o[2 * ki + par] = trow[j];
+                    }
                 }
                 if (++c == 3) {
                     c = 0;
@@ -777,7 +789,13 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 int rr = ln / 3, c = ln - 3 * rr;
                 const int ki = sb * kI8P + col0 + lane;
                 for (int r = 0; r < 32 && ln < p.line1; ++r, ++ln) {
-                    if (ki < nout && ln >= p.line0) p.out[(size_t)c * p.out_plane + (size_t)rr * p.out_pitch + 2 * ki + par] = tile[(size_t)r * OP + col0 + lane];
+                    if (ki < nout && ln >= p.line0) {
+                        const float v = tile[(size_t)r * OP + col0 + lane];
+                        if (p.out_u8)
+                            p.out_u8[(long long)rr * p.out_u8_pitch + 3 * (2 * ki + par) + c] = i8_to_u8(v);
+                        else
+                            p.out[(size_t)c * p.out_plane + (size_t)rr * p.out_pitch + 2 * ki + par] = v;
+                    }
                     if (++c == 3) {
                         c = 0;
                         ++rr;

@@ -104,6 +104,8 @@ struct I8GemmParams {
     double* R;                 // [3][lowk][lpc] exact row sums sum_j x[j] sin(..) for k0 < lowk (forward pass), or null
     int lowk;
     double rscale;             // R = t * rscale * lscale[line]
+    unsigned char* out_u8;     // non-null: the pass is the LAST one -- its epilogue clamps, truncates and stores the byte of channel c at
+    long long out_u8_pitch;    //   out_u8[r * out_u8_pitch + 3 * k0 + c] (OpenCV solve() epilogue + merge) instead of the float into `out`
     long long* trace;          // tuning aid (SCB_I8_TRACE=1): 8 clock64() stamps per CTA, or null
 };
 

@@ -370,11 +370,12 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowP
     const int L = n < kTriLowL ? n : kTriLowL;
     double w[kTriLowL];
     SCB_UNROLL
-    for (int l = 0; l < kTriLowL; ++l) {
-        double sum = 0.0;
-        if (l < L)
-            for (int sl = 0; sl < (p.w_slots > 1 ? p.w_slots : 1); ++sl) sum += p.W[(size_t)sl * 3 * kTriLowL * kTriLowK + ((size_t)c * kTriLowL + l) * kTriLowK + k];
-        w[l] = sum;
+    for (int l = 0; l < kTriLowL; ++l) w[l] = (l < L) ? p.W[((size_t)c * kTriLowL + l) * kTriLowK + k] : 0.0;
+    for (int sl = 1; sl < p.w_slots; ++sl) {  // row-sharded solves: the other ranks' partials (the static inner loop keeps w[] in registers)
+        const double* ws = p.W + (size_t)sl * 3 * kTriLowL * kTriLowK;
+        SCB_UNROLL
+        for (int l = 0; l < kTriLowL; ++l)
+            if (l < L) w[l] += ws[((size_t)c * kTriLowL + l) * kTriLowK + k];
     }
     const int yb = p.y0 + blockIdx.x * kTriLowRows;
     for (int y = yb + warp; y < yb + kTriLowRows && y < p.y1; y += kTriLowWarps) {

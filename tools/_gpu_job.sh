@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l > gpurun_out/r2_o_ngpus.txt
-nproc >> gpurun_out/r2_o_ngpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_o_bench_n8.json 2> gpurun_out/r2_o_bench_n8.err
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r2_o_bench_n4.json 2> gpurun_out/r2_o_bench_n4.err
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/r2_p_pytest_gpu.log
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_p_bench_cfg2.json 2> gpurun_out/r2_p_bench_cfg2.err
+SCB_I8_FUSE=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_p_bench_cfg2_nofuse.json 2> gpurun_out/r2_p_bench_cfg2_nofuse.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 80 --csv --log-file gpurun_out/r2_p_launches_cfg2.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_p_ncu.log 2>&1
