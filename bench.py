@@ -390,8 +390,15 @@ def roofline_objects(stages, px, workload, g=None):
         names.update({"rows_fwd": "i8_digitize_kernel<2> + i8_gemm_pkernel<2,4> (INT8 tensor-core DST)", "rows_inv": "i8_digitize_kernel<4> + i8_gemm_pkernel<4,3> + i8_compose_kernel",
                       "cols": "tri_solve_kernel + tri_low*_kernel (tridiagonal solve along y)"})
 
+    alg_bytes = dict(ALG_BYTES)
+    if i8 and stages.get("i8_digitize_fwd", 1.0) < 0.005:
+        # the stencil is fused with the fold + digit split: 7 B read (3 dst + 3 src + 1 mask) + 6 B of digit planes written per pixel
+        # (2 parities x 2 digits x half the columns x 3 channels) instead of 12 B of float right-hand side
+        alg_bytes["rhs"] = 13
+        names["rhs"] = "rhs_fold_kernel<2> (stencil fused with the fold + digit split of the INT8 engine)"
+
     def obj(k):
-        alg = ALG_BYTES[k] * px
+        alg = alg_bytes[k] * px
         ach = alg / (stages[k] * 1e-3) / 1e9 if stages.get(k) else None
         o = {"bound": "hbm", "kernel": names[k], "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
              "frac": (ach / peak) if ach else None, "algorithmic_bytes_per_launch": alg, "duration_ms": stages.get(k),
