@@ -140,34 +140,24 @@ __global__ void __launch_bounds__(kI8DigThreads) i8_digitize_kernel(I8DigitizePa
     }
     for (int j0 = 4 * t; j0 < p.g.kpad; j0 += 4 * kI8DigThreads) {
         unsigned w[2][DA];
-        SCB_UNROLL
-        for (int q = 0; q < 2; ++q)
-            SCB_UNROLL
-            for (int i = 0; i < DA; ++i) w[q][i] = 0u;
+        int f0[4] = {0, 0, 0, 0}, f1[4] = {0, 0, 0, 0};
         if (real && j0 < p.g.kpar[0]) {
             const bool first = j0 == 4 * t;
             SCB_UNROLL
             for (int e = 0; e < 4; ++e) {
                 const int j = j0 + e;
-                int f0 = 0, f1 = 0;
                 if (j < h) {
                     const float xa = first ? fa[e] : __ldg(x + j), xb = first ? fb[e] : __ldg(x + (n - 1 - j));
                     const int va = __float2int_rn(xa * s), vb = __float2int_rn(xb * s);
-                    f0 = va + vb;
-                    f1 = va - vb;
+                    f0[e] = va + vb;
+                    f1[e] = va - vb;
                 } else if (j == h && (n & 1)) {
-                    f0 = __float2int_rn((first ? fa[e] : __ldg(x + h)) * s);
-                }
-                int d0[DA], d1[DA];
-                i8_digits<DA>(f0, d0);
-                i8_digits<DA>(f1, d1);
-                SCB_UNROLL
-                for (int i = 0; i < DA; ++i) {
-                    w[0][i] |= (unsigned)(d0[i] & 255) << (8 * e);
-                    w[1][i] |= (unsigned)(d1[i] & 255) << (8 * e);
+                    f0[e] = __float2int_rn((first ? fa[e] : __ldg(x + h)) * s);
                 }
             }
         }
+        balanced_digits4<DA>(f0, w[0]);
+        balanced_digits4<DA>(f1, w[1]);
         SCB_UNROLL
         for (int q = 0; q < 2; ++q)
             SCB_UNROLL

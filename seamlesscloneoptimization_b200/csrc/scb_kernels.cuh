@@ -383,17 +383,6 @@ struct RhsFoldParams {
     int y0;
 };
 
-template <int ND>
-SCB_D void fold_digits(int v, int (&d)[ND]) {  // balanced base-256 digits, most significant first (== i8_digits of scb_i8.cu)
-    SCB_UNROLL
-    for (int i = ND - 1; i > 0; --i) {
-        const int lo = ((v + 128) & 255) - 128;
-        d[i] = lo;
-        v = (v - lo) >> 8;
-    }
-    d[0] = v;
-}
-
 template <int DA>
 __global__ void __launch_bounds__(kRhsThreads) rhs_fold_kernel(RhsFoldParams p) {
     const int y = p.y0 + blockIdx.y;
@@ -439,22 +428,15 @@ __global__ void __launch_bounds__(kRhsThreads) rhs_fold_kernel(RhsFoldParams p) 
         if (line >= p.m_rows) continue;
         if (j0 == 0) p.lscale[line] = 1.0f / p.scale;
         unsigned w[2][DA];
-        SCB_UNROLL
-        for (int q = 0; q < 2; ++q)
-            SCB_UNROLL
-            for (int i = 0; i < DA; ++i) w[q][i] = 0u;
+        int f0[4], f1[4];
         SCB_UNROLL
         for (int e = 0; e < 4; ++e) {
             const int va = __float2int_rn(a[c][e] * p.scale), vb = __float2int_rn(b[c][e] * p.scale);
-            int d0[DA], d1[DA];
-            fold_digits<DA>(va + vb, d0);
-            fold_digits<DA>(mid[e] ? 0 : va - vb, d1);
-            SCB_UNROLL
-            for (int i = 0; i < DA; ++i) {
-                w[0][i] |= (unsigned)(d0[i] & 255) << (8 * e);
-                w[1][i] |= (unsigned)(d1[i] & 255) << (8 * e);
-            }
+            f0[e] = va + vb;
+            f1[e] = mid[e] ? 0 : va - vb;
         }
+        balanced_digits4<DA>(f0, w[0]);
+        balanced_digits4<DA>(f1, w[1]);
         SCB_UNROLL
         for (int q = 0; q < 2; ++q)
             SCB_UNROLL

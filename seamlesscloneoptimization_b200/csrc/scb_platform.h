@@ -44,6 +44,29 @@ SCB_D float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, 
 SCB_D float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 SCB_D float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 #endif
+// Balanced base-256 digits of four integers at once, transposed: word i holds digit i (most significant first, DA digits) of
+// v[0..3] in its four bytes -- the layout of a digit plane.  v + 0x80808080 has the plain unsigned bytes d_k + 128 (the per-byte
+// bias absorbs the borrows of the balanced representation), so XOR 0x80 per byte gives the int8 digits; six byte permutes transpose.
+// Requires |v| < 2^(8 DA - 1) (the top digit takes what is left).
+template <int DA>
+SCB_D void balanced_digits4(const int (&v)[4], unsigned (&w)[DA]) {
+    unsigned u[4];
+    SCB_UNROLL
+    for (int e = 0; e < 4; ++e) u[e] = ((unsigned)v[e] + 0x80808080u) ^ 0x80808080u;  // byte k of u[e] = digit of weight 256^k
+    const unsigned lo01 = __byte_perm(u[0], u[1], 0x5140u), lo23 = __byte_perm(u[2], u[3], 0x5140u);
+    const unsigned k0 = __byte_perm(lo01, lo23, 0x5410u), k1 = __byte_perm(lo01, lo23, 0x7632u);
+    if (DA == 2) {
+        w[1] = k0;
+        w[0] = k1;
+    } else {
+        const unsigned hi01 = __byte_perm(u[0], u[1], 0x7362u), hi23 = __byte_perm(u[2], u[3], 0x7362u);
+        w[DA - 1] = k0;
+        w[DA - 2] = k1;
+        w[DA - 3] = __byte_perm(hi01, hi23, 0x5410u);
+        w[DA - 4] = __byte_perm(hi01, hi23, 0x7632u);
+    }
+}
+
 SCB_D float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 SCB_D float2 f2dup(float s) { return make_float2(s, s); }
 }  // namespace scb
