@@ -983,10 +983,89 @@ struct PlanInput {
     int px, py;
     int slot;
     bool staged;
+    bool host_bbox;  // HOST masks: the bounding box was taken on the host while the mask uploads -- no device reduction, no round trip
+    int hb[5];       // min x, min y, max x, max y, grey
 };
 
+// One pass over a HOST mask on the context's helper threads: the bounding box of the non-zero pixels inside the 1-pixel ring
+// (OpenCV: copyMakeBorder(mask(1..-1), 0) + boundingRect), whether a pixel inside the ring is neither 0 nor 255, and (for the
+// plan cache of scb_seamless_clone) a 64-bit hash of every byte.  8 bytes at a time; four independent multiply-xor chains keep
+// the multiplier pipelined.  Replaces the reference's device reduction + blocking D2H per call (initMask, imp.cpp:927-963, 1008-1012).
+struct MaskScan {
+    uint64_t hash = 0;
+    int minx = INT_MAX, miny = INT_MAX, maxx = -1, maxy = -1, grey = 0;
+};
+static MaskScan scan_rows(const scb_image* m, int y0, int y1) {
+    const uint64_t K = 0x9E3779B97F4A7C15ull, M01 = 0x0101010101010101ull;
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    MaskScan r;
+    const int cols = m->cols, nw = (cols + 7) / 8;
+    for (int y = y0; y < y1; ++y) {
+        const unsigned char* row = (const unsigned char*)m->data + (size_t)y * m->stride;
+        const bool inner = y > 0 && y < m->rows - 1;
+        int first = -1, last_i = -1;
+        uint64_t last_w = 0, grey = 0;
+        for (int i = 0; i < nw; ++i) {
+            uint64_t w = 0;
+            const int left = cols - 8 * i;
+            std::memcpy(&w, row + 8 * i, left >= 8 ? 8 : (size_t)left);
+            h[i & 3] = ((h[i & 3] ^ w) * K) ^ (h[i & 3] >> 29);
+            if (!inner || !w) continue;
+            if (i == 0) w &= ~0xFFull;                                          // column 0 belongs to the ring
+            if (8 * i + 7 >= cols - 1) w &= ~(0xFFull << (8 * (cols - 1 - 8 * i)));  // so does column cols-1
+            if (!w) continue;
+            if (first < 0) first = 8 * i + (__builtin_ctzll(w) >> 3);
+            last_i = i;
+            last_w = w;
+            grey |= w ^ (((w >> 7) & M01) * 0xFFull);  // a byte is 0 or 255 iff it equals its top bit spread over the byte
+        }
+        h[0] = ((h[0] ^ (uint64_t)y) * K) ^ (h[0] >> 31);
+        if (first >= 0) {
+            const int last = 8 * last_i + 7 - (__builtin_clzll(last_w) >> 3);
+            if (first < r.minx) r.minx = first;
+            if (last > r.maxx) r.maxx = last;
+            if (y < r.miny) r.miny = y;
+            if (y > r.maxy) r.maxy = y;
+            if (grey) r.grey = 1;
+        }
+    }
+    r.hash = ((h[0] * K) ^ h[1]) * K ^ ((h[2] * K) ^ h[3]);
+    return r;
+}
+static int host_threads();
+class HostPool;
+static HostPool& pool_of(scb_context* c);
+static void pool_run(scb_context* c, int n, const std::function<void(int)>& fn);  // defined next to the pool
+static MaskScan scan_mask(scb_context* c, const scb_image* m, bool parallel) {
+    const size_t bytes = (size_t)m->rows * m->cols;
+    int T = parallel ? (int)(bytes >> 18) : 1;  // one thread per 256 KiB
+    if (T > host_threads()) T = host_threads();
+    if (T > 16) T = 16;
+    if (T <= 1) return scan_rows(m, 0, m->rows);
+    MaskScan part[16];
+    const int per = (m->rows + T - 1) / T;
+    pool_run(c, T, [&](int t) {
+        const int a = t * per, b = (a + per < m->rows) ? a + per : m->rows;
+        if (a < b) part[t] = scan_rows(m, a, b);
+    });
+    MaskScan r;
+    uint64_t h = 0x452821E638D01377ull;
+    for (int t = 0; t < T; ++t) {
+        h = ((h ^ part[t].hash) * 0x9E3779B97F4A7C15ull) ^ (h >> 32);
+        if (part[t].maxx < 0) continue;
+        if (part[t].minx < r.minx) r.minx = part[t].minx;
+        if (part[t].maxx > r.maxx) r.maxx = part[t].maxx;
+        if (part[t].miny < r.miny) r.miny = part[t].miny;
+        if (part[t].maxy > r.maxy) r.maxy = part[t].maxy;
+        r.grey |= part[t].grey;
+    }
+    r.hash = h;
+    return r;
+}
+
 static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
-                      int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in, int clone_flags = SCB_NORMAL_CLONE) {
+                      int dst_rows, int dst_cols, int px, int py, int slot, scb_plan** out, PlanInput* in, int clone_flags = SCB_NORMAL_CLONE,
+                      const MaskScan* scanned = nullptr, bool parallel_scan = true) {
     NvtxRange nvtx_("scb:plan_begin");
     *out = nullptr;
     const bool wide = clone_flags >= SCB_NORMAL_CLONE_WIDE;
@@ -1015,6 +1094,7 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
     in->py = py;
     in->slot = slot;
     in->staged = false;
+    in->host_bbox = false;
     auto bad = [&](int code, const std::string& msg) {
         scb_plan_destroy(p);
         return fail(c, code, msg);
@@ -1029,6 +1109,16 @@ static int plan_begin(scb_context* c, Lane* lane, cudaStream_t prep, const scb_i
         mv.data = p->mask_stage;
         mv.pitch = (long long)pitch;
         in->staged = true;
+        // the bounding box on the host, while the upload is in flight: plan creation makes no device round trip for HOST masks
+        const MaskScan sc = scanned ? *scanned : scan_mask(c, mask, parallel_scan);
+        in->host_bbox = true;
+        in->hb[0] = sc.minx;
+        in->hb[1] = sc.miny;
+        in->hb[2] = sc.maxx;
+        in->hb[3] = sc.maxy;
+        in->hb[4] = sc.grey;
+        *out = p;
+        return SCB_OK;
     } else {
         mv.data = (const unsigned char*)mask->data;
         mv.pitch = mask->stride;
@@ -1053,7 +1143,7 @@ static int plan_finish(scb_plan* p, const PlanInput& in) {
     NvtxRange nvtx_("scb:plan_finish");
     scb_context* c = p->ctx;
     Lane* lane = p->lane;
-    const int* r = c->bbox_pinned + kBboxInts * (in.slot + 1);
+    const int* r = in.host_bbox ? in.hb : c->bbox_pinned + kBboxInts * (in.slot + 1);
     const int minx = r[0], miny = r[1], maxx = r[2], maxy = r[3];
     p->grey_mask = r[4] != 0;
     auto release_stage = [&]() {
@@ -1132,8 +1222,10 @@ extern "C" int scb_plan_create(scb_context* c, const scb_image* mask, int mask_m
     return scb_plan_create_ex(c, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, SCB_NORMAL_CLONE, out);
 }
 
-extern "C" int scb_plan_create_ex(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
-                                  int dst_rows, int dst_cols, int px, int py, int clone_flags, scb_plan** out) {
+// sync_mask = false: the caller (scb_seamless_clone) runs a HOST execute on the same stream next, whose trailing sync also covers the
+// mask upload -- a HOST plan then costs no synchronisation at all.  `scanned`: the mask scan the caller already did (hash + bbox).
+static int plan_create_impl(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols, int dst_rows, int dst_cols, int px, int py,
+                            int clone_flags, scb_plan** out, bool sync_mask, const MaskScan* scanned) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
     if (!out) return fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_plan_create: out is null");
     *out = nullptr;
@@ -1141,17 +1233,32 @@ extern "C" int scb_plan_create_ex(scb_context* c, const scb_image* mask, int mas
     Lane* lane = &c->lanes[0];
     scb_plan* p = nullptr;
     PlanInput in;
-    int rc = plan_begin(c, lane, lane->stream, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, 0, &p, &in, clone_flags);
+    int rc = plan_begin(c, lane, lane->stream, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, 0, &p, &in, clone_flags, scanned);
     if (rc) return rc;
-    cudaError_t e = cudaStreamSynchronize(lane->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        scb_plan_destroy(p);
-        return fail(c, SCB_ERR_CUDA, std::string("scb_plan_create: ") + cudaGetErrorString(e));
+    if (!in.host_bbox) {  // DEVICE masks: the bounding box comes back from the device
+        cudaError_t e = cudaStreamSynchronize(lane->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            scb_plan_destroy(p);
+            return fail(c, SCB_ERR_CUDA, std::string("scb_plan_create: ") + cudaGetErrorString(e));
+        }
     }
     if ((rc = plan_finish(p, in))) return rc;
+    if (in.host_bbox && sync_mask) {  // the caller's mask buffer is free again on return (the erosion has consumed the staged copy)
+        cudaError_t e = cudaStreamSynchronize(lane->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            scb_plan_destroy(p);
+            return fail(c, SCB_ERR_CUDA, std::string("scb_plan_create: ") + cudaGetErrorString(e));
+        }
+    }
     *out = p;
     return SCB_OK;
+}
+
+extern "C" int scb_plan_create_ex(scb_context* c, const scb_image* mask, int mask_mem_kind, int src_rows, int src_cols,
+                                  int dst_rows, int dst_cols, int px, int py, int clone_flags, scb_plan** out) {
+    return plan_create_impl(c, mask, mask_mem_kind, src_rows, src_cols, dst_rows, dst_cols, px, py, clone_flags, out, /*sync_mask=*/true, nullptr);
 }
 
 extern "C" int scb_plan_geometry(const scb_plan* p, scb_geometry* out) {
@@ -1426,6 +1533,7 @@ static HostPool& pool_of(scb_context* c) {
     if (!c->pool) c->pool = new HostPool();
     return *c->pool;
 }
+static void pool_run(scb_context* c, int n, const std::function<void(int)>& fn) { pool_of(c).run(n, fn); }
 static void host_pool_free(scb_context* c) {
     delete c->pool;
     c->pool = nullptr;
@@ -2282,42 +2390,6 @@ extern "C" int scb_plan_execute_timed_i8(scb_plan* p, const scb_image* src, cons
     return rc;
 }
 
-// 64-bit hash of a HOST mask (every byte: a mask that differs anywhere must miss), over the context's helper threads.
-// Four independent multiply-xor chains per thread keep the multiplier pipelined (~10 GB/s per thread).
-static uint64_t hash_rows(const scb_image* m, int y0, int y1) {
-    const uint64_t K = 0x9E3779B97F4A7C15ull;
-    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
-    for (int y = y0; y < y1; ++y) {
-        const unsigned char* r = (const unsigned char*)m->data + (size_t)y * m->stride;
-        size_t n = (size_t)m->cols, i = 0;
-        for (; i + 32 <= n; i += 32) {
-            uint64_t w[4];
-            std::memcpy(w, r + i, 32);
-            for (int k = 0; k < 4; ++k) h[k] = ((h[k] ^ w[k]) * K) ^ (h[k] >> 29);
-        }
-        uint64_t tail = 0;
-        for (; i < n; ++i) tail = (tail << 8) | r[i];
-        h[0] = ((h[0] ^ tail ^ (uint64_t)y) * K) ^ (h[0] >> 31);
-    }
-    return ((h[0] * K) ^ h[1]) * K ^ ((h[2] * K) ^ h[3]);
-}
-static uint64_t hash_mask(scb_context* c, const scb_image* m) {
-    const size_t bytes = (size_t)m->rows * m->cols;
-    int T = (int)(bytes >> 18);  // one thread per 256 KiB
-    if (T > host_threads()) T = host_threads();
-    if (T <= 1) return hash_rows(m, 0, m->rows);
-    uint64_t part[16] = {0};
-    if (T > 16) T = 16;
-    const int per = (m->rows + T - 1) / T;
-    pool_of(c).run(T, [&](int t) {
-        const int a = t * per, b = (a + per < m->rows) ? a + per : m->rows;
-        part[t] = a < b ? hash_rows(m, a, b) : 0;
-    });
-    uint64_t h = 0x452821E638D01377ull;
-    for (int t = 0; t < T; ++t) h = ((h ^ part[t]) * 0x9E3779B97F4A7C15ull) ^ (h >> 32);
-    return h;
-}
-
 extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const scb_image* dst, const scb_image* mask,
                                   int px, int py, scb_image* blend, int clone_flags, int mem_kind) {
     if (!c) return SCB_ERR_INVALID_ARGUMENT;
@@ -2334,9 +2406,11 @@ extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const sc
     }
     // plan cache: everything a plan depends on is in the key (the mask by its hash)
     scb_context::CachedPlan want;
+    MaskScan scan;
     {
-        NvtxRange nvtx_("scb:mask_hash");
-        want.hash = hash_mask(c, mask);
+        NvtxRange nvtx_("scb:mask_scan");
+        scan = scan_mask(c, mask, true);  // hash (the cache key) and bounding box (a miss needs it) in one pass
+        want.hash = scan.hash;
     }
     const int key[11] = {mask->rows, mask->cols, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, wanted_engine(c), c->orientation};
     std::memcpy(want.key, key, sizeof(key));
@@ -2350,7 +2424,7 @@ extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const sc
         }
     if (!p) {
         c->plan_misses++;
-        int rc = scb_plan_create_ex(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p);
+        int rc = plan_create_impl(c, mask, mem_kind, src->rows, src->cols, dst->rows, dst->cols, px, py, clone_flags, &p, /*sync_mask=*/false, &scan);
         if (rc) return rc;
         if ((int)c->plan_cache.size() >= c->plan_cache_cap) {  // evict the least recently used plan
             size_t lru = 0;
@@ -2362,6 +2436,11 @@ extern "C" int scb_seamless_clone(scb_context* c, const scb_image* src, const sc
         want.plan = p;
         want.last_use = ++c->use_clock;
         c->plan_cache.push_back(want);
+        const int rc2 = scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
+        // the plan was created without waiting for its mask upload: a HOST execute ends with a stream sync that covers it, except
+        // for an empty plan or a failed execute -- wait here then, so that the caller's mask buffer is always free on return
+        if (rc2 != SCB_OK || p->g.empty) cudaStreamSynchronize(c->lanes[0].stream);
+        return rc2;
     }
     return scb_plan_execute(p, src, dst, blend, mem_kind, SCB_EXEC_DEFAULT);
 }

@@ -384,7 +384,7 @@ struct RhsFoldParams {
 };
 
 template <int DA>
-__global__ void __launch_bounds__(kRhsThreads) rhs_fold_kernel(RhsFoldParams p) {
+__global__ void __launch_bounds__(kRhsThreads, 8) rhs_fold_kernel(RhsFoldParams p) {
     const int y = p.y0 + blockIdx.y;
     const int j0 = 4 * (blockIdx.x * kRhsThreads + threadIdx.x);
     if (j0 >= p.kpad) return;

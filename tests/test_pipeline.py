@@ -371,6 +371,41 @@ def test_launch_counter(ctx):
     plan.close()
 
 
+def test_host_mask_scan_matches_opencv_bounding_box(be):
+    """HOST masks: ring-zero + boundingRect are taken on the host in one word-wise pass (no device reduction, no round trip).
+    Random sparse masks of awkward widths (not multiples of 8, pixels only on the ring, single pixels, strided rows)."""
+    rng = np.random.default_rng(11)
+    ctx = be.context()
+    try:
+        for trial in range(60):
+            hs, ws = int(rng.integers(3, 30)), int(rng.integers(3, 45))
+            big = np.zeros((hs, ws + int(rng.integers(0, 5))), np.uint8)
+            mask = big[:, :ws]  # a view: padded row stride
+            k = int(rng.integers(0, 6))
+            for _ in range(k):
+                mask[int(rng.integers(0, hs)), int(rng.integers(0, ws))] = int(rng.choice([255, 255, 1, 200]))
+            if trial % 7 == 0:
+                mask[0, :] = 255
+                mask[:, 0] = 255
+                mask[-1, :] = 255
+                mask[:, -1] = 255  # the ring never counts
+            bb = so.bounding_box(so.ring_zero(np.ascontiguousarray(mask)))
+            if bb is not None and (bb[2] < 3 or bb[3] < 3):
+                with pytest.raises(scb.ScbError):  # refused (OpenCV itself crashes on such masks)
+                    scb.Plan(ctx, mask, (hs, ws), (400, 400), (200, 200))
+                continue
+            plan = scb.Plan(ctx, mask, (hs, ws), (400, 400), (200, 200))
+            g = plan.geometry
+            if bb is None:
+                assert g.empty, (trial, mask)
+            else:
+                assert (g.x, g.y, g.w, g.h) == tuple(bb), (trial, mask, bb)
+                assert (g.rx, g.ry) == (200 - bb[2] // 2, 200 - bb[3] // 2)
+            plan.close()
+    finally:
+        ctx.close()
+
+
 def test_plan_cache_of_the_one_shot_call(be):
     """scb_seamless_clone keeps its last plans keyed by the hash of the mask bytes: the same mask hits, a mask that differs in one
     byte (or another p) misses, and cached / uncached calls give the same bytes."""
