@@ -1473,6 +1473,7 @@ class HostPool {
             fn(0);
             return;
         }
+        std::lock_guard<std::mutex> call(call_mu_);  // one caller at a time (scb_clone_batch plans on a second thread)
         ensure(n - 1);
         {
             std::lock_guard<std::mutex> lk(mu_);
@@ -1521,7 +1522,7 @@ class HostPool {
             seen = epoch_;
         }
     }
-    std::mutex mu_;
+    std::mutex mu_, call_mu_;
     std::condition_variable cv_, done_;
     std::vector<std::thread> threads_;
     const std::function<void(int)>* fn_ = nullptr;
@@ -2592,8 +2593,9 @@ extern "C" int scb_clone_batch(scb_context* c, scb_job* jobs, int n_jobs, int me
                 note(j, fail(c, SCB_ERR_INVALID_ARGUMENT, "scb_clone_batch: null image"));
                 continue;
             }
+            // (the mask scan of a HOST job runs on THIS thread: the context's helper pool is busy submitting the previous chunk)
             note(j, plan_begin(c, &c->lanes[(base + i) % L], c->prep, &j.mask, mem_kind, j.src.rows, j.src.cols, j.dst.rows, j.dst.cols, j.px, j.py, parity * kMaxChunk + i,
-                               &ch.plans[i], &ch.inputs[i], j.flags ? j.flags : SCB_NORMAL_CLONE));
+                               &ch.plans[i], &ch.inputs[i], j.flags ? j.flags : SCB_NORMAL_CLONE, nullptr, /*parallel_scan=*/false));
         }
         double t1 = now();
         cudaError_t e = cudaStreamSynchronize(c->prep);
