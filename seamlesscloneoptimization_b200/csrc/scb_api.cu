@@ -766,10 +766,10 @@ static int get_tritab(scb_context* c, scb_plan* p, int w, int h, TriTabDev* out)
 }
 
 static bool tc_eligible(const scb_context* c, int nx, int ny) {
-    // AUTO resolves to the FFT engine: FP32 accumulation inside the tensor core truncates at every MMA step,
-    // which leaves ~1e-5 relative error after ~340 steps (K ~ 900) -- inside the 1e-4 bar for the float
-    // intermediates but enough to cost 0.2 % of exactly matching bytes at some shapes.
-    // The tensor-core engine is therefore opt-in (scb_set_engine / SCB_ENGINE=tc) until its accumulation is chunked.
+    // The TF32 tensor-core engine is opt-in (scb_set_engine / SCB_ENGINE=tc): FP32 accumulation inside the tensor core truncates at
+    // every MMA step, which leaves ~1e-5 relative error after ~340 steps (K ~ 900) -- inside the 1e-4 bar for the float intermediates
+    // but enough to cost 0.2 % of exactly matching bytes at some shapes.  The default engine contracts in exact INT8 digit planes
+    // instead (scb_i8.h).
     const int want = wanted_engine(c);
     if (want != SCB_ENGINE_TC) return false;
     return nx >= kTcMinN && ny >= kTcMinN && nx <= kTcMaxN && ny <= kTcMaxN;

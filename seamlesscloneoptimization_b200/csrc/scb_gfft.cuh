@@ -136,7 +136,7 @@ struct GCfg {
     // Twiddle tables live in shared memory when the CTA owns the SM anyway (M >= 4096: 17 KB / 81 KB
     // next to 209 KB / 139 KB of data).  At max carveout L1 is only ~24 KB and every table read would
     // otherwise pay L2 latency (ncu: long-scoreboard was the top stall of the fused passes).
-    static constexpr bool TW_SMEM = (LOG2M == SCB_TW_SMEM_LOG2M);  // experiment switch; see DESIGN.md section 5
+    static constexpr bool TW_SMEM = (LOG2M == SCB_TW_SMEM_LOG2M);  // experiment switch (round 1, profiles/README.md)
     static constexpr int TW_F4 = gtw_total_c(LOG2M);
     static constexpr size_t SMEM = DATA_BYTES + (TW_SMEM ? (size_t)TW_F4 * sizeof(float4) : 0);
 };

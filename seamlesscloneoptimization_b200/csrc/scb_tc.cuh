@@ -15,7 +15,10 @@
 //      (cvt.rna.tf32.f32); D += a_hi s_hi + a_lo s_hi + a_hi s_lo with FP32 accumulation in TMEM.  The
 //      dropped a_lo s_lo term is 2^-22 relative.  Measured end to end (profiles/, tests): the final image
 //      matches cv2.seamlessClone exactly as often as a float64 solve does.
-//  (3) The exact low-frequency refinement of the FFT engine is kept unchanged.
+//  (3) The exact low-frequency refinement of the FFT engine (lowfreq_rows / lowfreq_cols kernels) is kept unchanged.
+//
+// Superseded as the tensor-core path by the exact INT8 engine (scb_i8.h): FP32 accumulation in TMEM truncates at every MMA step,
+// ~1e-5 relative at K ~ 900, which costs 0.2-0.3 % of exactly matching bytes.  Kept selectable (SCB_ENGINE_TC) for comparison.
 //
 // One pass = one kernel:  out = epilogue( fold(in) x basis ).
 //   CTA tile : 128 lines (UMMA M) x NT output bins of one parity (UMMA N <= 256), K loop over the folded line.
