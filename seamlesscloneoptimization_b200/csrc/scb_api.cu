@@ -997,29 +997,60 @@ struct MaskScan {
 };
 static MaskScan scan_rows(const scb_image* m, int y0, int y1) {
     const uint64_t K = 0x9E3779B97F4A7C15ull, M01 = 0x0101010101010101ull;
-    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    uint64_t h0 = 0x243F6A8885A308D3ull, h1 = 0x13198A2E03707344ull, h2 = 0xA4093822299F31D0ull, h3 = 0x082EFA98EC4E6C89ull;
     MaskScan r;
-    const int cols = m->cols, nw = (cols + 7) / 8;
+    const int cols = m->cols, nw = (cols + 7) / 8, nfull = cols / 8;
+    const int wl = (cols - 1) / 8;                                    // the word that holds column cols-1 (ring)
+    const uint64_t last_mask = ~(0xFFull << (8 * ((cols - 1) & 7)));
     for (int y = y0; y < y1; ++y) {
         const unsigned char* row = (const unsigned char*)m->data + (size_t)y * m->stride;
         const bool inner = y > 0 && y < m->rows - 1;
         int first = -1, last_i = -1;
         uint64_t last_w = 0, grey = 0;
-        for (int i = 0; i < nw; ++i) {
-            uint64_t w = 0;
-            const int left = cols - 8 * i;
-            std::memcpy(&w, row + 8 * i, left >= 8 ? 8 : (size_t)left);
-            h[i & 3] = ((h[i & 3] ^ w) * K) ^ (h[i & 3] >> 29);
-            if (!inner || !w) continue;
-            if (i == 0) w &= ~0xFFull;                                          // column 0 belongs to the ring
-            if (8 * i + 7 >= cols - 1) w &= ~(0xFFull << (8 * (cols - 1 - 8 * i)));  // so does column cols-1
-            if (!w) continue;
+        auto visit = [&](int i, uint64_t w) {  // bounding box / grey flag of one word of an inner row
+            if (i == 0) w &= ~0xFFull;         // column 0 belongs to the ring
+            if (i == wl) w &= last_mask;       // so does column cols-1
+            if (!w) return;
             if (first < 0) first = 8 * i + (__builtin_ctzll(w) >> 3);
             last_i = i;
             last_w = w;
             grey |= w ^ (((w >> 7) & M01) * 0xFFull);  // a byte is 0 or 255 iff it equals its top bit spread over the byte
+        };
+        int i = 0;
+        for (; i + 4 <= nfull; i += 4) {  // 32 bytes per step, four independent multiply-xor chains
+            uint64_t w[4];
+            std::memcpy(w, row + 8 * i, 32);
+            h0 = ((h0 ^ w[0]) * K) ^ (h0 >> 29);
+            h1 = ((h1 ^ w[1]) * K) ^ (h1 >> 29);
+            h2 = ((h2 ^ w[2]) * K) ^ (h2 >> 29);
+            h3 = ((h3 ^ w[3]) * K) ^ (h3 >> 29);
+            if (inner && (w[0] | w[1] | w[2] | w[3])) {
+                if (i == 0 || i + 3 >= wl) {  // the blocks that touch the ring columns: word by word
+                    visit(i, w[0]);
+                    visit(i + 1, w[1]);
+                    visit(i + 2, w[2]);
+                    visit(i + 3, w[3]);
+                } else {
+                    if (first < 0) {
+                        const int k = w[0] ? 0 : (w[1] ? 1 : (w[2] ? 2 : 3));
+                        first = 8 * (i + k) + (__builtin_ctzll(w[k]) >> 3);
+                    }
+                    const int k = w[3] ? 3 : (w[2] ? 2 : (w[1] ? 1 : 0));
+                    last_i = i + k;
+                    last_w = w[k];
+                    grey |= (w[0] ^ (((w[0] >> 7) & M01) * 0xFFull)) | (w[1] ^ (((w[1] >> 7) & M01) * 0xFFull)) | (w[2] ^ (((w[2] >> 7) & M01) * 0xFFull)) |
+                            (w[3] ^ (((w[3] >> 7) & M01) * 0xFFull));
+                }
+            }
         }
-        h[0] = ((h[0] ^ (uint64_t)y) * K) ^ (h[0] >> 31);
+        for (; i < nw; ++i) {  // the last words of the row (the very last one may be partial)
+            uint64_t w = 0;
+            const int left = cols - 8 * i;
+            std::memcpy(&w, row + 8 * i, left >= 8 ? 8 : (size_t)left);
+            h0 = ((h0 ^ w) * K) ^ (h0 >> 29);
+            if (inner && w) visit(i, w);
+        }
+        h1 = ((h1 ^ (uint64_t)y) * K) ^ (h1 >> 31);
         if (first >= 0) {
             const int last = 8 * last_i + 7 - (__builtin_clzll(last_w) >> 3);
             if (first < r.minx) r.minx = first;
@@ -1029,7 +1060,7 @@ static MaskScan scan_rows(const scb_image* m, int y0, int y1) {
             if (grey) r.grey = 1;
         }
     }
-    r.hash = ((h[0] * K) ^ h[1]) * K ^ ((h[2] * K) ^ h[3]);
+    r.hash = ((h0 * K) ^ h1) * K ^ ((h2 * K) ^ h3);
     return r;
 }
 static int host_threads();
