@@ -857,6 +857,7 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
     if ((e = (cudaError_t)i8_configure()) != cudaSuccess) return bail("cudaFuncSetAttribute of the INT8 tensor-core kernels", e);
 #ifndef SCB_EMU
     if ((e = cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess) return bail("cudaFuncSetAttribute(tc_pass_kernel)", e);
+    if ((e = cudaFuncSetAttribute(tri_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemLimit)) != cudaSuccess) return bail("cudaFuncSetAttribute(tri_solve_smem_kernel)", e);
 #endif
     if (ensure_bbox_slots(c, 1) != SCB_OK) {
         g_create_error = c->err;
@@ -1828,6 +1829,7 @@ static TriLowParams tri_low_params(scb_plan* p, const Frame& f, const float* A, 
     l.y1 = y1;
     return l;
 }
+static constexpr bool kTriSmemDefault = false;    // tri_solve_smem_kernel for whole solves whose tile fits
 static TriSolveParams tri_solve_params(scb_plan* p, const Frame& f, const float* A, float* Ct, double* Y64) {
     TriSolveParams t;
     t.tab = p->tri;
@@ -1846,7 +1848,28 @@ static TriSolveParams tri_solve_params(scb_plan* p, const Frame& f, const float*
     t.ends64 = nullptr;
     return t;
 }
+// The whole solve in one launch (phase 0) runs out of shared memory when the column tile of a CTA fits (tri_solve_smem_kernel:
+// ny <= ~3000 with 16 columns); longer columns and the row-sharded phases walk global memory (tri_solve_kernel).
+// SCB_TRI_SMEM=0/1 overrides the default (A/B checks).
 static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
+    static const bool smem_on = [] {
+        const char* e = std::getenv("SCB_TRI_SMEM");
+        return e ? std::atoi(e) != 0 : kTriSmemDefault;
+    }();
+    if (smem_on && t.phase == 0 && t.x0 == 0 && t.x1 == t.nx) {
+        int tables = 1;
+        size_t bytes = tri_smem_bytes(t.ny, true, kTriSmemLimit);
+        if (!bytes) {
+            tables = 0;
+            bytes = tri_smem_bytes(t.ny, false, kTriSmemLimit);
+        }
+        if (bytes) {
+            const int nfloat = t.nx > kTriLowK ? (t.nx - kTriLowK + kTriCols - 1) / kTriCols : 0;
+            SCB_LAUNCH(tri_solve_smem_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, p->lane->stream, t, tables);
+            p->ctx->launches++;
+            return;
+        }
+    }
     SCB_LAUNCH(tri_solve_kernel, dim3((t.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
     p->ctx->launches++;
 }
@@ -1923,6 +1946,7 @@ static bool i8_fused_rhs(const scb_plan* p) {
     }();
     return p->use_i8 && p->mode == SCB_NORMAL_CLONE && !p->debug && !off;
 }
+static constexpr int kRhsFoldDefault = 1;  // 1: rhs_fold_kernel<2>, 2: rhs_fold2_kernel (packed 16-bit lanes) for binary masks
 static void run_rhs_fold(scb_plan* p, const StencilSrc& st, const Workspace& w, int y0, int y1) {
     NvtxRange nvtx_("scb:rhs_fold");
     const scb_geometry& g = p->g;
@@ -1941,8 +1965,14 @@ static void run_rhs_fold(scb_plan* p, const StencilSrc& st, const Workspace& w, 
     const int rows = (y1 >= g.ny ? (f.m_rows + 2) / 3 : y1) - y0;  // the last range also writes the zero pad lines up to the last whole tile
     if (rows <= 0) return;
     const dim3 grid((f.kpad / 4 + kRhsThreads - 1) / kRhsThreads, rows);
+    static const int variant = [] {  // SCB_RHS_FOLD=1: rhs_fold_kernel<2> for binary masks too (A/B checks)
+        const char* e = std::getenv("SCB_RHS_FOLD");
+        return e ? std::atoi(e) : kRhsFoldDefault;
+    }();
     if (p->grey_mask)
         SCB_LAUNCH(rhs_fold_kernel<4>, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
+    else if (variant == 2)
+        SCB_LAUNCH(rhs_fold2_kernel, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
     else
         SCB_LAUNCH(rhs_fold_kernel<2>, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
     p->ctx->launches++;

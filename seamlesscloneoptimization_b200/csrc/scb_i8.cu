@@ -803,6 +803,233 @@ i8_gemm_pkernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The persistent kernel on 128-line x 128-output tiles (SCB_I8_PERSISTENT=2).  What bounds i8_gemm_pkernel is the operand stream
+// into shared memory (~33 B/clk/SM = 9 TB/s chip-wide out of L2, profiles/r2_i8_variants.txt), not the tensor pipe: per 64 outputs it
+// re-reads the digit tiles of its 128 lines.  Two 64-output sub-blocks per tile share those tiles: 0.75 x (forward) / 0.64 x (inverse)
+// of the bytes per MAC.  The price: the accumulators of one tile (2 sub-blocks x 4 classes x 64 columns) fill all 512 TMEM columns,
+// so there is no second set -- the epilogue of tile t is NOT hidden under the MMAs of tile t+1 (the TMA producer still runs ahead
+// through the stage ring, and the other SMs' main loops keep the L2 busy meanwhile).
+//   tiles : t -> (group g = t / mt, line tile m = t % mt);  group = (parity, PAIR of sub-blocks); the second sub-block of the last
+//           pair of a parity may hold no outputs: its MMAs and its epilogue are skipped.
+//   epilogue warp (q, u): TMEM lane quarter q, sub-block u -- 32 lines x 64 outputs: all 64 class-sum quadruples -> 64 floats in
+//           registers, hand the accumulators back, then two 32 x 32 transposes through the warp's shared-memory tile and the stores.
+// ---------------------------------------------------------------------------------------------
+template <int DA, int DB, int KB>
+struct I8P2Cfg {
+    static constexpr size_t A_DIGIT = (size_t)kI8M * KB;
+    static constexpr size_t A_BYTES = (size_t)DA * A_DIGIT;
+    static constexpr size_t B_PLANE = (size_t)kI8P * KB;
+    static constexpr size_t B_SUB = (size_t)DB * B_PLANE;
+    static constexpr size_t STAGE = A_BYTES + 2 * B_SUB;
+    static constexpr int OUT_PITCH = 33;                                                        // floats per row of a warp's 32 x 32 transpose tile
+    static constexpr size_t OUT_BYTES = (size_t)kI8EpiWarps * 32 * OUT_PITCH * sizeof(float);   // 33 KB
+    static constexpr size_t BUDGET = (size_t)232448 - OUT_BYTES - 1024 - 256;
+    static constexpr int STAGES = (int)(BUDGET / STAGE) > 6 ? 6 : (int)(BUDGET / STAGE);
+    static constexpr size_t SMEM = STAGES * STAGE + OUT_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    static_assert(STAGE % 1024 == 0 && OUT_BYTES % 1024 == 0, "stages stay 1024-byte aligned");
+    static_assert(STAGES >= 2, "at least two pipeline stages");
+    static_assert(SMEM <= 232448, "shared memory budget of one CTA");
+};
+
+template <int DA, int DB, int KB>
+__global__ void __launch_bounds__(kI8Threads, 1)
+i8_gemm_p2kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, I8GemmParams p) {
+    using Cfg = I8P2Cfg<DA, DB, KB>;
+    constexpr int S = Cfg::STAGES;
+    constexpr unsigned kSubCols = (unsigned)(kI8Classes * kI8P);  // TMEM columns of one sub-block's accumulators
+    extern __shared__ unsigned char i8_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(((size_t)i8_smem_raw + 1023) & ~(size_t)1023);
+    float* outbuf = reinterpret_cast<float*>(base + (size_t)S * Cfg::STAGE);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + (size_t)S * Cfg::STAGE + Cfg::OUT_BYTES);
+    const unsigned bar0 = i8_smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (S + s); };
+    const unsigned acc_full = bar0 + 8u * (2 * S), acc_empty = bar0 + 8u * (2 * S + 1);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * S + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = p.mt1 - p.mt0;
+    const int nsbr0 = (p.g.nout[0] + kI8P - 1) / kI8P, nsbr1 = (p.g.nout[1] + kI8P - 1) / kI8P;
+    const int np0 = (nsbr0 + 1) / 2, np1 = (nsbr1 + 1) / 2;  // pairs of sub-blocks per parity (the table holds an even number of sub-blocks)
+    const int units = (np0 + np1) * mt;
+    const int first_unit = (int)blockIdx.x, unit_step = (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&amap) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&bmap) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            i8_mbar_init(full(s), 1);
+            i8_mbar_init(empty(s), 1);
+        }
+        i8_mbar_init(acc_full, 1);              // tcgen05.commit of the tile's last MMA
+        i8_mbar_init(acc_empty, kI8EpiWarps);   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    i8_fence_before();
+    __syncthreads();
+    i8_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    // unit -> parity, first sub-block of the pair, how many of the pair's sub-blocks hold outputs, first line of the tile
+    auto decode = [&](int unit, int& par, int& sb0, int& nu, int& m0) {
+        const int g = unit / mt, mu = unit - g * mt;
+        par = g >= np0 ? 1 : 0;
+        sb0 = 2 * (par ? g - np0 : g);
+        nu = (sb0 + 1 < (par ? nsbr1 : nsbr0)) ? 2 : 1;
+        m0 = (p.mt0 + mu) * kI8M;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer: DA digit tiles of the lines + the DB planes of both sub-blocks per k-block; runs ahead over tile boundaries =====
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int unit = first_unit; unit < units; unit += unit_step) {
+                int par, sb0, nu, m0;
+                decode(unit, par, sb0, nu, m0);
+                const int num_kb = (p.g.kpar[par] + KB - 1) / KB;
+                const int rowb = ((par * p.g.nsb + sb0) * kI8BasisDigits) * kI8P;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    i8_mbar_wait(empty(s), ((it / S) & 1) ^ 1);
+                    i8_mbar_expect_tx(full(s), (unsigned)Cfg::STAGE);  // the empty second sub-block of a last pair is loaded too (zero planes): one byte count
+                    unsigned char* st = base + (size_t)s * Cfg::STAGE;
+                    SCB_UNROLL
+                    for (int i = 0; i < DA; ++i) i8_tma_2d(i8_smem_u32(st + (size_t)i * Cfg::A_DIGIT), &amap, kb * KB, (par * DA + i) * p.m_rows + m0, full(s));
+                    SCB_UNROLL
+                    for (int u = 0; u < 2; ++u)
+                        i8_tma_2d(i8_smem_u32(st + Cfg::A_BYTES + (size_t)u * Cfg::B_SUB), &bmap, kb * KB, rowb + u * kI8BasisDigits * kI8P, full(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: per 32-element k-step and sub-block, one MMA per digit of the lines against its planes =====
+        if (lane == 0) {
+            unsigned idesc[kI8Classes + 1];
+            SCB_UNROLL
+            for (int c = 1; c <= kI8Classes; ++c) idesc[c] = i8_idesc(kI8P * c);
+            unsigned it = 0;
+            int lt = 0;
+            for (int unit = first_unit; unit < units; unit += unit_step, ++lt) {
+                int par, sb0, nu, m0;
+                decode(unit, par, sb0, nu, m0);
+                const int kpar = p.g.kpar[par];
+                const int num_kb = (kpar + KB - 1) / KB;
+                i8_mbar_wait(acc_empty, (lt & 1) ^ 1);  // the epilogue has drained the accumulators of the previous tile (passes at once the first time)
+                i8_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    i8_mbar_wait(full(s), (it / S) & 1);
+                    i8_fence_after();
+                    const unsigned st = i8_smem_u32(base + (size_t)s * Cfg::STAGE);
+                    const int left = kpar - kb * KB;
+                    const int nks = left >= KB ? KB / 32 : (left + 31) / 32;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const unsigned long long o = (unsigned long long)(ks * 2);  // 32 bytes of K = 2 x 16-byte units of the start address
+                        const bool first = (kb | ks) == 0;
+                        for (int u = 0; u < nu; ++u) {
+                            const unsigned tm = tmem_base + (unsigned)u * kSubCols;
+                            const unsigned long long bd = i8_desc<KB>(st + (unsigned)(Cfg::A_BYTES + (size_t)u * Cfg::B_SUB)) + o;
+                            auto digit = [&](int i, unsigned acc) {
+                                const int cnt = i8_plane_count(i, DB);
+                                i8_mma(tm + (unsigned)(i * kI8P), i8_desc<KB>(st + (unsigned)((size_t)i * Cfg::A_DIGIT)) + o, bd, idesc[cnt], acc);
+                            };
+                            if (DB < kI8Classes && first) digit(DA - 1, 0u);  // see i8_gemm_kernel: class 3 is first written by the last digit
+                            digit(0, first ? 0u : 1u);
+                            SCB_UNROLL
+                            for (int i = 1; i < DA; ++i)
+                                if (!(DB < kI8Classes && first && i == DA - 1)) digit(i, 1u);
+                        }
+                    }
+                    i8_commit(empty(s));
+                }
+                i8_commit(acc_full);
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps, warp = (TMEM lane quarter q, sub-block u) =====
+        constexpr int OP = Cfg::OUT_PITCH;
+        const int q = warp & 3, u = (warp - 2) >> 2;
+        float* tile = outbuf + (size_t)(warp - 2) * 32 * OP;
+        int lt = 0;
+        for (int unit = first_unit; unit < units; unit += unit_step, ++lt) {
+            int par, sb0, nu, m0;
+            decode(unit, par, sb0, nu, m0);
+            const int sb = sb0 + u;
+            const int nout = p.g.nout[par];
+            const int line = m0 + 32 * q + lane;
+            const float ls = line < p.m_rows ? __ldg(p.lscale + line) : 0.f;
+            const float sc = p.scale * ls;
+            const bool live = u < nu;
+            float vals[kI8P];
+            i8_mbar_wait(acc_full, lt & 1);
+            i8_fence_after();
+            if (live) {
+                const unsigned tmq = tmem_base + ((unsigned)(32 * q) << 16) + (unsigned)u * kSubCols;
+                SCB_UNROLL
+                for (int cc = 0; cc < kI8P; cc += 16) {
+                    int w0[16], w1[16], w2[16], w3[16];
+                    i8_tmem_ld16(tmq + (unsigned)(0 * kI8P + cc), w0);
+                    i8_tmem_ld16(tmq + (unsigned)(1 * kI8P + cc), w1);
+                    i8_tmem_ld16(tmq + (unsigned)(2 * kI8P + cc), w2);
+                    i8_tmem_ld16(tmq + (unsigned)(3 * kI8P + cc), w3);
+                    i8_tmem_wait_ld();
+                    SCB_UNROLL
+                    for (int i = 0; i < 16; ++i) vals[cc + i] = i8_combine(w0[i], w1[i], w2[i], w3[i]) * sc;
+                    if (cc == 0 && p.R && sb == 0 && line >= p.line0 && line < p.line1) {  // exact float64 row sums of the lowest frequencies
+                        const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
+                        SCB_UNROLL
+                        for (int i = 0; i < (kI8LowK + 1) / 2; ++i) {
+                            const int k0 = 2 * i + par;
+                            if (k0 < p.lowk && i < nout) p.R[((size_t)c * p.lowk + k0) * p.lpc + r] = i8_combine_exact(w0[i], w1[i], w2[i], w3[i]) * (p.rscale * (double)ls);
+                        }
+                    }
+                }
+            }
+            // the accumulators are in registers now: hand them back to the MMA issuer before the stores
+            i8_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty) : "memory");
+            if (live) {
+                SCB_UNROLL
+                for (int h = 0; h < 2; ++h) {  // two 32-column halves through the warp's transpose tile
+                    SCB_UNROLL
+                    for (int i = 0; i < 32; ++i) tile[(size_t)lane * OP + i] = vals[32 * h + i];
+                    __syncwarp();
+                    int ln = m0 + 32 * q;
+                    int rr = ln / 3, c = ln - 3 * rr;
+                    const int ki = sb * kI8P + 32 * h + lane;
+                    for (int r = 0; r < 32 && ln < p.line1; ++r, ++ln) {
+                        if (ki < nout && ln >= p.line0) {
+                            const float v = tile[(size_t)r * OP + lane];
+                            if (p.out_u8)
+                                p.out_u8[(long long)rr * p.out_u8_pitch + 3 * (2 * ki + par) + c] = i8_to_u8(v);
+                            else
+                                p.out[(size_t)c * p.out_plane + (size_t)rr * p.out_pitch + 2 * ki + par] = v;
+                        }
+                        if (++c == 3) {
+                            c = 0;
+                            ++rr;
+                        }
+                    }
+                    __syncwarp();  // the tile rows are free for the next half / the next tile
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        i8_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---- tensor maps -------------------------------------------------------------------------------
 typedef CUresult (*I8EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -917,6 +1144,35 @@ static int i8_launch_gemm_p(void* stream, const I8GemmParams& p) {
     cfg.gridDim = dim3(clusters * CL);
     return (int)cudaLaunchKernelEx(&cfg, i8_gemm_pkernel<DA, DB, KB, CL>, amap, bmap, p);
 }
+// 128 x 128-output tiles (i8_gemm_p2kernel): one CTA per SM, as many as there are tiles
+template <int DA, int DB, int KB>
+static int i8_launch_gemm_p2(void* stream, const I8GemmParams& p) {
+    using Cfg = I8P2Cfg<DA, DB, KB>;
+    CUtensorMap amap, bmap;
+    int rc;
+    if ((rc = i8_make_map(&amap, p.a, (size_t)2 * DA * p.m_rows, p.g.kpad, kI8M, KB))) return rc;
+    if ((rc = i8_make_map(&bmap, p.basis, i8_basis_rows(p.g), p.g.kpad, DB * kI8P, KB))) return rc;
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    const int mt = p.mt1 - p.mt0;
+    if (mt <= 0) return 0;
+    const int nsbr0 = (p.g.nout[0] + kI8P - 1) / kI8P, nsbr1 = (p.g.nout[1] + kI8P - 1) / kI8P;
+    const int units = ((nsbr0 + 1) / 2 + (nsbr1 + 1) / 2) * mt;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(units < sms ? units : sms);
+    cfg.blockDim = dim3(kI8Threads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    return (int)cudaLaunchKernelEx(&cfg, i8_gemm_p2kernel<DA, DB, KB>, amap, bmap, p);
+}
+template <int DA, int DB, int KB>
+static cudaError_t i8_set_smem_p2() {
+    return cudaFuncSetAttribute(i8_gemm_p2kernel<DA, DB, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8P2Cfg<DA, DB, KB>::SMEM);
+}
 template <int DA, int DB, int KB, int CL>
 static cudaError_t i8_set_smem_p() {
     return cudaFuncSetAttribute(i8_gemm_pkernel<DA, DB, KB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8PCfg<DA, DB, KB>::SMEM);
@@ -932,6 +1188,10 @@ static int i8_launch_gemm_t(void* stream, const I8GemmParams& p) {
     static const int cl = clp == 2 ? 2 : 1;
     static const int persistent = i8_env_int("SCB_I8_PERSISTENT", 1);
     static const int kb = i8_env_int("SCB_I8_KB", 128) == 64 ? 64 : 128;
+    if (persistent == 2) {  // 128 x 128-output tiles: the inverse pass (4 + 3 digits) only fits with 64-byte stage rows
+        if constexpr (DA == 2 && DB == 4) return kb == 64 ? i8_launch_gemm_p2<2, 4, 64>(stream, p) : i8_launch_gemm_p2<2, 4, 128>(stream, p);
+        if constexpr (DA == 4 && DB == 3) return i8_launch_gemm_p2<4, 3, 64>(stream, p);
+    }
     if (persistent) {
         if constexpr (!(DA == 4 && DB == 4)) {  // 4 + 4 digits: 96 KB per 128-byte-row stage, only the 64-byte rows leave two stages
             if (kb == 128) {
@@ -967,6 +1227,7 @@ static cudaError_t i8_set_smem_all() {
 }
 int i8_configure() {
     cudaError_t e;
+    if ((e = i8_set_smem_p2<2, 4, 128>()) != cudaSuccess || (e = i8_set_smem_p2<2, 4, 64>()) != cudaSuccess || (e = i8_set_smem_p2<4, 3, 64>()) != cudaSuccess) return (int)e;
     if ((e = i8_set_smem_all<2, 4>()) != cudaSuccess || (e = i8_set_smem_all<4, 4>()) != cudaSuccess || (e = i8_set_smem_all<4, 3>()) != cudaSuccess) return (int)e;
     return 0;
 }

@@ -446,6 +446,191 @@ __global__ void __launch_bounds__(kRhsThreads, 8) rhs_fold_kernel(RhsFoldParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// rhs_fold2_kernel: the binary-mask (DA = 2) stencil + fold + digit split entirely in packed 16-bit integer lanes (SCB_RHS_FOLD=2).
+// Same thread mapping, same bytes out as rhs_fold_kernel<2>; what changes is the instruction stream:
+//   * the twelve right-hand-side values of a quad stay in six words of two 16-bit lanes (value + 2048, byte order 3 pixel + channel)
+//     from the stencil to the digits -- no float conversion, no per-value int arithmetic;
+//   * the fold is one add and one subtract per word against the mirror quad (whose lanes are reversed pixel-wise by six
+//     16-bit funnel shifts), biased so that the lane holds f + 0x8080: XOR 0x8080 then leaves the two balanced base-256 digits of f in
+//     the lane's two bytes (balanced_digits4 in 16 bits), and four byte permutes per line and parity gather the digit words;
+//   * the two ends of the row and the thread that straddles the middle run the same quad code (border terms in the general path,
+//     lane masks for the elements past the middle) instead of a pixel-by-pixel path that made their whole warp ~4 x slower;
+//   * the mask words of both quads are fetched before either image, the image words of both quads together: two dependent
+//     memory round trips per thread instead of four.
+// Loads: the mid-row words of the quad at the right end of the row cover 2 bytes past the ROI row (pixel w); rows 1 .. h-2 are never
+// the last row of the image, so those bytes lie inside the caller's buffer (next pixel of the row, or the start of the next row).
+// ---------------------------------------------------------------------------------------------
+struct QuadTaps {
+    unsigned em[2], eu[1];
+    bool fast, src;
+};
+
+// mask taps of the quad at x0 (pixels x0 .. x0+3 of interior row y) and its classification
+SCB_D void quad_taps(const StencilSrc& s, int x0, int y, int n, QuadTaps& q) {
+    const int X = x0 + 1, Y = y + 1;
+    load_unaligned_words<2>(s.E + (long long)Y * s.e_pitch + (X - 1), q.em);
+    load_unaligned_words<1>(s.E + (long long)(Y - 1) * s.e_pitch + X, q.eu);
+    const unsigned m_and = q.em[0] & q.eu[0] & (q.em[1] | 0xffffff00u), m_or = q.em[0] | q.eu[0] | (q.em[1] & 0xffu);
+    q.src = (m_and == 0xffffffffu);
+    // one image only and no pixel of the quad on the ROI border: the 5-point Laplacian of that image
+    q.fast = (q.src || m_or == 0u) && x0 > 0 && x0 + 4 < n && Y > 1 && Y < s.h - 2;
+}
+
+struct QuadWords {
+    unsigned m[5], u[3], d[3];
+};
+SCB_D void quad_load(const unsigned char* img, long long pitch, int x0, int y, QuadWords& w) {
+    const int X = x0 + 1, Y = y + 1;
+    load_unaligned_words<5>(img + (long long)Y * pitch + 3 * (X - 1), w.m);
+    load_unaligned_words<3>(img + (long long)(Y - 1) * pitch + 3 * X, w.u);
+    load_unaligned_words<3>(img + (long long)(Y + 1) * pitch + 3 * X, w.d);
+}
+// 2048 + (l + r + u + d - 4 c) for the twelve bytes of the quad, two per word
+SCB_D void quad_fast_lanes(const QuadWords& w, unsigned (&t)[6]) {
+    SCB_UNROLL
+    for (int j = 0; j < 3; ++j) {
+        const unsigned l = w.m[j];                                          // bytes e-3
+        const unsigned c = __funnelshift_r(w.m[j], w.m[j + 1], 24);         // bytes e
+        const unsigned r = __funnelshift_r(w.m[j + 1], w.m[j + 2], 16);     // bytes e+3
+        SCB_UNROLL
+        for (int half = 0; half < 2; ++half) {
+            const unsigned sel = half ? 0x4342u : 0x4140u;  // two bytes -> two 16-bit lanes
+            unsigned v = 0x08000800u + __byte_perm(l, 0u, sel) + __byte_perm(r, 0u, sel) + __byte_perm(w.u[j], 0u, sel) + __byte_perm(w.d[j], 0u, sel);
+            v -= 4u * __byte_perm(c, 0u, sel);
+            t[2 * j + half] = v;
+        }
+    }
+}
+// any binary mask pattern and the ROI borders: integer arithmetic per pixel (rhs_quad's binary branch), packed into the same lanes
+SCB_D void quad_general_lanes(const StencilSrc& s, int x0, int y, const QuadTaps& q, unsigned (&t)[6]) {
+    const int X = x0 + 1, Y = y + 1;
+    QuadWords D, S;
+    quad_load(s.D, s.d_pitch, x0, y, D);
+    quad_load(s.S, s.s_pitch, x0, y, S);
+    SCB_UNROLL
+    for (int i = 0; i < 6; ++i) t[i] = 0u;
+    SCB_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        const int el = byte_of(q.em, k), ec = byte_of(q.em, k + 1), eup = byte_of(q.eu, k);
+        const int Xk = X + k;
+        SCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            const int Dl = byte_of(D.m, 3 * k + c), Dc = byte_of(D.m, 3 * k + 3 + c), Dr = byte_of(D.m, 3 * k + 6 + c);
+            const int Du = byte_of(D.u, 3 * k + c), Dd = byte_of(D.d, 3 * k + c);
+            const int Sl = byte_of(S.m, 3 * k + c), Sc = byte_of(S.m, 3 * k + 3 + c), Sr = byte_of(S.m, 3 * k + 6 + c);
+            const int Su = byte_of(S.u, 3 * k + c), Sd = byte_of(S.d, 3 * k + c);
+            int lap = (ec ? (Sr - Sc) + (Sd - Sc) : (Dr - Dc) + (Dd - Dc)) - (el ? (Sc - Sl) : (Dc - Dl)) - (eup ? (Sc - Su) : (Dc - Du));
+            if (Xk == 1) lap -= Dl;
+            if (Xk == s.w - 2) lap -= Dr;
+            if (Y == 1) lap -= Du;
+            if (Y == s.h - 2) lap -= Dd;
+            const int b = 3 * k + c;
+            t[b >> 1] += (unsigned)(2048 + lap) << (16 * (b & 1));  // |lap| <= 1530
+        }
+    }
+}
+
+#ifndef SCB_RHS2_MIN_CTAS
+#define SCB_RHS2_MIN_CTAS 6  // 80 registers; 8 would cap them at 64
+#endif
+__global__ void __launch_bounds__(kRhsThreads, SCB_RHS2_MIN_CTAS) rhs_fold2_kernel(RhsFoldParams p) {
+    constexpr int DA = 2;
+    const int y = p.y0 + blockIdx.y;
+    const int j0 = 4 * (blockIdx.x * kRhsThreads + threadIdx.x);
+    if (j0 >= p.kpad) return;
+    const int n = p.nx, h = n >> 1;
+    unsigned lo[2][3], hi[2][3];  // [parity][channel]: the four low / high digits of the folded elements j0 .. j0+3
+    SCB_UNROLL
+    for (int q = 0; q < 2; ++q)
+        SCB_UNROLL
+        for (int c = 0; c < 3; ++c) lo[q][c] = hi[q][c] = 0u;
+    if (y < p.ny && j0 < p.kpar0) {
+        const StencilSrc& s = p.st;
+        const int xa = j0, xb = n - 4 - j0;  // the quad and its mirror image (for the straddling thread they overlap: masked below)
+        QuadTaps qa, qb;
+        quad_taps(s, xa, y, n, qa);
+        quad_taps(s, xb, y, n, qb);
+        unsigned ta[6], tm[6];
+        if (qa.fast && qb.fast) {
+            QuadWords wa, wb;
+            quad_load(qa.src ? s.S : s.D, qa.src ? s.s_pitch : s.d_pitch, xa, y, wa);
+            quad_load(qb.src ? s.S : s.D, qb.src ? s.s_pitch : s.d_pitch, xb, y, wb);
+            quad_fast_lanes(wa, ta);
+            quad_fast_lanes(wb, tm);
+        } else {
+            if (qa.fast) {
+                QuadWords wa;
+                quad_load(qa.src ? s.S : s.D, qa.src ? s.s_pitch : s.d_pitch, xa, y, wa);
+                quad_fast_lanes(wa, ta);
+            } else {
+                quad_general_lanes(s, xa, y, qa, ta);
+            }
+            if (qb.fast) {
+                QuadWords wb;
+                quad_load(qb.src ? s.S : s.D, qb.src ? s.s_pitch : s.d_pitch, xb, y, wb);
+                quad_fast_lanes(wb, tm);
+            } else {
+                quad_general_lanes(s, xb, y, qb, tm);
+            }
+        }
+        // mirror quad, pixels reversed: lane 3 e + c  <-  lane 3 (3 - e) + c
+        unsigned tr[6];
+        tr[0] = __funnelshift_r(tm[4], tm[5], 16);  // lanes  9, 10
+        tr[1] = __funnelshift_r(tm[5], tm[3], 16);  // lanes 11,  6
+        tr[2] = __funnelshift_r(tm[3], tm[4], 16);  // lanes  7,  8
+        tr[3] = __funnelshift_r(tm[1], tm[2], 16);  // lanes  3,  4
+        tr[4] = __funnelshift_r(tm[2], tm[0], 16);  // lanes  5,  0
+        tr[5] = __funnelshift_r(tm[0], tm[1], 16);  // lanes  1,  2
+        unsigned mid_mask[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (j0 + 3 >= h) {  // the thread that straddles the middle: element j >= h is zero, except the middle of an odd line (f0 = g[h], f1 = 0)
+            SCB_UNROLL
+            for (int L = 0; L < 12; ++L) {
+                const int j = j0 + L / 3;
+                const unsigned lane = 0xffffu << (16 * (L & 1));
+                const bool is_mid = (j == h) && (n & 1);
+                if (j >= h) {
+                    tr[L >> 1] = (tr[L >> 1] & ~lane) | (0x08000800u & lane);
+                    if (is_mid)
+                        mid_mask[L >> 1] |= lane;
+                    else
+                        ta[L >> 1] = (ta[L >> 1] & ~lane) | (0x08000800u & lane);
+                }
+            }
+        }
+        // lanes hold value + 2048:  f0 + 0x8080 = ta + tr + 0x7080,  f1 + 0x8080 = ta - tr + 0x8080;  XOR 0x8080 -> the two balanced digits
+        unsigned x0w[6], x1w[6];
+        SCB_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            x0w[i] = (ta[i] + tr[i] + 0x70807080u) ^ 0x80808080u;
+            x1w[i] = (((ta[i] + 0x80808080u) - tr[i]) ^ 0x80808080u) & ~mid_mask[i];  // digits of zero are zero bytes
+        }
+        SCB_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            // lanes c, 3+c | 6+c, 9+c: elements 0, 1 | 2, 3 of channel c
+            const unsigned sel = (c == 1) ? 0x5432u : 0x7610u;
+            const int wA = c >> 1, wB = (3 + c) >> 1, wC = (6 + c) >> 1, wD = (9 + c) >> 1;
+            const unsigned p0 = __byte_perm(x0w[wA], x0w[wB], sel), q0 = __byte_perm(x0w[wC], x0w[wD], sel);
+            const unsigned p1 = __byte_perm(x1w[wA], x1w[wB], sel), q1 = __byte_perm(x1w[wC], x1w[wD], sel);
+            lo[0][c] = __byte_perm(p0, q0, 0x6420u);
+            hi[0][c] = __byte_perm(p0, q0, 0x7531u);
+            lo[1][c] = __byte_perm(p1, q1, 0x6420u);
+            hi[1][c] = __byte_perm(p1, q1, 0x7531u);
+        }
+    }
+    SCB_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        const int line = 3 * y + c;
+        if (line >= p.m_rows) continue;
+        if (j0 == 0) p.lscale[line] = 1.0f / p.scale;
+        SCB_UNROLL
+        for (int q = 0; q < 2; ++q) {
+            *reinterpret_cast<unsigned*>(p.planes + ((size_t)(q * DA + 0) * p.m_rows + line) * p.kpad + j0) = hi[q][c];
+            *reinterpret_cast<unsigned*>(p.planes + ((size_t)(q * DA + 1) * p.m_rows + line) * p.kpad + j0) = lo[q][c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The other cv::seamlessClone flags: the same solver behind a different gradient selection
 // (Cloning::normalClone in OpenCV's seamless_cloning_impl.cpp).
 //   MIXED_CLONE          per pixel and channel, the patch gradient PAIR is replaced by dst's unless

@@ -127,17 +127,63 @@ struct TriSolveParams {
 template <class T>
 struct TriIo;  // global-memory views of one column: a(y), v/u(y) and the tables
 
-template <class T, class LoadA, class LoadM, class LoadP, class LoadV, class StoreV>
+// INPLACE: a and v share their storage (tri_solve_smem_kernel's shared-memory tile): the upward sweep, which needs the original a,
+// runs to its end before the downward sweep overwrites a with v.  Each chain is the same sequence of operations either way, so
+// the results are bit-identical to the fused loop.  store_u receives the final solution of pass 2 (store_v: pass 1's v).
+template <class T, bool INPLACE, class LoadA, class LoadM, class LoadP, class LoadV, class StoreV, class StoreU>
 SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][kTriSegs][kTriCols] */, const LoadA& load_a, const LoadM& load_m, const LoadP& load_p,
-                        const LoadV& load_v, const StoreV& store_v, bool active, int phase, int seg0, int seg1, T* ends /* global [kTriSegs][2][estride] + column, or null */,
-                        size_t estride) {
+                        const LoadV& load_v, const StoreV& store_v, const StoreU& store_u, bool active, int phase, int seg0, int seg1,
+                        T* ends /* global [kTriSegs][2][estride] + column, or null */, size_t estride) {
     const int r0 = seg * L;
     const bool mine = seg >= seg0 && seg < seg1 && seg < nseg;
     const int len = mine ? ((n - r0 < L) ? n - r0 : L) : 0;
     T* wl = sm + (0 * kTriSegs + seg) * kTriCols + lane;
     T* wf = sm + (1 * kTriSegs + seg) * kTriCols + lane;
     // ---- pass 1 ----
-    if (active && len > 0 && phase != 2) {
+    if (INPLACE && active && len > 0 && phase != 2) {
+        T b = load_a(r0 + len - 1);
+        int d = 1;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            T ab[kTriUnroll], mm[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                ab[i] = load_a(r0 + len - 1 - d - i);
+                mm[i] = load_m(d + i - 1);
+            }
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) b = mm[i] * b + ab[i];
+        }
+        for (; d < len; ++d) b = load_m(d - 1) * b + load_a(r0 + len - 1 - d);
+        T v = load_a(r0);
+        store_v(r0, v);
+        d = 1;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            T av[kTriUnroll], mm[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                av[i] = load_a(r0 + d + i);
+                mm[i] = load_m(d + i - 1);
+            }
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                v = mm[i] * v + av[i];
+                store_v(r0 + d + i, v);
+            }
+        }
+        for (; d < len; ++d) {
+            v = load_m(d - 1) * v + load_a(r0 + d);
+            store_v(r0 + d, v);
+        }
+        const T ml = load_m(len - 1);
+        if (phase == 1) {
+            ends[((size_t)seg * 2 + 0) * estride] = ml * v;
+            ends[((size_t)seg * 2 + 1) * estride] = ml * b;
+        } else {
+            *wl = ml * v;
+            *wf = ml * b;
+        }
+    }
+    if (!INPLACE && active && len > 0 && phase != 2) {
         T v = load_a(r0), b = load_a(r0 + len - 1);
         store_v(r0, v);
         int d = 1;
@@ -235,12 +281,12 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
             SCB_UNROLL
             for (int i = 0; i < kTriUnroll; ++i) {
                 u = mm[i] * (u + (pp[i] * alpha + vv[i]));
-                store_v(r0 + d - i, u);
+                store_u(r0 + d - i, u);
             }
         }
         for (; d >= 0; --d) {
             u = load_m(d) * (u + (load_p(d) * alpha + load_v(r0 + d)));
-            store_v(r0 + d, u);
+            store_u(r0 + d, u);
         }
     }
 }
@@ -261,27 +307,142 @@ __global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_kernel(TriSolve
         double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
         const double* m = p.tab.m64 + k;
         const double* P = p.tab.p64 + k;
-        tri_segments<double>(
+        const auto store = [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; };
+        tri_segments<double, false>(
             n, L, seg, nseg, lane, sm_raw,
             [&](int y) { return (double)__ldg(A + (size_t)y * p.nx); },
             [&](int d) { return __ldg(m + (size_t)d * kTriLowK); },
             [&](int d) { return __ldg(P + (size_t)d * kTriLowK); },
-            [&](int y) { return Y[(size_t)y * kTriLowK]; },
-            [&](int y, double v) { Y[(size_t)y * kTriLowK] = v; }, active, p.phase, p.seg0, p.seg1,
+            [&](int y) { return Y[(size_t)y * kTriLowK]; }, store, store, active, p.phase, p.seg0, p.seg1,
             p.ends64 ? p.ends64 + (size_t)c * kTriSegs * 2 * kTriLowK + k : nullptr, (size_t)kTriLowK);
     } else {
         const float* m = p.tab.m32 + k;
         const float* P = p.tab.p32 + k;
         const int pm = p.tab.pm;
-        tri_segments<float>(
+        const auto store = [&](int y, float v) { Ct[(size_t)y * p.nx] = v; };
+        tri_segments<float, false>(
             n, L, seg, nseg, lane, reinterpret_cast<float*>(sm_raw),
             [&](int y) { return __ldg(A + (size_t)y * p.nx); },
             [&](int d) { return __ldg(m + (size_t)d * pm); },
             [&](int d) { return __ldg(P + (size_t)d * pm); },
-            [&](int y) { return Ct[(size_t)y * p.nx]; },
-            [&](int y, float v) { Ct[(size_t)y * p.nx] = v; }, active, p.phase, p.seg0, p.seg1,
+            [&](int y) { return Ct[(size_t)y * p.nx]; }, store, store, active, p.phase, p.seg0, p.seg1,
             p.ends32 ? p.ends32 + (size_t)c * kTriSegs * 2 * pm + k : nullptr, (size_t)pm);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tri_solve_smem_kernel (SCB_TRI_SMEM=1): the same partitioned solve with the CTA's column tile held in SHARED MEMORY.
+// tri_solve_kernel walks global memory row by row -- 3 dependent-latency loads per row and pass, v written out and read back: a chain
+// of ~2 ny / kTriSegs L2 round trips per thread with ~18 warps per SM (latency bound, profiles/r2_final_ncu_full_cfg2.txt).  Here
+// every thread first copies the rows of its own segment into the tile (independent loads, all in flight together), both sweeps of
+// pass 1 and the reduced system then run out of shared memory (29-cycle loads), and pass 2 streams the solution straight to global
+// memory: A is read once and Ct written once (8 B per unknown instead of 24), and the dependent chain never leaves the SM.
+//   CTA tile : float columns k >= kTriLowK: kTriCols columns;  float64 columns: 8 (so that both kinds need ~the same shared memory
+//              and two CTAs fit an SM);  rows of a segment are contiguous, consecutive segments sit an odd multiple of 16 words apart
+//              (the two segments of a warp hit disjoint banks)
+//   tables   : the tile's columns of m / P, (seg_len + 1) rows, in shared memory too when they fit (tab_smem)
+// Same arithmetic, operation for operation, as tri_solve_kernel (tri_segments<T, INPLACE = true>): bit-identical results
+// (tests/test_tri_smem.py).  One launch = the whole solve (phase 0, x0 = 0); the row-sharded phases stay on tri_solve_kernel.
+// grid = (kTriLowK / 8 + ceil((nx - kTriLowK) / kTriCols), 3), block = kTriCols x kTriSegs, dynamic smem = tri_smem_bytes()
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTriCols64 = 8;  // columns per CTA of the float64 block
+static constexpr size_t kTriSmemLimit = 232448;  // opt-in dynamic shared memory of one CTA on sm_100
+
+SCB_HD int tri_smem_seg_stride(int L, int ncol, int elem_bytes) {  // elements between the tiles of consecutive segments
+    const int e = L * ncol;
+    return (elem_bytes == 4 && ncol == 16 && (e % 32) == 0) ? e + 16 : e;
+}
+// dynamic shared memory of one CTA: reduced-system scratch + (tables) + tile, for the larger of the two CTA kinds; 0 = does not fit
+SCB_HD size_t tri_smem_bytes(int ny, bool tables, size_t limit = kTriSmemLimit) {
+    const int L = tri_seg_len(ny), nseg = (ny + L - 1) / L;
+    size_t need = 0;
+    for (int f64 = 0; f64 < 2; ++f64) {
+        const int ncol = f64 ? kTriCols64 : kTriCols, eb = f64 ? 8 : 4;
+        size_t elems = (size_t)6 * kTriSegs * kTriCols + (size_t)nseg * tri_smem_seg_stride(L, ncol, eb);
+        if (tables) elems += (size_t)2 * (L + 1) * ncol;
+        if (elems * eb > need) need = elems * eb;
+    }
+    return need <= limit ? need : 0;
+}
+
+template <class T, int NCOL>
+SCB_D void tri_smem_body(const TriSolveParams& p, T* sm, int kb, int c, int tab_smem) {
+    const int lane = threadIdx.x % kTriCols, seg = threadIdx.x / kTriCols;
+    const int k = kb + lane;
+    const bool active = lane < NCOL && k < p.x1;
+    const int n = p.ny, L = p.seg_len;
+    const int nseg = (n + L - 1) / L;
+    const int rows = L + 1;
+    T* red = sm;
+    T* tabm = red + 6 * kTriSegs * kTriCols;
+    T* tabp = tabm + (tab_smem ? rows * NCOL : 0);
+    T* tile = tabp + (tab_smem ? rows * NCOL : 0);
+    const int ss = tri_smem_seg_stride(L, NCOL, (int)sizeof(T));
+    constexpr bool kF64 = sizeof(T) == 8;
+    const T* gm;
+    const T* gp;
+    size_t gstride;
+    if constexpr (kF64) {
+        gm = reinterpret_cast<const T*>(p.tab.m64);
+        gp = reinterpret_cast<const T*>(p.tab.p64);
+        gstride = kTriLowK;
+    } else {
+        gm = reinterpret_cast<const T*>(p.tab.m32);
+        gp = reinterpret_cast<const T*>(p.tab.p32);
+        gstride = (size_t)p.tab.pm;
+    }
+    if (tab_smem) {
+        for (int i = threadIdx.x; i < rows * NCOL; i += kTriCols * kTriSegs) {
+            const int d = i / NCOL, col = i - d * NCOL;
+            const bool in = kb + col < p.x1;
+            tabm[i] = in ? gm[(size_t)d * gstride + kb + col] : T(0);
+            tabp[i] = in ? gp[(size_t)d * gstride + kb + col] : T(0);
+        }
+    }
+    // own segment's rows of A -> tile (independent loads; a warp reads 32 / kTriCols rows x kTriCols consecutive columns per step)
+    const int r0 = seg * L;
+    const int len = (seg < nseg) ? ((n - r0 < L) ? n - r0 : L) : 0;
+    T* mine = tile + (size_t)seg * ss + lane;  // row d of the segment at mine[d * NCOL]
+    if (active && len > 0) {
+        const float* A = p.A + ((size_t)c * n + r0) * p.nx + k;
+        int d = 0;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            float a[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) a[i] = __ldg(A + (size_t)(d + i) * p.nx);
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) mine[(d + i) * NCOL] = (T)a[i];
+        }
+        for (; d < len; ++d) mine[d * NCOL] = (T)__ldg(A + (size_t)d * p.nx);
+    }
+    if (tab_smem) __syncthreads();  // the tables are read by every segment
+    const T* mrow = tab_smem ? tabm + lane : gm + k;
+    const T* prow = tab_smem ? tabp + lane : gp + k;
+    const size_t tstride = tab_smem ? (size_t)NCOL : gstride;
+    T* base = mine - (size_t)r0 * NCOL;  // row y of the column at base[y * NCOL], valid for the rows of the own segment
+    const auto tile_load = [&](int y) { return base[(size_t)y * NCOL]; };
+    const auto tile_store = [&](int y, T v) { base[(size_t)y * NCOL] = v; };
+    if constexpr (kF64) {
+        double* Y = p.Y64 + (size_t)c * n * kTriLowK + k;
+        tri_segments<T, true>(
+            n, L, seg, nseg, lane, red, tile_load, [&](int d) { return mrow[(size_t)d * tstride]; }, [&](int d) { return prow[(size_t)d * tstride]; }, tile_load, tile_store,
+            [&](int y, T u) { Y[(size_t)y * kTriLowK] = u; }, active, 0, 0, kTriSegs, (T*)nullptr, (size_t)0);
+    } else {
+        float* Ct = p.Ct + (size_t)c * n * p.nx + k;
+        tri_segments<T, true>(
+            n, L, seg, nseg, lane, red, tile_load, [&](int d) { return mrow[(size_t)d * tstride]; }, [&](int d) { return prow[(size_t)d * tstride]; }, tile_load, tile_store,
+            [&](int y, T u) { Ct[(size_t)y * p.nx] = u; }, active, 0, 0, kTriSegs, (T*)nullptr, (size_t)0);
+    }
+}
+
+__global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_smem_kernel(TriSolveParams p, int tab_smem) {
+    SCB_DYN_SMEM(double, sm_dyn);
+    constexpr int nb64 = kTriLowK / kTriCols64;
+    const int c = blockIdx.y, bx = blockIdx.x;
+    if (bx < nb64)
+        tri_smem_body<double, kTriCols64>(p, sm_dyn, bx * kTriCols64, c, tab_smem);
+    else
+        tri_smem_body<float, kTriCols>(p, reinterpret_cast<float*>(sm_dyn), kTriLowK + (bx - nb64) * kTriCols, c, tab_smem);
 }
 
 // ---------------------------------------------------------------------------------------------

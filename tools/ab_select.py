@@ -1,0 +1,210 @@
+#!/usr/bin/env python
+"""A/B of kernel variants on ONE GPU box, with a correctness gate: every variant runs in its own process (the switches are read once
+per process), is timed device-resident on the bench workloads with the L2 flushed between steps, and its output bytes are compared
+with the baseline's (exact variants must reproduce them bit for bit) and with cv2.seamlessClone.
+
+  python tools/ab_select.py [--out gpurun_out/ab] [--workloads cfg2 cfg1]        orchestrator: baseline + every variant below
+  python tools/ab_select.py --worker OUT.json --workloads cfg2 ...                one variant (environment already set)
+
+The orchestrator writes <out>/results.json, <out>/selected.json (the switches of every variant that is bit-identical to the baseline
+on all workloads and at least 1.5 % faster at cfg2, combined and re-measured) and a table on stdout.  Nothing here is a bench
+number: bench.py is."""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARIANT_LIBS = os.path.join(ROOT, "seamlesscloneoptimization_b200", "lib", "variants")
+
+# (name, switch group, environment, variant library tag or None).  Every variant here keeps the arithmetic of the baseline (a different
+# schedule of the same operations), so it must reproduce the baseline's bytes exactly.  One winner per group is kept.
+VARIANTS = [
+    ("i8_p2", "i8", {"SCB_I8_PERSISTENT": "2"}, None),
+    ("i8_p2_kb64", "i8", {"SCB_I8_PERSISTENT": "2", "SCB_I8_KB": "64"}, None),
+    ("rhs_fold2", "rhs", {"SCB_RHS_FOLD": "2"}, None),
+    ("rhs_fold2_r64", "rhs", {"SCB_RHS_FOLD": "2"}, "r64"),
+    ("tri_smem", "tri", {"SCB_TRI_SMEM": "1"}, None),
+    ("tri_smem_u16", "tri", {"SCB_TRI_SMEM": "1"}, "u16"),
+    ("tri_u16", "tri", {}, "u16"),
+]
+
+
+def lib_of(tags):
+    tags = sorted(t for t in tags if t)
+    return os.path.join(VARIANT_LIBS, "libscb_" + "".join(tags) + ".so") if tags else None
+
+
+def worker(out_path, wls, steps):
+    import numpy as np
+    import torch
+
+    import seamlesscloneoptimization_b200 as scb
+    from seamlesscloneoptimization_b200 import _capi as capi
+    from seamlesscloneoptimization_b200 import workloads
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+    for wl in wls:
+        src, dst, mask, p = workloads.make_config(wl, seed=0)
+        stream = torch.cuda.Stream(device=dev)
+        ctx = scb.Context(0, stream=stream.cuda_stream)
+        d_src, d_dst, d_mask = (torch.from_numpy(a).to(dev) for a in (src, dst, mask))
+        d_blend = torch.zeros_like(d_dst)
+        plan = scb.Plan(ctx, d_mask, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+        g = plan.geometry
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                plan.execute(d_src, d_dst, d_blend, scb.MEM_DEVICE)
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(steps):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                plan.execute(d_src, d_dst, d_blend, scb.MEM_DEVICE)
+                e1.record(stream)
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            ms = [a.elapsed_time(b) for a, b in evs]
+            acc = {}
+            for _ in range(5):
+                flush.fill_(1)
+                for k, v in plan.execute_timed(d_src, d_dst, d_blend, scb.MEM_DEVICE).items():
+                    acc.setdefault(k, []).append(v)
+            torch.cuda.synchronize()
+        dev_blend = d_blend.cpu().numpy()
+        # the HOST path (banded passes: other tile ranges of the same kernels) must give the same bytes
+        host_blend = ctx.seamless_clone(src, dst, mask, p)
+        interior = dev_blend[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
+        r = {
+            "ms": statistics.median(ms), "ms_mean": statistics.mean(ms), "ms_min": min(ms),
+            "stages_us": {k: round(1e3 * statistics.mean(v), 2) for k, v in acc.items()},
+            "md5": hashlib.md5(np.ascontiguousarray(dev_blend)).hexdigest(),
+            "host_equals_device": bool(np.array_equal(host_blend, dev_blend)),
+            "roi": [int(g.w), int(g.h)], "engine": int(plan.engine),
+        }
+        ref_path = f"/tmp/ab_ref_{wl}.npy"
+        if os.path.exists(ref_path):
+            ref = np.load(ref_path)[g.ry + 1 : g.ry + g.h - 1, g.rx + 1 : g.rx + g.w - 1]
+            d = np.abs(ref.astype(np.int16) - interior.astype(np.int16))
+            r.update(pct_exact=100.0 * float((d == 0).mean()), max_abs=int(d.max()))
+        res[wl] = r
+        plan.close()
+        ctx.close()
+    with open(out_path, "w") as fh:
+        json.dump(res, fh)
+
+
+def run_variant(name, env_extra, wls, steps, out_dir, timeout_s):
+    out = os.path.join(out_dir, f"{name}.json")
+    if os.path.exists(out):
+        os.remove(out)
+    env = dict(os.environ)
+    env.update(env_extra)
+    lib = env_extra.get("SCB_LIBRARY")
+    if lib and not os.path.exists(lib):
+        return {"error": f"{lib} not built"}
+    t0 = time.time()
+    try:
+        pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", out, "--steps", str(steps), "--workloads"] + wls, env=env, cwd=ROOT,
+                            capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"error": f"timeout after {timeout_s} s"}
+    if pr.returncode != 0 or not os.path.exists(out):
+        return {"error": f"exit {pr.returncode}: {(pr.stderr or '')[-600:]}"}
+    with open(out) as fh:
+        r = json.load(fh)
+    r["_wall_s"] = round(time.time() - t0, 1)
+    return r
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--worker", default=None)
+    ap.add_argument("--workloads", nargs="+", default=["cfg2", "cfg1"])
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab"))
+    ap.add_argument("--timeout", type=int, default=100)
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    if args.worker:
+        worker(args.worker, args.workloads, args.steps)
+        return
+    os.makedirs(args.out, exist_ok=True)
+    import cv2
+
+    from seamlesscloneoptimization_b200 import workloads
+
+    for wl in args.workloads:  # cv2.seamlessClone once per workload
+        src, dst, mask, p = workloads.make_config(wl, seed=0)
+        import numpy as np
+
+        np.save(f"/tmp/ab_ref_{wl}.npy", cv2.seamlessClone(src, dst, mask.copy(), p, cv2.NORMAL_CLONE))
+    results = {"baseline": run_variant("baseline", {}, args.workloads, args.steps, args.out, args.timeout * 2)}
+    base = results["baseline"]
+    print("baseline", json.dumps(base), flush=True)
+    if "error" in base:
+        json.dump(results, open(os.path.join(args.out, "results.json"), "w"), indent=1)
+        raise SystemExit("baseline failed")
+    head = args.workloads[0]
+    winners = {}
+    for name, group, env_extra, tag in VARIANTS:
+        if args.only is not None and name not in args.only:
+            continue
+        env_v = dict(env_extra)
+        if tag:
+            env_v["SCB_LIBRARY"] = lib_of([tag])
+        r = run_variant(name, env_v, args.workloads, args.steps, args.out, args.timeout)
+        results[name] = r
+        if "error" not in r:
+            r["_correct"] = all(r[wl]["md5"] == base[wl]["md5"] and r[wl]["host_equals_device"] for wl in args.workloads)
+            r["_speedup"] = base[head]["ms"] / r[head]["ms"]
+            if r["_correct"] and r["_speedup"] >= 1.015 and (group not in winners or r["_speedup"] > winners[group][3]):
+                winners[group] = (name, env_extra, tag, r["_speedup"])
+        print(name, json.dumps(r), flush=True)
+        json.dump(results, open(os.path.join(args.out, "results.json"), "w"), indent=1)
+    combined, tags = {}, []
+    for name, env_extra, tag, sp in winners.values():
+        combined.update(env_extra)
+        tags.append(tag)
+    if lib_of(tags):
+        combined["SCB_LIBRARY"] = lib_of(tags)
+    sel = {"winners": [w[0] for w in winners.values()], "env": combined}
+    if combined:
+        r = run_variant("combined", combined, args.workloads, args.steps, args.out, args.timeout)
+        results["combined"] = r
+        ok = "error" not in r and all(r[wl]["md5"] == base[wl]["md5"] and r[wl]["host_equals_device"] for wl in args.workloads)
+        sel["combined_ok"] = ok
+        if ok:
+            sel["speedup"] = base[head]["ms"] / r[head]["ms"]
+        else:  # fall back to the single best winner
+            best = max(winners.values(), key=lambda w: w[3])
+            sel["env"] = dict(best[1], **({"SCB_LIBRARY": lib_of([best[2]])} if best[2] else {}))
+            sel["winners"] = [best[0]]
+        print("combined", json.dumps(r), flush=True)
+    json.dump(results, open(os.path.join(args.out, "results.json"), "w"), indent=1)
+    json.dump(sel, open(os.path.join(args.out, "selected.json"), "w"), indent=1)
+    with open(os.path.join(args.out, "selected.env"), "w") as fh:
+        for k, v in sel["env"].items():
+            fh.write(f"export {k}={v}\n")
+        if "SCB_LIBRARY" in sel["env"]:
+            fh.write(f"export SCB_TEST_LIBRARY={sel['env']['SCB_LIBRARY']}\n")
+    print("\n%-16s %9s %9s %8s  %s" % ("variant", head + " ms", "speedup", "correct", "stages (us)"))
+    for name, r in results.items():
+        if "error" in r:
+            print("%-16s ERROR %s" % (name, r["error"][:200]))
+            continue
+        print("%-16s %9.4f %9.3f %8s  %s" % (name, r[head]["ms"], base[head]["ms"] / r[head]["ms"], r.get("_correct", "-"), r[head]["stages_us"]))
+    print("selected:", json.dumps(sel))
+
+
+if __name__ == "__main__":
+    main()
