@@ -1873,11 +1873,18 @@ static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
     SCB_LAUNCH(tri_solve_kernel, dim3((t.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
     p->ctx->launches++;
 }
+static constexpr int kLowProjDefault = 1;  // 1: tri_lowproj_kernel, 2: tri_lowproj2_kernel (no shared-memory atomics, 4 frequencies per thread)
 static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaStream_t stream) {
     const dim3 grid((l.y1 - l.y0 + kTriLowRows - 1) / kTriLowRows, 3), block(32 * kTriLowWarps);
     if (l.y1 <= l.y0) return;
+    static const int proj_variant = [] {  // SCB_LOWPROJ=1: tri_lowproj_kernel (A/B checks)
+        const char* e = std::getenv("SCB_LOWPROJ");
+        return e ? std::atoi(e) : kLowProjDefault;
+    }();
     if (apply)
         SCB_LAUNCH(tri_lowapply_kernel, grid, block, 0, stream, l);
+    else if (proj_variant == 2)
+        SCB_LAUNCH(tri_lowproj2_kernel, grid, block, 0, stream, l);
     else
         SCB_LAUNCH(tri_lowproj_kernel, grid, block, 0, stream, l);
     p->ctx->launches++;
@@ -1885,7 +1892,8 @@ static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaS
 
 // Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][cnt][len] -> Ct [3][cnt][len]);
 // the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
-static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap) {
+// `fuse_apply`: the caller's inverse digitise applies the low-frequency block itself (i8_digitize2_kernel): no tri_lowapply launch.
+static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap, bool fuse_apply = false) {
     NvtxRange nvtx_("scb:tri_solve");
     scb_context* c = p->ctx;
     const Frame f = frame_of(p, swap);  // "columns" of the solve = the f.len frequencies of a line, solved across the f.cnt lines
@@ -1901,7 +1909,7 @@ static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, doub
     if (proj_stream != ms) SCB_CUDA(c, cudaEventRecord(L->ev_join, proj_stream));
     launch_tri_solve(p, tri_solve_params(p, f, A, Ct, Y64));
     if (proj_stream != ms) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
-    launch_tri_low(p, true, l, ms);
+    if (!fuse_apply) launch_tri_low(p, true, l, ms);
     return SCB_OK;
 }
 
@@ -2038,8 +2046,19 @@ static bool i8_fused_compose(const scb_plan* p) {
     }();
     return p->use_i8 && !p->debug && !off;
 }
+// tri_lowapply fused into the digitise of the inverse pass (i8_digitize2_kernel, lines of up to 2048 points).  SCB_LOWAPPLY_FUSE=0/1
+// overrides the default (A/B checks); debug plans dump Ct and keep the separate kernel.
+static constexpr bool kLowApplyFuseDefault = false;
+static bool i8_fused_lowapply(const scb_plan* p, bool swap) {
+    static const bool on = [] {
+        const char* e = std::getenv("SCB_LOWAPPLY_FUSE");
+        return e ? std::atoi(e) != 0 : kLowApplyFuseDefault;
+    }();
+    // (lines of at least 2 x 32 points: the low-frequency columns must all lie in the first half of the folded line)
+    return on && p->use_i8 && p->use_tri && !p->debug && !swap && p->g.nx >= 2 * kTriLowK && i8_digitize2_serves(p->i8x->g);
+}
 static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1, StageTimer* tm = nullptr, unsigned char* out8 = nullptr,
-                          long long out8_pitch = 0) {
+                          long long out8_pitch = 0, bool fuse_apply = false) {
     NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -2056,6 +2075,14 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     d.lscale = w.lscale;
     d.fixed_scale = 1.0f;
     d.per_line = 1;  // 30-bit fixed point relative to the line's largest magnitude
+    if (fuse_apply) {
+        d.low_w = w.W;
+        d.low_y64 = w.Y64;
+        d.low_k = kTriLowK;
+        d.low_l = kTriLowL;
+        d.low_nk = g.nx < kTriLowK ? g.nx : kTriLowK;
+        d.low_nl = g.ny < kTriLowL ? g.ny : kTriLowL;
+    }
     d.line0 = 3 * y0;
     d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;
     if (i8_launch_digitize((void*)p->lane->stream, d, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
@@ -2362,8 +2389,9 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         }
         if (!serial) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
+        const bool fa = i8_fused_lowapply(p, swap);
         if (p->use_tri) {
-            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, serial ? ms : L->side, swap))) return rc;
+            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, serial ? ms : L->side, swap, fa))) return rc;
         } else
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
@@ -2371,7 +2399,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (nb_out == 1) {
             if (p->use_i8) {
                 const bool fc = i8_fused_compose(p);
-                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm, fc ? out : nullptr, out_pitch))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
+                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm, fc ? out : nullptr, out_pitch, fa))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
                 if (!fc) run_compose(p, w.At, out, out_pitch, 0, g.ny);
             } else {
                 run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
@@ -2380,7 +2408,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
             for (int b = 0; b < nb; ++b) {
                 if (p->use_i8) {
                     const bool fc = i8_fused_compose(p);
-                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1], nullptr, fc ? out : nullptr, out_pitch))) return rc;
+                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1], nullptr, fc ? out : nullptr, out_pitch, fa))) return rc;
                     if (!fc) run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
                 } else {
                     run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);

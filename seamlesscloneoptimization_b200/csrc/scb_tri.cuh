@@ -523,6 +523,74 @@ __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj_kernel(TriLowPa
     }
 }
 
+// tri_lowproj2_kernel (SCB_LOWPROJ=2): the same projections without the 64 float64 accumulators per thread (170 registers, one CTA
+// per SM) and without the shared-memory atomics that fold eight warps' partial sums (8-way contention on every address -- the bulk of
+// tri_lowproj_kernel's 13 us).  The CTA's 32 rows of sines (the same three-term recurrence, one row per lane of warp 0) and of
+// a_fft / a_exact - a_fft go to shared memory once; thread (warp w, lane k) then owns the frequencies l = w, w + 8, w + 16, w + 24 of
+// column k outright and sums them over the CTA's rows in registers -- no reduction inside the CTA -- and finishes them as before
+// (one float64 atomicAdd per (l, k) and CTA into W).  Summation order differs from tri_lowproj_kernel's (which is itself not
+// deterministic: atomics), values agree to ~1e-15 relative.
+// grid = (ceil(ny / kTriLowRows), 3), block = 32 x kTriLowWarps
+__global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowproj2_kernel(TriLowParams p) {
+    static_assert(kTriLowRows == 32 && kTriLowL == 32 && kTriLowK == 32, "one row / frequency / column per lane");
+    __shared__ double S[kTriLowRows][kTriLowL + 1];  // sin(pi (y+1)(l+1) / N); +1: the recurrence writes a column per step, conflict free
+    __shared__ double Af[kTriLowRows][32];           // a_fft
+    __shared__ double Dx[kTriLowRows][32];           // a_exact - a_fft
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y, n = p.ny;
+    const int yb = p.y0 + blockIdx.x * kTriLowRows;
+    const int k = lane;
+    const bool kin = k < p.nx;
+    const bool has_r = p.R && k < p.lowkx;
+    const int L = n < kTriLowL ? n : kTriLowL;
+    for (int row = warp; row < kTriLowRows; row += kTriLowWarps) {
+        const int y = yb + row;
+        const bool yin = y < p.y1;
+        const double af = (kin && yin) ? (double)__ldg(p.A + ((size_t)c * n + y) * p.nx + k) : 0.0;
+        Af[row][lane] = af;
+        Dx[row][lane] = (has_r && yin) ? -2.0 * __ldg(p.R + ((size_t)c * p.lowkx + k) * n + y) - af : 0.0;
+    }
+    if (warp == 0) {  // lane = row
+        const int y = yb + lane;
+        const double ph = (double)(y + 1) / (double)(n + 1);
+        const double twoc = 2.0 * cospi(ph);
+        double s0 = 0.0, s1 = (y < p.y1) ? sinpi(ph) : 0.0;  // rows past the end contribute nothing (their a are zero too)
+        SCB_UNROLL
+        for (int l = 0; l < kTriLowL; ++l) {
+            S[lane][l] = s1;
+            const double s2 = twoc * s1 - s0;
+            s0 = s1;
+            s1 = s2;
+        }
+    }
+    __syncthreads();
+    constexpr int NL = kTriLowL / kTriLowWarps;  // frequencies per thread
+    double tf[NL], te[NL];
+    SCB_UNROLL
+    for (int j = 0; j < NL; ++j) tf[j] = te[j] = 0.0;
+    for (int row = 0; row < kTriLowRows; ++row) {
+        const double af = Af[row][lane], dx = Dx[row][lane];
+        SCB_UNROLL
+        for (int j = 0; j < NL; ++j) {
+            const double s = S[row][warp + kTriLowWarps * j];
+            tf[j] += s * af;
+            te[j] += s * dx;
+        }
+    }
+    if (kin) {
+        const float fxk = __ldg(p.fx + k);
+        SCB_UNROLL
+        for (int j = 0; j < NL; ++j) {
+            const int l = warp + kTriLowWarps * j;
+            if (l >= L) continue;
+            const double sf = tf[j], se = te[j];
+            const double i32 = 1.0 / (double)__fsub_rn(__fadd_rn(fxk, __ldg(p.fy + l)), 4.0f);             // OpenCV: (filter_X + filter_Y) - 4 in float32
+            const double iex = 1.0 / ((double)fxk + 2.0 * cospi((double)(l + 1) / (double)(n + 1)) - 4.0);  // what the tridiagonal solve divides by
+            const double w = -(2.0 / (double)(n + 1)) * ((sf + se) * i32 - sf * iex);
+            atomicAdd(p.W + ((size_t)c * kTriLowL + l) * kTriLowK + k, w);
+        }
+    }
+}
+
 // grid = (ceil(ny / kTriLowRows), 3), block = 32 x kTriLowWarps
 __global__ void __launch_bounds__(32 * kTriLowWarps) tri_lowapply_kernel(TriLowParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = blockIdx.y, n = p.ny;

@@ -22,8 +22,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANT_LIBS = os.path.join(ROOT, "seamlesscloneoptimization_b200", "lib", "variants")
 
-# (name, switch group, environment, variant library tag or None).  Every variant here keeps the arithmetic of the baseline (a different
-# schedule of the same operations), so it must reproduce the baseline's bytes exactly.  One winner per group is kept.
+# (name, switch group, environment, variant library tag or None).  Every variant but lowproj2 keeps the arithmetic of the baseline (a
+# different schedule of the same operations) and must reproduce the baseline's bytes exactly; lowproj2 reorders float64 sums (the
+# baseline's own order is not deterministic: atomics) and must stay within +-1 LSB and 0.003 points of the baseline's exact-byte share.
+# One winner per group is kept.
 VARIANTS = [
     ("i8_p2", "i8", {"SCB_I8_PERSISTENT": "2"}, None),
     ("i8_p2_kb64", "i8", {"SCB_I8_PERSISTENT": "2", "SCB_I8_KB": "64"}, None),
@@ -31,8 +33,25 @@ VARIANTS = [
     ("rhs_fold2_r64", "rhs", {"SCB_RHS_FOLD": "2"}, "r64"),
     ("tri_smem", "tri", {"SCB_TRI_SMEM": "1"}, None),
     ("tri_smem_u16", "tri", {"SCB_TRI_SMEM": "1"}, "u16"),
-    ("tri_u16", "tri", {}, "u16"),
+    ("i8_dig2", "dig", {"SCB_I8_DIGITIZE": "2"}, None),
+    ("i8_dig2_low", "dig", {"SCB_I8_DIGITIZE": "2", "SCB_LOWAPPLY_FUSE": "1"}, None),
 ]
+
+
+# second round, measured on top of the first round's winners (alone, the projections hide behind the column solve)
+ON_TOP = [("lowproj2", {"SCB_LOWPROJ": "2"})]
+INEXACT = {"lowproj2"}
+
+
+def same_result(r, base, wls, exact):
+    for wl in wls:
+        if not r[wl]["host_equals_device"]:
+            return False
+        if r[wl]["md5"] == base[wl]["md5"]:
+            continue
+        if exact or r[wl].get("max_abs", 9) > 1 or abs(r[wl].get("pct_exact", 0.0) - base[wl].get("pct_exact", 100.0)) > 0.003:
+            return False
+    return True
 
 
 def lib_of(tags):
@@ -40,7 +59,22 @@ def lib_of(tags):
     return os.path.join(VARIANT_LIBS, "libscb_" + "".join(tags) + ".so") if tags else None
 
 
+def fake_worker(out_path, wls):
+    """AB_FAKE=1: synthetic results, so that the orchestrator's bookkeeping can be exercised without a GPU (tests/test_tools.py)."""
+    gain = {"SCB_I8_PERSISTENT": 0.03, "SCB_RHS_FOLD": 0.012, "SCB_TRI_SMEM": 0.03, "SCB_I8_DIGITIZE": 0.006, "SCB_LOWAPPLY_FUSE": 0.006, "SCB_LOWPROJ": 0.004}
+    ms = 0.24 - sum(v for k, v in gain.items() if os.environ.get(k, "0") not in ("0", "1") or (k in ("SCB_TRI_SMEM", "SCB_LOWAPPLY_FUSE") and os.environ.get(k) == "1"))
+    if os.environ.get("SCB_LIBRARY"):
+        ms -= 0.001
+    broken = os.environ.get("SCB_I8_KB") == "64"  # pretend one variant computes something else
+    res = {wl: {"ms": ms, "ms_mean": ms, "ms_min": ms, "stages_us": {}, "md5": "beef" if broken else "cafe", "host_equals_device": True, "roi": [0, 0], "engine": 4,
+                "pct_exact": 99.85, "max_abs": 1} for wl in wls}
+    with open(out_path, "w") as fh:
+        json.dump(res, fh)
+
+
 def worker(out_path, wls, steps):
+    if os.environ.get("AB_FAKE"):
+        return fake_worker(out_path, wls)
     import numpy as np
     import torch
 
@@ -53,7 +87,12 @@ def worker(out_path, wls, steps):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     res = {}
     for wl in wls:
-        src, dst, mask, p = workloads.make_config(wl, seed=0)
+        cache = f"/tmp/ab_wl_{wl}.npz"  # written once by the orchestrator: generating the 4K workload takes seconds
+        if os.path.exists(cache):
+            z = np.load(cache)
+            src, dst, mask, p = z["src"], z["dst"], z["mask"], tuple(int(v) for v in z["p"])
+        else:
+            src, dst, mask, p = workloads.make_config(wl, seed=0)
         stream = torch.cuda.Stream(device=dev)
         ctx = scb.Context(0, stream=stream.cuda_stream)
         d_src, d_dst, d_mask = (torch.from_numpy(a).to(dev) for a in (src, dst, mask))
@@ -139,15 +178,16 @@ def main():
         worker(args.worker, args.workloads, args.steps)
         return
     os.makedirs(args.out, exist_ok=True)
-    import cv2
-
-    from seamlesscloneoptimization_b200 import workloads
-
-    for wl in args.workloads:  # cv2.seamlessClone once per workload
-        src, dst, mask, p = workloads.make_config(wl, seed=0)
+    if not os.environ.get("AB_FAKE"):
+        import cv2
         import numpy as np
 
-        np.save(f"/tmp/ab_ref_{wl}.npy", cv2.seamlessClone(src, dst, mask.copy(), p, cv2.NORMAL_CLONE))
+        from seamlesscloneoptimization_b200 import workloads
+
+        for wl in args.workloads:  # cv2.seamlessClone once per workload
+            src, dst, mask, p = workloads.make_config(wl, seed=0)
+            np.savez(f"/tmp/ab_wl_{wl}.npz", src=src, dst=dst, mask=mask, p=np.array(p))
+            np.save(f"/tmp/ab_ref_{wl}.npy", cv2.seamlessClone(src, dst, mask.copy(), p, cv2.NORMAL_CLONE))
     results = {"baseline": run_variant("baseline", {}, args.workloads, args.steps, args.out, args.timeout * 2)}
     base = results["baseline"]
     print("baseline", json.dumps(base), flush=True)
@@ -165,10 +205,11 @@ def main():
         r = run_variant(name, env_v, args.workloads, args.steps, args.out, args.timeout)
         results[name] = r
         if "error" not in r:
-            r["_correct"] = all(r[wl]["md5"] == base[wl]["md5"] and r[wl]["host_equals_device"] for wl in args.workloads)
+            r["_correct"] = same_result(r, base, args.workloads, name not in INEXACT)
             r["_speedup"] = base[head]["ms"] / r[head]["ms"]
-            if r["_correct"] and r["_speedup"] >= 1.015 and (group not in winners or r["_speedup"] > winners[group][3]):
-                winners[group] = (name, env_extra, tag, r["_speedup"])
+            score = r["_speedup"] - (0.01 if tag else 0.0)  # a compile-time variant must earn its keep: +1 % over the plain switch
+            if r["_correct"] and score >= 1.015 and (group not in winners or score > winners[group][3]):
+                winners[group] = (name, env_extra, tag, score)
         print(name, json.dumps(r), flush=True)
         json.dump(results, open(os.path.join(args.out, "results.json"), "w"), indent=1)
     combined, tags = {}, []
@@ -181,7 +222,7 @@ def main():
     if combined:
         r = run_variant("combined", combined, args.workloads, args.steps, args.out, args.timeout)
         results["combined"] = r
-        ok = "error" not in r and all(r[wl]["md5"] == base[wl]["md5"] and r[wl]["host_equals_device"] for wl in args.workloads)
+        ok = "error" not in r and same_result(r, base, args.workloads, not any(w[0] in INEXACT for w in winners.values()))
         sel["combined_ok"] = ok
         if ok:
             sel["speedup"] = base[head]["ms"] / r[head]["ms"]
@@ -190,6 +231,19 @@ def main():
             sel["env"] = dict(best[1], **({"SCB_LIBRARY": lib_of([best[2]])} if best[2] else {}))
             sel["winners"] = [best[0]]
         print("combined", json.dumps(r), flush=True)
+    for name, env_extra in ON_TOP:
+        env_v = dict(sel["env"], **env_extra)
+        r = run_variant(name + "_on_top", env_v, args.workloads, args.steps, args.out, args.timeout)
+        results[name + "_on_top"] = r
+        if "error" not in r:
+            ref_ms = results["combined"][head]["ms"] if sel.get("combined_ok") else base[head]["ms"]
+            r["_correct"] = same_result(r, base, args.workloads, False)
+            r["_speedup"] = base[head]["ms"] / r[head]["ms"]
+            if r["_correct"] and ref_ms / r[head]["ms"] >= 1.01:
+                sel["env"] = env_v
+                sel["winners"].append(name)
+                sel["speedup"] = r["_speedup"]
+        print(name + "_on_top", json.dumps(r), flush=True)
     json.dump(results, open(os.path.join(args.out, "results.json"), "w"), indent=1)
     json.dump(sel, open(os.path.join(args.out, "selected.json"), "w"), indent=1)
     with open(os.path.join(args.out, "selected.env"), "w") as fh:
