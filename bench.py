@@ -67,6 +67,17 @@ def library_stamp():
         return None
 
 
+def kernel_variants() -> dict:
+    """The kernel generations in force in the loaded library (scb_kernel_variants: defaults or SCB_* overrides), as a dict."""
+    try:
+        from seamlesscloneoptimization_b200 import _capi
+
+        txt = (_capi.load().scb_kernel_variants() or b"").decode()
+        return dict(kv.split("=", 1) for kv in txt.split() if "=" in kv)
+    except Exception:
+        return {}
+
+
 def _profile_json(name: str):
     """profiles/<name>: ncu numbers quoted beside the live ones.  Each file carries the source hash of the library it was
     captured from ("library_stamp"); numbers of another library state are DROPPED (returned as None), never quoted silently."""
@@ -386,16 +397,23 @@ def roofline_objects(stages, px, workload, g=None):
     peak, peak_kind = measured_peak_gbs()
     i8 = "i8_gemm_inv" in stages
     names = dict(KERNEL_NAMES)
+    kv = kernel_variants()
+    pers = kv.get("i8_persistent", "1")
+    gemm_fwd = "i8_gemm_p2kernel<2,4> (128x128 tiles)" if pers in ("2", "3") else "i8_gemm_pkernel<2,4>"
+    gemm_inv = "i8_gemm_p2kernel<4,3> (128x128 tiles)" if pers == "2" else "i8_gemm_pkernel<4,3>"
+    tri = {"0": "tri_solve_kernel", "1": "tri_solve_smem_kernel", "2": "tri_solve_smem2_kernel"}.get(kv.get("tri_smem", "0"), "tri_solve_kernel")
+    proj = "tri_lowproj2_kernel" if kv.get("lowproj") == "2" else "tri_lowproj_kernel"
     if i8:
-        names.update({"rows_fwd": "i8_digitize_kernel<2> + i8_gemm_pkernel<2,4> (INT8 tensor-core DST)", "rows_inv": "i8_digitize_kernel<4> + i8_gemm_pkernel<4,3> + i8_compose_kernel",
-                      "cols": "tri_solve_kernel + tri_low*_kernel (tridiagonal solve along y)"})
+        names.update({"rows_fwd": f"i8_digitize_kernel<2> + {gemm_fwd} (INT8 tensor-core DST)", "rows_inv": f"i8_digitize_kernel<4> + {gemm_inv} + i8_compose_kernel",
+                      "cols": f"{tri} + {proj} + tri_lowapply_kernel (tridiagonal solve along y; column tile in shared memory where it fits)"})
 
     alg_bytes = dict(ALG_BYTES)
     if i8 and stages.get("i8_digitize_fwd", 1.0) < 0.005:
         # the stencil is fused with the fold + digit split: 7 B read (3 dst + 3 src + 1 mask) + 6 B of digit planes written per pixel
         # (2 parities x 2 digits x half the columns x 3 channels) instead of 12 B of float right-hand side
         alg_bytes["rhs"] = 13
-        names["rhs"] = "rhs_fold_kernel<2> (stencil fused with the fold + digit split of the INT8 engine)"
+        names["rhs"] = ("rhs_fold2_kernel (stencil, fold and digit split of the INT8 engine in packed 16-bit lanes)" if kv.get("rhs_fold") == "2" else
+                        "rhs_fold_kernel<2> (stencil fused with the fold + digit split of the INT8 engine)")
 
     def obj(k):
         alg = alg_bytes[k] * px
@@ -414,7 +432,7 @@ def roofline_objects(stages, px, workload, g=None):
         tpeak, tkind = measured_tensor_peak()
         ops = i8_tensor_ops(g, inverse)
         ach = ops / (stages[k] * 1e-3) / 1e12 if stages.get(k) else None
-        o = {"bound": "tensor", "kernel": "i8_gemm_pkernel<4,3> (inverse DST along x)" if inverse else "i8_gemm_pkernel<2,4> (forward DST along x)",
+        o = {"bound": "tensor", "kernel": f"{gemm_inv} (inverse DST along x)" if inverse else f"{gemm_fwd} (forward DST along x)",
              "achieved": ach, "peak": tpeak, "peak_kind": tkind, "unit": "TOP/s (int8)", "frac": (ach / tpeak) if ach else None,
              "algorithmic_ops_per_launch": ops, "duration_ms": stages.get(k),
              "duration_source": "live CUDA-event pair around the kernel on the library's stream",
@@ -839,6 +857,7 @@ def main():
             line["sharded"] = sh
     if env.rank == 0 and line is not None:
         line["library_stamp"] = library_stamp()
+        line["kernel_variants"] = kernel_variants()
         pin = line.pop("_parity_inputs", None)
         if env.world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)

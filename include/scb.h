@@ -123,6 +123,9 @@ uint64_t scb_kernel_launches(const scb_context* ctx); /* kernels this library ha
 int scb_device_count(void);
 /* 16 hex digits: hash of the sources the library was built from (the test fixture compares it with the tree and rebuilds a stale library) */
 const char* scb_source_hash(void);
+/* "name=value ..." of the kernel generations in force (defaults, or the SCB_* environment overrides used for A/B measurements);
+ * bench.py prints it with every line so that a number always names the kernels that produced it. */
+const char* scb_kernel_variants(void);
 /* Chooses the DST engine of plans created afterwards (SCB_ENGINE_*).  The reference makes the same choice at
  * compile time: SC_FFT_ENABLE, seamlessClone_imp.h:15 (cuFFT solver vs cuBLAS sine-basis solver). */
 int scb_set_engine(scb_context* ctx, int engine);

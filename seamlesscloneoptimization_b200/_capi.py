@@ -36,7 +36,7 @@ INT_GRADIENT_X, INT_GRADIENT_Y, INT_RHS, INT_SPECTRUM, INT_SOLVED, INT_ERODED_MA
 # every symbol include/scb.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "scb_create", "scb_destroy", "scb_sync", "scb_stream", "scb_last_error", "scb_status_string",
-    "scb_kernel_launches", "scb_device_count", "scb_source_hash", "scb_set_engine", "scb_set_orientation", "scb_tc_selftest", "scb_host_alloc", "scb_host_free",
+    "scb_kernel_launches", "scb_device_count", "scb_source_hash", "scb_kernel_variants", "scb_set_engine", "scb_set_orientation", "scb_tc_selftest", "scb_host_alloc", "scb_host_free",
     "scb_plan_create", "scb_plan_create_ex", "scb_plan_destroy", "scb_plan_geometry", "scb_plan_engine", "scb_plan_execute", "scb_plan_execute_timed", "scb_plan_execute_timed_i8", "scb_plan_execute_graph", "scb_plan_set_debug",
     "scb_plan_get_intermediate", "scb_seamless_clone", "scb_plan_cache_stats", "scb_clone_batch",
     "scb_plan_rows_forward", "scb_plan_cols", "scb_plan_lowfreq_finish", "scb_plan_rows_inverse", "scb_plan_lowk",
@@ -92,6 +92,7 @@ def load(path: str | None = None) -> C.CDLL:
         "scb_kernel_launches": (C.c_uint64, [vp]),
         "scb_device_count": (i, []),
         "scb_source_hash": (C.c_char_p, []),
+        "scb_kernel_variants": (C.c_char_p, []),
         "scb_set_engine": (i, [vp, i]),
         "scb_set_orientation": (i, [vp, i]),
         "scb_tc_selftest": (i, [vp, i, i, i, P(C.c_double)]),

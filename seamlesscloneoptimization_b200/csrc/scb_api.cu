@@ -371,6 +371,26 @@ static cudaError_t configure_one() {
 
 #define SCB_FOR_LOG2M(X) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 
+// ---- kernel switches -------------------------------------------------------------------------------------------------------------
+// Each hot kernel that exists in two generations is chosen by a default below; the environment variable of the same name overrides it
+// for A/B runs (tools/ab_select.py measures every switch on a B200 and requires the variant to reproduce the default's bytes).
+// scb_kernel_variants() reports what is in force.
+static constexpr int kRhsFoldDefault = 2;       // SCB_RHS_FOLD      1: rhs_fold_kernel<2>, 2: rhs_fold2_kernel (packed 16-bit lanes), binary masks
+static constexpr int kTriSmemDefault = 1;       // SCB_TRI_SMEM      1: tri_solve_smem_kernel for whole solves whose column tile fits in shared memory, 2: tri_solve_smem2_kernel
+static constexpr int kLowProjDefault = 1;       // SCB_LOWPROJ       1: tri_lowproj_kernel, 2: tri_lowproj2_kernel (no shared-memory atomics)
+static int sw_env(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+static int sw_rhs_fold() { return sw_env("SCB_RHS_FOLD", kRhsFoldDefault); }
+static int sw_tri_smem() { return sw_env("SCB_TRI_SMEM", kTriSmemDefault); }
+static int sw_lowproj() { return sw_env("SCB_LOWPROJ", kLowProjDefault); }
+extern "C" const char* scb_kernel_variants(void) {
+    static const std::string v = "rhs_fold=" + std::to_string(sw_rhs_fold()) + " tri_smem=" + std::to_string(sw_tri_smem()) + " tri_unroll=" + std::to_string(kTriUnroll) +
+                                 " lowproj=" + std::to_string(sw_lowproj()) + " " + i8_variant_string();
+    return v.c_str();
+}
+
 static cudaError_t configure_all() {
     cudaError_t e = cudaSuccess;
 #define X(L) if (e == cudaSuccess) e = configure_one<L>();
@@ -858,6 +878,7 @@ extern "C" int scb_create(int device, void* external_stream, scb_context** out) 
 #ifndef SCB_EMU
     if ((e = cudaFuncSetAttribute(tc_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess) return bail("cudaFuncSetAttribute(tc_pass_kernel)", e);
     if ((e = cudaFuncSetAttribute(tri_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemLimit)) != cudaSuccess) return bail("cudaFuncSetAttribute(tri_solve_smem_kernel)", e);
+    if ((e = cudaFuncSetAttribute(tri_solve_smem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTriSmemLimit)) != cudaSuccess) return bail("cudaFuncSetAttribute(tri_solve_smem2_kernel)", e);
 #endif
     if (ensure_bbox_slots(c, 1) != SCB_OK) {
         g_create_error = c->err;
@@ -1829,7 +1850,6 @@ static TriLowParams tri_low_params(scb_plan* p, const Frame& f, const float* A, 
     l.y1 = y1;
     return l;
 }
-static constexpr bool kTriSmemDefault = false;    // tri_solve_smem_kernel for whole solves whose tile fits
 static TriSolveParams tri_solve_params(scb_plan* p, const Frame& f, const float* A, float* Ct, double* Y64) {
     TriSolveParams t;
     t.tab = p->tri;
@@ -1852,10 +1872,8 @@ static TriSolveParams tri_solve_params(scb_plan* p, const Frame& f, const float*
 // ny <= ~3000 with 16 columns); longer columns and the row-sharded phases walk global memory (tri_solve_kernel).
 // SCB_TRI_SMEM=0/1 overrides the default (A/B checks).
 static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
-    static const bool smem_on = [] {
-        const char* e = std::getenv("SCB_TRI_SMEM");
-        return e ? std::atoi(e) != 0 : kTriSmemDefault;
-    }();
+    static const int smem_variant = sw_tri_smem();
+    static const bool smem_on = smem_variant != 0;
     if (smem_on && t.phase == 0 && t.x0 == 0 && t.x1 == t.nx) {
         int tables = 1;
         size_t bytes = tri_smem_bytes(t.ny, true, kTriSmemLimit);
@@ -1865,7 +1883,10 @@ static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
         }
         if (bytes) {
             const int nfloat = t.nx > kTriLowK ? (t.nx - kTriLowK + kTriCols - 1) / kTriCols : 0;
-            SCB_LAUNCH(tri_solve_smem_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, p->lane->stream, t, tables);
+            if (smem_variant == 2)
+                SCB_LAUNCH(tri_solve_smem2_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, p->lane->stream, t, tables);
+            else
+                SCB_LAUNCH(tri_solve_smem_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, p->lane->stream, t, tables);
             p->ctx->launches++;
             return;
         }
@@ -1873,14 +1894,10 @@ static void launch_tri_solve(scb_plan* p, const TriSolveParams& t) {
     SCB_LAUNCH(tri_solve_kernel, dim3((t.nx + kTriCols - 1) / kTriCols, 3), dim3(kTriCols * kTriSegs), 0, p->lane->stream, t);
     p->ctx->launches++;
 }
-static constexpr int kLowProjDefault = 1;  // 1: tri_lowproj_kernel, 2: tri_lowproj2_kernel (no shared-memory atomics, 4 frequencies per thread)
 static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaStream_t stream) {
     const dim3 grid((l.y1 - l.y0 + kTriLowRows - 1) / kTriLowRows, 3), block(32 * kTriLowWarps);
     if (l.y1 <= l.y0) return;
-    static const int proj_variant = [] {  // SCB_LOWPROJ=1: tri_lowproj_kernel (A/B checks)
-        const char* e = std::getenv("SCB_LOWPROJ");
-        return e ? std::atoi(e) : kLowProjDefault;
-    }();
+    static const int proj_variant = sw_lowproj();
     if (apply)
         SCB_LAUNCH(tri_lowapply_kernel, grid, block, 0, stream, l);
     else if (proj_variant == 2)
@@ -1892,8 +1909,7 @@ static void launch_tri_low(scb_plan* p, bool apply, const TriLowParams& l, cudaS
 
 // Tridiagonal engine, pass B (scb_tri.cuh): partitioned Thomas solve of every spectral column (A [3][cnt][len] -> Ct [3][cnt][len]);
 // the projections of the low-frequency block need only pass A and run on `proj_stream` beside the solve.
-// `fuse_apply`: the caller's inverse digitise applies the low-frequency block itself (i8_digitize2_kernel): no tri_lowapply launch.
-static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap, bool fuse_apply = false) {
+static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, double* Y64, double* W, cudaStream_t proj_stream, bool swap) {
     NvtxRange nvtx_("scb:tri_solve");
     scb_context* c = p->ctx;
     const Frame f = frame_of(p, swap);  // "columns" of the solve = the f.len frequencies of a line, solved across the f.cnt lines
@@ -1909,7 +1925,7 @@ static int run_tri(scb_plan* p, const float* A, float* Ct, const double* R, doub
     if (proj_stream != ms) SCB_CUDA(c, cudaEventRecord(L->ev_join, proj_stream));
     launch_tri_solve(p, tri_solve_params(p, f, A, Ct, Y64));
     if (proj_stream != ms) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
-    if (!fuse_apply) launch_tri_low(p, true, l, ms);
+    launch_tri_low(p, true, l, ms);
     return SCB_OK;
 }
 
@@ -1954,7 +1970,6 @@ static bool i8_fused_rhs(const scb_plan* p) {
     }();
     return p->use_i8 && p->mode == SCB_NORMAL_CLONE && !p->debug && !off;
 }
-static constexpr int kRhsFoldDefault = 1;  // 1: rhs_fold_kernel<2>, 2: rhs_fold2_kernel (packed 16-bit lanes) for binary masks
 static void run_rhs_fold(scb_plan* p, const StencilSrc& st, const Workspace& w, int y0, int y1) {
     NvtxRange nvtx_("scb:rhs_fold");
     const scb_geometry& g = p->g;
@@ -1973,10 +1988,7 @@ static void run_rhs_fold(scb_plan* p, const StencilSrc& st, const Workspace& w, 
     const int rows = (y1 >= g.ny ? (f.m_rows + 2) / 3 : y1) - y0;  // the last range also writes the zero pad lines up to the last whole tile
     if (rows <= 0) return;
     const dim3 grid((f.kpad / 4 + kRhsThreads - 1) / kRhsThreads, rows);
-    static const int variant = [] {  // SCB_RHS_FOLD=1: rhs_fold_kernel<2> for binary masks too (A/B checks)
-        const char* e = std::getenv("SCB_RHS_FOLD");
-        return e ? std::atoi(e) : kRhsFoldDefault;
-    }();
+    static const int variant = sw_rhs_fold();
     if (p->grey_mask)
         SCB_LAUNCH(rhs_fold_kernel<4>, grid, dim3(kRhsThreads), 0, p->lane->stream, f);
     else if (variant == 2)
@@ -2046,19 +2058,8 @@ static bool i8_fused_compose(const scb_plan* p) {
     }();
     return p->use_i8 && !p->debug && !off;
 }
-// tri_lowapply fused into the digitise of the inverse pass (i8_digitize2_kernel, lines of up to 2048 points).  SCB_LOWAPPLY_FUSE=0/1
-// overrides the default (A/B checks); debug plans dump Ct and keep the separate kernel.
-static constexpr bool kLowApplyFuseDefault = false;
-static bool i8_fused_lowapply(const scb_plan* p, bool swap) {
-    static const bool on = [] {
-        const char* e = std::getenv("SCB_LOWAPPLY_FUSE");
-        return e ? std::atoi(e) != 0 : kLowApplyFuseDefault;
-    }();
-    // (lines of at least 2 x 32 points: the low-frequency columns must all lie in the first half of the folded line)
-    return on && p->use_i8 && p->use_tri && !p->debug && !swap && p->g.nx >= 2 * kTriLowK && i8_digitize2_serves(p->i8x->g);
-}
 static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, float* U, int y0, int y1, StageTimer* tm = nullptr, unsigned char* out8 = nullptr,
-                          long long out8_pitch = 0, bool fuse_apply = false) {
+                          long long out8_pitch = 0) {
     NvtxRange nvtx_("scb:rows_inv_i8");
     scb_context* c = p->ctx;
     const scb_geometry& g = p->g;
@@ -2075,14 +2076,6 @@ static int run_i8_inverse(scb_plan* p, const Workspace& w, const float* Ct, floa
     d.lscale = w.lscale;
     d.fixed_scale = 1.0f;
     d.per_line = 1;  // 30-bit fixed point relative to the line's largest magnitude
-    if (fuse_apply) {
-        d.low_w = w.W;
-        d.low_y64 = w.Y64;
-        d.low_k = kTriLowK;
-        d.low_l = kTriLowL;
-        d.low_nk = g.nx < kTriLowK ? g.nx : kTriLowK;
-        d.low_nl = g.ny < kTriLowL ? g.ny : kTriLowL;
-    }
     d.line0 = 3 * y0;
     d.line1 = y1 >= g.ny ? d.m_rows : 3 * y1;
     if (i8_launch_digitize((void*)p->lane->stream, d, 4) != 0) return fail(c, SCB_ERR_CUDA, "i8_digitize_kernel launch failed");
@@ -2389,9 +2382,8 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         }
         if (!serial) SCB_CUDA(c, cudaStreamWaitEvent(ms, L->ev_join, 0));
         tm.mark(ST_ROWS_FWD);
-        const bool fa = i8_fused_lowapply(p, swap);
         if (p->use_tri) {
-            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, serial ? ms : L->side, swap, fa))) return rc;
+            if ((rc = run_tri(p, w.At, w.Ct, w.R, w.Y64, w.W, serial ? ms : L->side, swap))) return rc;
         } else
             run_cols(p, w.At, w.Ct, w.lowspec, 0, g.nx);
         tm.mark(ST_COLS);
@@ -2399,7 +2391,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
         if (nb_out == 1) {
             if (p->use_i8) {
                 const bool fc = i8_fused_compose(p);
-                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm, fc ? out : nullptr, out_pitch, fa))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
+                if ((rc = run_i8_inverse(p, w, w.Ct, w.At, 0, g.ny, &tm, fc ? out : nullptr, out_pitch))) return rc;  // the row-transformed right-hand side is dead: U overwrites it
                 if (!fc) run_compose(p, w.At, out, out_pitch, 0, g.ny);
             } else {
                 run_rows_inv(p, w.Ct, out, out_pitch, 0, fr.cnt, swap);
@@ -2408,7 +2400,7 @@ static int execute_impl(scb_plan* p, const scb_image* src, const scb_image* dst,
             for (int b = 0; b < nb; ++b) {
                 if (p->use_i8) {
                     const bool fc = i8_fused_compose(p);
-                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1], nullptr, fc ? out : nullptr, out_pitch, fa))) return rc;
+                    if ((rc = run_i8_inverse(p, w, w.Ct, w.At, yb[b], yb[b + 1], nullptr, fc ? out : nullptr, out_pitch))) return rc;
                     if (!fc) run_compose(p, w.At, out, out_pitch, yb[b], yb[b + 1]);
                 } else {
                     run_rows_inv(p, w.Ct, out, out_pitch, yb[b], yb[b + 1]);

@@ -3,6 +3,8 @@
 // Replaces, along x, the reference's per-row transform  dft_kernel_0 -> cufftExecC2C -> dft_kernel_1
 // (/root/reference/seamlessClone-CUDA/seamlessClone_imp.cpp:1694-1811) and its GEMM flavour (cublasSgemmBatched,
 // imp.cpp:1266-1334), with the same mathematical operator and results that are exact up to 2^-31 of full scale.
+#include <string>  // (before the platform header: the emulator build defines CUDA keywords as macros)
+
 #include "scb_i8.h"
 
 #include <cmath>
@@ -164,114 +166,6 @@ __global__ void __launch_bounds__(kI8DigThreads) i8_digitize_kernel(I8DigitizePa
             for (int i = 0; i < DA; ++i)
                 *reinterpret_cast<unsigned*>(p.a + ((size_t)(q * DA + i) * p.m_rows + line) * p.g.kpad + j0) = w[q][i];
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// i8_digitize2_kernel (SCB_I8_DIGITIZE=2): the same digit planes and scales, for lines of up to 2048 points (one chunk of four folded
-// elements per thread), with the per-element conditions of i8_digitize_kernel hoisted out of the common case: a thread whose four
-// elements are all below the middle of the line (every thread but one per line, and those past the end) runs straight-line code --
-// eight loads, the line maximum, eight conversions, two digit splits, eight stores.  i8_digitize_kernel executes ~340 instructions
-// per thread and is issue bound (profiles/r2_final_ncu_full_cfg2.txt: issue slots 78 % busy, DRAM 22 %); this one ~130.
-// ---------------------------------------------------------------------------------------------
-template <int DA>
-__global__ void __launch_bounds__(kI8DigThreads) i8_digitize2_kernel(I8DigitizeParams p) {
-    __shared__ float red[kI8DigThreads / 32];
-    const int t = threadIdx.x;
-    const int line = p.line0 + blockIdx.x;
-    const int n = p.g.n, h = n >> 1;
-    const int j0 = 4 * t;
-    const bool real = line < p.lines;
-    const bool full = real && j0 + 3 < h;             // four pairs (x[j], x[n-1-j])
-    const bool part = real && !full && j0 < p.g.kpar[0];  // the thread that holds the middle of the line
-    float fa[4] = {0.f, 0.f, 0.f, 0.f}, fb[4] = {0.f, 0.f, 0.f, 0.f};
-    bool mid[4] = {false, false, false, false};       // the middle element of an odd line: f0 = x[h], f1 = 0
-    __shared__ float lowv[32];
-    if (p.low_w) {  // fused tri_lowapply_kernel: warp 0 forms the lowest low_nk (<= 32 <= h) elements of the line in float64
-        if (t < 32 && real && t < p.low_nk) {
-            const int r = line / 3, c = line - 3 * r, k = t, rows = p.lpc;
-            double sum = p.low_y64[((size_t)c * rows + r) * p.low_k + k];
-            const double ph = (double)(r + 1) / (double)(rows + 1);
-            const double twoc = 2.0 * cospi(ph);
-            double s0 = 0.0, s1 = sinpi(ph);
-            const double* wk = p.low_w + (size_t)c * p.low_l * p.low_k + k;
-            for (int l = 0; l < p.low_l; ++l) {
-                const double w = (l < p.low_nl) ? wk[(size_t)l * p.low_k] : 0.0;
-                sum += w * s1;
-                const double s2 = twoc * s1 - s0;
-                s0 = s1;
-                s1 = s2;
-            }
-            lowv[k] = (float)sum;
-        }
-        __syncthreads();
-    }
-    if (real) {
-        const int r = line / 3, c = line - 3 * r;  // lines are channel-interleaved: line = 3 row + channel
-        const float* x = p.in + (size_t)c * p.in_plane + (size_t)r * p.in_pitch;
-        if (full) {
-            SCB_UNROLL
-            for (int e = 0; e < 4; ++e) {
-                fa[e] = __ldg(x + j0 + e);
-                fb[e] = __ldg(x + (n - 1 - j0) - e);
-            }
-            if (p.low_w && j0 < p.low_nk) {
-                SCB_UNROLL
-                for (int e = 0; e < 4; ++e)
-                    if (j0 + e < p.low_nk) fa[e] = lowv[j0 + e];
-            }
-        } else if (part) {
-            for (int e = 0; e < 4; ++e) {
-                const int j = j0 + e;
-                if (j < h) {
-                    fa[e] = __ldg(x + j);
-                    fb[e] = __ldg(x + (n - 1 - j));
-                } else if (j == h && (n & 1)) {
-                    fa[e] = __ldg(x + h);
-                    mid[e] = true;
-                }
-            }
-        }
-    }
-    float s = p.fixed_scale;
-    if (p.per_line) {
-        float m = 0.f;
-        SCB_UNROLL
-        for (int e = 0; e < 4; ++e) m = fmaxf(m, fmaxf(fabsf(fa[e]), fabsf(fb[e])));
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((t & 31) == 0) red[t >> 5] = m;
-        __syncthreads();
-        m = red[0];
-        SCB_UNROLL
-        for (int w = 1; w < kI8DigThreads / 32; ++w) m = fmaxf(m, red[w]);
-        int e = 0;
-        if (m > 0.f) (void)frexpf(m, &e);  // m = f 2^e, 0.5 <= f < 1
-        if (e < -60) e = -60;
-        if (e > 90) e = 90;
-        s = ldexpf(1.0f, 29 - e);
-        if (t == 0) p.lscale[line] = ldexpf(1.0f, e - 29);
-    } else if (t == 0) {
-        p.lscale[line] = 1.0f / p.fixed_scale;
-    }
-    if (j0 >= p.g.kpad) return;
-    int f0[4], f1[4];
-    SCB_UNROLL
-    for (int e = 0; e < 4; ++e) {
-        const int va = __float2int_rn(fa[e] * s), vb = __float2int_rn(fb[e] * s);
-        f0[e] = va + vb;
-        f1[e] = va - vb;
-    }
-    if (part) {
-        for (int e = 0; e < 4; ++e)
-            if (mid[e]) f1[e] = 0;
-    }
-    unsigned w[2][DA];
-    balanced_digits4<DA>(f0, w[0]);
-    balanced_digits4<DA>(f1, w[1]);
-    SCB_UNROLL
-    for (int q = 0; q < 2; ++q)
-        SCB_UNROLL
-        for (int i = 0; i < DA; ++i)
-            *reinterpret_cast<unsigned*>(p.a + ((size_t)(q * DA + i) * p.m_rows + line) * p.g.kpad + j0) = w[q][i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1167,6 +1061,9 @@ static int i8_env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
 }
+static constexpr int kI8PersistentDefault = 1;  // 0: one tile per CTA, 1: i8_gemm_pkernel (128 x 64 tiles, TMEM ping-pong), 2: i8_gemm_p2kernel (128 x 128 tiles), 3: p2 forward / p inverse
+static int i8_sw_persistent() { return i8_env_int("SCB_I8_PERSISTENT", kI8PersistentDefault); }
+static int i8_sw_kb() { return i8_env_int("SCB_I8_KB", 128) == 64 ? 64 : 128; }
 template <int DA, int DB, int NSUB, int KB, int CL>
 static int i8_launch_gemm_t5(void* stream, const I8GemmParams& p) {
     using Cfg = I8Cfg<DA, DB, NSUB, KB>;
@@ -1294,11 +1191,13 @@ static int i8_launch_gemm_t(void* stream, const I8GemmParams& p) {
     static const int nsub = i8_env_int("SCB_I8_NSUB", 1) == 2 ? 2 : 1;
     static const int clp = i8_env_int("SCB_I8_CLUSTER", 1);
     static const int cl = clp == 2 ? 2 : 1;
-    static const int persistent = i8_env_int("SCB_I8_PERSISTENT", 1);
-    static const int kb = i8_env_int("SCB_I8_KB", 128) == 64 ? 64 : 128;
-    if (persistent == 2) {  // 128 x 128-output tiles: the inverse pass (4 + 3 digits) only fits with 64-byte stage rows
+    static const int persistent = i8_sw_persistent();
+    static const int kb = i8_sw_kb();
+    if (persistent == 2 || persistent == 3) {  // 128 x 128-output tiles; 3: for the forward pass only (the inverse pass, whose 4 + 3
+        // digits only fit with 64-byte stage rows and three stages, measured slower on them: profiles/r2b_ab_variants_call1.log)
         if constexpr (DA == 2 && DB == 4) return kb == 64 ? i8_launch_gemm_p2<2, 4, 64>(stream, p) : i8_launch_gemm_p2<2, 4, 128>(stream, p);
-        if constexpr (DA == 4 && DB == 3) return i8_launch_gemm_p2<4, 3, 64>(stream, p);
+        if constexpr (DA == 4 && DB == 3)
+            if (persistent == 2) return i8_launch_gemm_p2<4, 3, 64>(stream, p);
     }
     if (persistent) {
         if constexpr (!(DA == 4 && DB == 4)) {  // 4 + 4 digits: 96 KB per 128-byte-row stage, only the 64-byte rows leave two stages
@@ -1367,25 +1266,18 @@ int i8_launch_compose(void* stream, const I8ComposeParams& p, int rows) {
 #endif
 }
 
-static constexpr int kI8DigitizeDefault = 1;  // 1: i8_digitize_kernel, 2: i8_digitize2_kernel for lines of up to 2048 points
-static int i8_digitize_variant() {
-    static const int variant = [] {  // SCB_I8_DIGITIZE=1: i8_digitize_kernel for every length (A/B checks)
-        const char* e = std::getenv("SCB_I8_DIGITIZE");
-        return e ? std::atoi(e) : kI8DigitizeDefault;
-    }();
-    return variant;
+const char* i8_variant_string() {
+#ifdef SCB_EMU
+    static const std::string v = "i8_gemm=emulator";
+#else
+    static const std::string v = "i8_persistent=" + std::to_string(i8_sw_persistent()) + " i8_kb=" + std::to_string(i8_sw_kb());
+#endif
+    return v.c_str();
 }
-bool i8_digitize2_serves(const I8Geom& g) { return i8_digitize_variant() == 2 && g.kpad <= 4 * kI8DigThreads; }
 int i8_launch_digitize(void* stream, const I8DigitizeParams& p, int da) {
     if (p.line1 <= p.line0) return 0;
     const dim3 grid(p.line1 - p.line0), block(kI8DigThreads);
-    if (p.low_w && !i8_digitize2_serves(p.g)) return 1;  // the fused low-frequency block exists in i8_digitize2_kernel only
-    if (i8_digitize2_serves(p.g)) {
-        if (da == 2)
-            SCB_LAUNCH(i8_digitize2_kernel<2>, grid, block, 0, (cudaStream_t)stream, p);
-        else
-            SCB_LAUNCH(i8_digitize2_kernel<4>, grid, block, 0, (cudaStream_t)stream, p);
-    } else if (da == 2)
+    if (da == 2)
         SCB_LAUNCH(i8_digitize_kernel<2>, grid, block, 0, (cudaStream_t)stream, p);
     else
         SCB_LAUNCH(i8_digitize_kernel<4>, grid, block, 0, (cudaStream_t)stream, p);

@@ -87,15 +87,6 @@ struct I8DigitizeParams {
     float* lscale;          // [m_rows] per-line scale the epilogue multiplies by
     float fixed_scale;      // per_line == 0: x is multiplied by this before rounding (1: integer input, 65536: 16 fractional bits)
     int per_line;           // 1: per-line power-of-two scale from the line's largest magnitude (inverse pass)
-    // i8_digitize2_kernel only -- tri_lowapply_kernel (scb_tri.cuh) fused into the digitise of the inverse pass: the first low_nk elements
-    // of line (r, c) are not read from `in` but formed here, operation for operation as tri_lowapply_kernel forms them,
-    //   x[k] = (float)(Y64[c][r][k] + sum_l W[c][l][k] sin(pi (r+1)(l+1) / (lpc+1))),
-    // so the low-frequency block never makes its own pass over Ct.  Needs n >= 2 low_k (the block lies in the first half of the
-    // folded line).  low_w == null: off.
-    const double* low_w;    // [3][low_l][low_k]
-    const double* low_y64;  // [3][lpc][low_k]
-    int low_k, low_l;       // kTriLowK, kTriLowL (table strides)
-    int low_nk, low_nl;     // columns / frequencies actually present: min(n, low_k), min(lpc, low_l)
 };
 
 struct I8GemmParams {
@@ -133,7 +124,7 @@ struct I8ComposeParams {
 int i8_configure();  // cudaFuncSetAttribute of the kernels, once per device context
 int i8_launch_basis(void* stream, const I8Geom& g, signed char* basis);
 int i8_launch_digitize(void* stream, const I8DigitizeParams& p, int da);
-bool i8_digitize2_serves(const I8Geom& g);  // i8_digitize2_kernel (the only one with the fused low-frequency block) takes this line length
+const char* i8_variant_string();  // the kernel switches in force ("i8_persistent=.. i8_kb=..")
 int i8_launch_gemm(void* stream, const I8GemmParams& p, int da, int db);
 int i8_launch_compose(void* stream, const I8ComposeParams& p, int rows);
 

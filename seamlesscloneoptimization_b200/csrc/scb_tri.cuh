@@ -127,6 +127,49 @@ struct TriSolveParams {
 template <class T>
 struct TriIo;  // global-memory views of one column: a(y), v/u(y) and the tables
 
+// The reduced system of one column (run by the thread of its first segment, between pass 1 and pass 2): from the ends of the
+// segments' local solutions (sm rows 0 = w_last, 1 = w_first) to the true values just above / below every segment
+// (alpha[s] = sm row 2, beta[s] = sm row 3; rows 4, 5 are scratch).
+template <class T, class LoadM, class LoadP>
+SCB_D void tri_reduced_system(int n, int L, int nseg, int lane, T* sm /* [6][kTriSegs][kTriCols] */, const LoadM& load_m, const LoadP& load_p) {
+    T* al = sm + (2 * kTriSegs) * kTriCols + lane;  // alpha[s] at al[s * kTriCols]
+    T* be = sm + (3 * kTriSegs) * kTriCols + lane;  // beta[s]
+    T* Js = sm + (4 * kTriSegs) * kTriCols + lane;
+    T* Ks = sm + (5 * kTriSegs) * kTriCols + lane;
+    const int lastlen = n - (nseg - 1) * L;
+    auto ecoef = [&](int s) { return load_p((s == nseg - 1) ? lastlen : L); };      // sinh(theta) / sinh((len+1) theta)
+    auto fcoef = [&](int s) { return load_m(((s == nseg - 1) ? lastlen : L) - 1); };  // sinh(len theta) / sinh((len+1) theta)
+    const T* WL = sm + lane;
+    const T* WF = sm + kTriSegs * kTriCols + lane;
+    // p_s = G + H q_s  (p_s: last row of segment s, q_s: first row of segment s+1);  q_s = J_s + K_s q_(s+1)
+    T G = WL[0], H = fcoef(0);
+    T* Gs = al;  // alpha/beta slots double as G/H storage until the back substitution
+    T* Hs = be;
+    for (int s = 0; s + 1 < nseg; ++s) {
+        const T e1 = ecoef(s + 1), f1 = fcoef(s + 1);
+        const T den = T(1) - f1 * H;
+        const T J = (WF[(s + 1) * kTriCols] + f1 * G) / den, K = e1 / den;
+        Js[s * kTriCols] = J;
+        Ks[s * kTriCols] = K;
+        Gs[s * kTriCols] = G;
+        Hs[s * kTriCols] = H;
+        const T Gn = WL[(s + 1) * kTriCols] + e1 * (G + H * J);
+        H = f1 + e1 * H * K;
+        G = Gn;
+    }
+    // back substitution: q_(nseg-1) = 0 (Dirichlet boundary below the last segment);  alpha_s = p_(s-1),  beta_s = q_s
+    T qn = T(0);
+    be[(nseg - 1) * kTriCols] = T(0);
+    for (int s = nseg - 2; s >= 0; --s) {
+        const T q = Js[s * kTriCols] + Ks[s * kTriCols] * qn;
+        const T pp = Gs[s * kTriCols] + Hs[s * kTriCols] * q;
+        be[s * kTriCols] = q;         // H_s consumed
+        al[(s + 1) * kTriCols] = pp;  // G_(s+1) consumed
+        qn = q;
+    }
+    al[0] = T(0);
+}
+
 // INPLACE: a and v share their storage (tri_solve_smem_kernel's shared-memory tile): the upward sweep, which needs the original a,
 // runs to its end before the downward sweep overwrites a with v.  Each chain is the same sequence of operations either way, so
 // the results are bit-identical to the fused loop.  store_u receives the final solution of pass 2 (store_v: pass 1's v).
@@ -226,46 +269,11 @@ SCB_D void tri_segments(int n, int L, int seg, int nseg, int lane, T* sm /* [6][
     }
     __syncthreads();
     // ---- reduced system: thread (lane, seg 0) of every column ----
-    T* al = sm + (2 * kTriSegs) * kTriCols + lane;  // alpha[s] at al[s * kTriCols]
-    T* be = sm + (3 * kTriSegs) * kTriCols + lane;  // beta[s]
-    T* Js = sm + (4 * kTriSegs) * kTriCols + lane;
-    T* Ks = sm + (5 * kTriSegs) * kTriCols + lane;
-    if (active && seg == 0) {
-        const int lastlen = n - (nseg - 1) * L;
-        auto ecoef = [&](int s) { return load_p((s == nseg - 1) ? lastlen : L); };      // sinh(theta) / sinh((len+1) theta)
-        auto fcoef = [&](int s) { return load_m(((s == nseg - 1) ? lastlen : L) - 1); };  // sinh(len theta) / sinh((len+1) theta)
-        const T* WL = sm + lane;
-        const T* WF = sm + kTriSegs * kTriCols + lane;
-        // p_s = G + H q_s  (p_s: last row of segment s, q_s: first row of segment s+1);  q_s = J_s + K_s q_(s+1)
-        T G = WL[0], H = fcoef(0);
-        T* Gs = al;  // alpha/beta slots double as G/H storage until the back substitution
-        T* Hs = be;
-        for (int s = 0; s + 1 < nseg; ++s) {
-            const T e1 = ecoef(s + 1), f1 = fcoef(s + 1);
-            const T den = T(1) - f1 * H;
-            const T J = (WF[(s + 1) * kTriCols] + f1 * G) / den, K = e1 / den;
-            Js[s * kTriCols] = J;
-            Ks[s * kTriCols] = K;
-            Gs[s * kTriCols] = G;
-            Hs[s * kTriCols] = H;
-            const T Gn = WL[(s + 1) * kTriCols] + e1 * (G + H * J);
-            H = f1 + e1 * H * K;
-            G = Gn;
-        }
-        // back substitution: q_(nseg-1) = 0 (Dirichlet boundary below the last segment);  alpha_s = p_(s-1),  beta_s = q_s
-        T qn = T(0);
-        be[(nseg - 1) * kTriCols] = T(0);
-        for (int s = nseg - 2; s >= 0; --s) {
-            const T q = Js[s * kTriCols] + Ks[s * kTriCols] * qn;
-            const T pp = Gs[s * kTriCols] + Hs[s * kTriCols] * q;
-            be[s * kTriCols] = q;         // H_s consumed
-            al[(s + 1) * kTriCols] = pp;  // G_(s+1) consumed
-            qn = q;
-        }
-        al[0] = T(0);
-    }
+    if (active && seg == 0) tri_reduced_system<T>(n, L, nseg, lane, sm, load_m, load_p);
     __syncthreads();
     // ---- pass 2 ----
+    const T* al = sm + (2 * kTriSegs) * kTriCols + lane;  // alpha[s] at al[s * kTriCols]
+    const T* be = sm + (3 * kTriSegs) * kTriCols + lane;  // beta[s]
     if (active && len > 0) {
         const T alpha = al[seg * kTriCols];
         T u = be[seg * kTriCols];
@@ -432,6 +440,150 @@ SCB_D void tri_smem_body(const TriSolveParams& p, T* sm, int kb, int c, int tab_
         tri_segments<T, true>(
             n, L, seg, nseg, lane, red, tile_load, [&](int d) { return mrow[(size_t)d * tstride]; }, [&](int d) { return prow[(size_t)d * tstride]; }, tile_load, tile_store,
             [&](int y, T u) { Ct[(size_t)y * p.nx] = u; }, active, 0, 0, kTriSegs, (T*)nullptr, (size_t)0);
+    }
+}
+
+// tri_solve_smem2_kernel (SCB_TRI_SMEM=2): the same kernel written out by hand -- 32-bit shared-memory offsets instead of 64-bit
+// pointer arithmetic through the load / store functors of tri_segments, the table pointers in ONE address space per instantiation
+// (tri_solve_smem_kernel selects shared or global tables at run time, which turns every table access into a generic load with 64-bit
+// address arithmetic: ~56 instructions per row, profiles/r2b_*), the ends and the reduced system unchanged.  Same operations in the
+// same order: bit-identical to both other kernels (tests/emu/test_tri_smem.cpp).
+template <class T, int NCOL, bool TAB>
+SCB_D void tri_smem2_body(const TriSolveParams& p, T* sm, int kb, int c) {
+    const int lane = threadIdx.x % kTriCols, seg = threadIdx.x / kTriCols;
+    const int k = kb + lane;
+    const bool active = lane < NCOL && k < p.x1;
+    const int n = p.ny, L = p.seg_len;
+    const int nseg = (n + L - 1) / L;
+    const int rows = L + 1;
+    T* red = sm;
+    T* tabm = red + 6 * kTriSegs * kTriCols;
+    T* tabp = tabm + (TAB ? rows * NCOL : 0);
+    T* tile = tabp + (TAB ? rows * NCOL : 0);
+    const int ss = tri_smem_seg_stride(L, NCOL, (int)sizeof(T));
+    constexpr bool kF64 = sizeof(T) == 8;
+    const T* gm = kF64 ? reinterpret_cast<const T*>(p.tab.m64) : reinterpret_cast<const T*>(p.tab.m32);
+    const T* gp = kF64 ? reinterpret_cast<const T*>(p.tab.p64) : reinterpret_cast<const T*>(p.tab.p32);
+    const int gstride = kF64 ? kTriLowK : p.tab.pm;
+    if (TAB) {
+        for (int i = threadIdx.x; i < rows * NCOL; i += kTriCols * kTriSegs) {
+            const int d = i / NCOL, col = i - d * NCOL;
+            const bool in = kb + col < p.x1;
+            tabm[i] = in ? __ldg(gm + (size_t)d * gstride + kb + col) : T(0);
+            tabp[i] = in ? __ldg(gp + (size_t)d * gstride + kb + col) : T(0);
+        }
+    }
+    const int r0 = seg * L;
+    const int len = (seg < nseg) ? ((n - r0 < L) ? n - r0 : L) : 0;
+    T* col = tile + seg * ss + lane;  // row d of the own segment at col[d * NCOL]
+    const T* gmk = gm + k;
+    const T* gpk = gp + k;
+    // table entry d of the own column: shared (TAB) or global, decided at compile time
+    auto M = [&](int d) { return TAB ? tabm[d * NCOL + lane] : __ldg(gmk + (size_t)d * gstride); };
+    auto P = [&](int d) { return TAB ? tabp[d * NCOL + lane] : __ldg(gpk + (size_t)d * gstride); };
+    const bool work = active && len > 0;
+    if (work) {  // own rows of A -> tile
+        const float* A = p.A + ((size_t)c * n + r0) * p.nx + k;
+        const size_t nx = (size_t)p.nx;
+        int d = 0;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            float a[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) a[i] = __ldg(A + (d + i) * nx);
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) col[(d + i) * NCOL] = (T)a[i];
+        }
+        for (; d < len; ++d) col[d * NCOL] = (T)__ldg(A + d * nx);
+    }
+    if (TAB) __syncthreads();  // the tables are read by every segment
+    if (work) {
+        // ---- pass 1: the upward sweep to its end (it needs the original a), then the downward sweep in place ----
+        T b = col[(len - 1) * NCOL];
+        int d = 1;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            T ab[kTriUnroll], mm[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                ab[i] = col[(len - 1 - d - i) * NCOL];
+                mm[i] = M(d + i - 1);
+            }
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) b = mm[i] * b + ab[i];
+        }
+        for (; d < len; ++d) b = M(d - 1) * b + col[(len - 1 - d) * NCOL];
+        T v = col[0];
+        d = 1;
+        for (; d + kTriUnroll <= len; d += kTriUnroll) {
+            T av[kTriUnroll], mm[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                av[i] = col[(d + i) * NCOL];
+                mm[i] = M(d + i - 1);
+            }
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                v = mm[i] * v + av[i];
+                col[(d + i) * NCOL] = v;
+            }
+        }
+        for (; d < len; ++d) {
+            v = M(d - 1) * v + col[d * NCOL];
+            col[d * NCOL] = v;
+        }
+        const T ml = M(len - 1);
+        red[(0 * kTriSegs + seg) * kTriCols + lane] = ml * v;
+        red[(1 * kTriSegs + seg) * kTriCols + lane] = ml * b;
+    }
+    __syncthreads();
+    if (active && seg == 0) tri_reduced_system<T>(n, L, nseg, lane, red, M, P);
+    __syncthreads();
+    if (work) {
+        // ---- pass 2: back substitution with the true neighbours, straight to global memory ----
+        const T alpha = red[(2 * kTriSegs + seg) * kTriCols + lane];
+        T u = red[(3 * kTriSegs + seg) * kTriCols + lane];
+        const size_t ostride = kF64 ? (size_t)kTriLowK : (size_t)p.nx;
+        auto out = [&](int dd, T val) {
+            if constexpr (kF64)
+                p.Y64[((size_t)c * n + r0 + dd) * kTriLowK + k] = val;
+            else
+                p.Ct[((size_t)c * n + r0 + dd) * ostride + k] = val;
+        };
+        int d = len - 1;
+        for (; d >= kTriUnroll - 1; d -= kTriUnroll) {
+            T vv[kTriUnroll], mm[kTriUnroll], pp[kTriUnroll];
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                vv[i] = col[(d - i) * NCOL];
+                mm[i] = M(d - i);
+                pp[i] = P(d - i);
+            }
+            SCB_UNROLL
+            for (int i = 0; i < kTriUnroll; ++i) {
+                u = mm[i] * (u + (pp[i] * alpha + vv[i]));
+                out(d - i, u);
+            }
+        }
+        for (; d >= 0; --d) {
+            u = M(d) * (u + (P(d) * alpha + col[d * NCOL]));
+            out(d, u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTriCols * kTriSegs) tri_solve_smem2_kernel(TriSolveParams p, int tab_smem) {
+    SCB_DYN_SMEM(double, sm_dyn);
+    constexpr int nb64 = kTriLowK / kTriCols64;
+    const int c = blockIdx.y, bx = blockIdx.x;
+    if (bx < nb64) {
+        if (tab_smem)
+            tri_smem2_body<double, kTriCols64, true>(p, sm_dyn, bx * kTriCols64, c);
+        else
+            tri_smem2_body<double, kTriCols64, false>(p, sm_dyn, bx * kTriCols64, c);
+    } else {
+        if (tab_smem)
+            tri_smem2_body<float, kTriCols, true>(p, reinterpret_cast<float*>(sm_dyn), kTriLowK + (bx - nb64) * kTriCols, c);
+        else
+            tri_smem2_body<float, kTriCols, false>(p, reinterpret_cast<float*>(sm_dyn), kTriLowK + (bx - nb64) * kTriCols, c);
     }
 }
 

@@ -1,4 +1,4 @@
-// CI check (g++ -DSCB_EMU): tri_solve_smem_kernel produces the SAME bits as tri_solve_kernel -- Ct for the float columns, Y64 for the
+// CI check (g++ -DSCB_EMU): tri_solve_smem_kernel and tri_solve_smem2_kernel produce the SAME bits as tri_solve_kernel -- Ct for the float columns, Y64 for the
 // float64 block -- on random right-hand sides, for column counts with ragged last tiles, row counts with short last segments,
 // nx below / across the float64 block, tables in shared memory and in global memory.
 //   build + run: tests/test_kernel_variants.py
@@ -12,7 +12,7 @@
 
 using namespace scb;
 
-static int run_case(int nx, int ny, unsigned seed, int tables) {
+static int run_case(int nx, int ny, unsigned seed, int tables, int variant) {
     std::mt19937 rng(seed);
     std::uniform_real_distribution<float> dist(-1000.f, 1000.f);
     const int L = tri_seg_len(ny), rows = L + 1, pm = (nx + 3) / 4 * 4;
@@ -67,7 +67,10 @@ static int run_case(int nx, int ny, unsigned seed, int tables) {
         return 0;
     }
     const int nfloat = nx > kTriLowK ? (nx - kTriLowK + kTriCols - 1) / kTriCols : 0;
-    SCB_LAUNCH(tri_solve_smem_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, 0, t, tables);
+    if (variant == 2)
+        SCB_LAUNCH(tri_solve_smem2_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, 0, t, tables);
+    else
+        SCB_LAUNCH(tri_solve_smem_kernel, dim3(kTriLowK / kTriCols64 + nfloat, 3), dim3(kTriCols * kTriSegs), bytes, 0, t, tables);
     long long bad = 0;
     for (int c = 0; c < 3; ++c)
         for (int y = 0; y < ny; ++y) {
@@ -85,7 +88,7 @@ static int run_case(int nx, int ny, unsigned seed, int tables) {
         for (int y = 0; y < ny; ++y)
             for (int k = 0; k < kTriLowK && k < nx; ++k) bad += C2[((size_t)c * ny + y) * nx + k] != -7.f;
     if (bad) {
-        std::printf("FAIL nx=%d ny=%d seed=%u tables=%d: %lld differing values\n", nx, ny, seed, tables, bad);
+        std::printf("FAIL nx=%d ny=%d seed=%u tables=%d kernel %d: %lld differing values\n", nx, ny, seed, tables, variant, bad);
         return 1;
     }
     return 0;
@@ -98,13 +101,16 @@ int main() {
     unsigned seed = 1;
     for (int nx : nxs)
         for (int ny : nys)
-            for (int tables = 0; tables < 2; ++tables) {
-                fails += run_case(nx, ny, seed++, tables);
-                ++cases;
-            }
-    fails += run_case(100, 1337, seed++, 1);  // the 4K clone's column length
-    fails += run_case(40, 3070, seed++, 0);   // the 8K clone's: tables stay in global memory
-    cases += 2;
+            for (int tables = 0; tables < 2; ++tables)
+                for (int variant = 1; variant <= 2; ++variant) {
+                    fails += run_case(nx, ny, seed++, tables, variant);
+                    ++cases;
+                }
+    for (int variant = 1; variant <= 2; ++variant) {
+        fails += run_case(100, 1337, seed++, 1, variant);  // the 4K clone's column length
+        fails += run_case(40, 3070, seed++, 0, variant);   // the 8K clone's: tables stay in global memory
+        cases += 2;
+    }
     std::printf("%d cases, %d failed\n", cases, fails);
     return fails ? 1 : 0;
 }

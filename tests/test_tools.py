@@ -36,3 +36,20 @@ def test_cli_and_compare_report(tmp_path, request, backend):
     assert "diff sum" in r.stdout
     d = np.abs(blend.astype(int) - expect)
     assert d.max() <= 1 and (d != 0).sum() <= common.allowed_mismatches(3 * (w - 2) * (h - 2))
+
+
+def test_ab_selector_bookkeeping(tmp_path):
+    """tools/ab_select.py with synthetic worker results (AB_FAKE=1): a variant whose bytes differ from the baseline's is never selected,
+    one winner per switch group is combined, and the on-top round extends the selection."""
+    import json
+
+    env = dict(os.environ, AB_FAKE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab_select.py"), "--out", str(tmp_path), "--workloads", "cfg2", "cfg1"], env=env, capture_output=True,
+                       text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    sel = json.load(open(tmp_path / "selected.json"))
+    res = json.load(open(tmp_path / "results.json"))
+    assert res["i8_p2"]["_correct"] is False and "i8_p2" not in sel["winners"]
+    assert sel["combined_ok"] and {"tri_smem2", "lowproj2"} <= set(sel["winners"])
+    assert sel["env"]["SCB_TRI_SMEM"] == "2" and sel["env"].get("SCB_I8_PERSISTENT") != "2"
+    assert "export SCB_TRI_SMEM=2" in open(tmp_path / "selected.env").read()

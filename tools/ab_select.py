@@ -22,25 +22,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANT_LIBS = os.path.join(ROOT, "seamlesscloneoptimization_b200", "lib", "variants")
 
-# (name, switch group, environment, variant library tag or None).  Every variant but lowproj2 keeps the arithmetic of the baseline (a
-# different schedule of the same operations) and must reproduce the baseline's bytes exactly; lowproj2 reorders float64 sums (the
-# baseline's own order is not deterministic: atomics) and must stay within +-1 LSB and 0.003 points of the baseline's exact-byte share.
-# One winner per group is kept.
+# (name, switch group, environment, variant library tag or None).  The baseline is the library's defaults.  A variant that keeps the
+# arithmetic of the baseline (a different schedule of the same operations) must reproduce the baseline's bytes exactly; the ones in
+# INEXACT change a summation order -- lowproj2 reorders float64 sums (the baseline's own order is not deterministic: atomics), the
+# `s32` library cuts the columns of the tridiagonal solve into 32 segments instead of 16 -- and must stay within +-1 LSB of cv2 and
+# within 0.01 points of the baseline's exact-byte share.  One winner per group is kept.
+# (The first call of round 2 measured rhs_fold2, tri_smem, i8_p2, a leaner digitise and a digitise with the low-frequency block
+# fused in: profiles/r2b_ab_variants_call1.log.  The first two became defaults, the last two gained nothing and were removed.)
 VARIANTS = [
+    ("tri_smem2", "tri", {"SCB_TRI_SMEM": "2"}, None),
+    ("tri_s32", "tri", {}, "s32"),
+    ("tri_smem2_s32", "tri", {"SCB_TRI_SMEM": "2"}, "s32"),
+    ("i8_fwd_p2", "i8", {"SCB_I8_PERSISTENT": "3"}, None),
     ("i8_p2", "i8", {"SCB_I8_PERSISTENT": "2"}, None),
-    ("i8_p2_kb64", "i8", {"SCB_I8_PERSISTENT": "2", "SCB_I8_KB": "64"}, None),
-    ("rhs_fold2", "rhs", {"SCB_RHS_FOLD": "2"}, None),
-    ("rhs_fold2_r64", "rhs", {"SCB_RHS_FOLD": "2"}, "r64"),
-    ("tri_smem", "tri", {"SCB_TRI_SMEM": "1"}, None),
-    ("tri_smem_u16", "tri", {"SCB_TRI_SMEM": "1"}, "u16"),
-    ("i8_dig2", "dig", {"SCB_I8_DIGITIZE": "2"}, None),
-    ("i8_dig2_low", "dig", {"SCB_I8_DIGITIZE": "2", "SCB_LOWAPPLY_FUSE": "1"}, None),
 ]
 
 
 # second round, measured on top of the first round's winners (alone, the projections hide behind the column solve)
 ON_TOP = [("lowproj2", {"SCB_LOWPROJ": "2"})]
-INEXACT = {"lowproj2"}
+INEXACT = {"lowproj2", "tri_s32", "tri_smem2_s32"}
 
 
 def same_result(r, base, wls, exact):
@@ -49,7 +49,7 @@ def same_result(r, base, wls, exact):
             return False
         if r[wl]["md5"] == base[wl]["md5"]:
             continue
-        if exact or r[wl].get("max_abs", 9) > 1 or abs(r[wl].get("pct_exact", 0.0) - base[wl].get("pct_exact", 100.0)) > 0.003:
+        if exact or r[wl].get("max_abs", 9) > 1 or abs(r[wl].get("pct_exact", 0.0) - base[wl].get("pct_exact", 100.0)) > 0.01:
             return False
     return True
 
@@ -61,11 +61,11 @@ def lib_of(tags):
 
 def fake_worker(out_path, wls):
     """AB_FAKE=1: synthetic results, so that the orchestrator's bookkeeping can be exercised without a GPU (tests/test_tools.py)."""
-    gain = {"SCB_I8_PERSISTENT": 0.03, "SCB_RHS_FOLD": 0.012, "SCB_TRI_SMEM": 0.03, "SCB_I8_DIGITIZE": 0.006, "SCB_LOWAPPLY_FUSE": 0.006, "SCB_LOWPROJ": 0.004}
-    ms = 0.24 - sum(v for k, v in gain.items() if os.environ.get(k, "0") not in ("0", "1") or (k in ("SCB_TRI_SMEM", "SCB_LOWAPPLY_FUSE") and os.environ.get(k) == "1"))
+    gain = {"SCB_I8_PERSISTENT": 0.003, "SCB_TRI_SMEM": 0.02, "SCB_LOWPROJ": 0.004}
+    ms = 0.215 - sum(v for k, v in gain.items() if os.environ.get(k, "1") not in ("0", "1"))
     if os.environ.get("SCB_LIBRARY"):
         ms -= 0.001
-    broken = os.environ.get("SCB_I8_KB") == "64"  # pretend one variant computes something else
+    broken = os.environ.get("SCB_I8_PERSISTENT") == "2"  # pretend one variant computes something else
     res = {wl: {"ms": ms, "ms_mean": ms, "ms_min": ms, "stages_us": {}, "md5": "beef" if broken else "cafe", "host_equals_device": True, "roi": [0, 0], "engine": 4,
                 "pct_exact": 99.85, "max_abs": 1} for wl in wls}
     with open(out_path, "w") as fh:
