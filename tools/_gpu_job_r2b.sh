@@ -3,7 +3,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 START=$(date +%s)
-LIMIT=${JOB_LIMIT:-830}
+LIMIT=${JOB_LIMIT:-460}
 left() { echo $(( LIMIT - ($(date +%s) - START) )); }
 step() {  # step <max seconds> <command...>: skipped when fewer than 20 s remain
   local max=$1; shift
@@ -22,7 +22,8 @@ step 400 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytes
 tail -15 gpurun_out/pytest_gpu_selected_full.log > gpurun_out/pytest_gpu_selected.log
 step 150 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_cfg2_selected.json 2> gpurun_out/bench_cfg2_selected.err
 step 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_selected.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
+step 240 ncu --set full --clock-control none --import-source on -k "regex:rhs_fold|i8_gemm_p|tri_solve|i8_digitize|tri_low" -s 12 -c 7 -o gpurun_out/prof_selected python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
 step 90 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg4_selected.json 2> gpurun_out/bench_cfg4_selected.err
 step 90 python bench.py --workload cfg1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_cfg1_selected.json 2> gpurun_out/bench_cfg1_selected.err
-step 240 ncu --set full --clock-control none --import-source on -k "regex:rhs_fold|i8_gemm_p|tri_solve|i8_digitize|tri_low" -s 12 -c 7 -o gpurun_out/prof_selected python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
+step 90 python bench.py --workload cfg5 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_cfg5_selected.json 2> gpurun_out/bench_cfg5_selected.err
 echo "done at $(( $(date +%s) - START )) s" >> gpurun_out/job.log

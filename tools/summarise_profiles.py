@@ -19,6 +19,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2_final"
+# `--selected`: the files written by tools/_gpu_job_r2b.sh (A/B selection, then tests / bench / ncu under the selected switches)
+SELECTED = "--selected" in sys.argv
+SRC = {"bench": "bench_{w}_selected.json", "launches": "launches_selected.csv", "rep": "prof_selected.ncu-rep", "pytest": "pytest_gpu_selected.log"} if SELECTED else \
+      {"bench": "final_bench_{w}.json", "launches": "final_launches.csv", "rep": "final_prof.ncu-rep", "pytest": "final_pytest_gpu.log"}
 
 WANT = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active",
@@ -43,12 +47,16 @@ def copy(src, dst):
 
 
 for w in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "n2", "n4", "n8"):
-    copy(f"final_bench_{w}.json", f"{tag}_bench_{w}.json")
+    copy(SRC["bench"].format(w=w), f"{tag}_bench_{w}.json")
 copy("final_parity_tri.txt", f"{tag}_parity_vs_cv2_fft_rows.txt")
 copy("final_bench_ref.json", f"{tag}_bench_cfg2_reference.json")
-copy("final_pytest_gpu.log", f"{tag}_pytest_gpu.log")
+copy(SRC["pytest"], f"{tag}_pytest_gpu.log")
+if SELECTED:
+    copy("ab.log", f"{tag}_ab_variants.log")
+    copy(os.path.join("ab", "results.json"), f"{tag}_ab_variants.json")
+    copy(os.path.join("ab", "selected.json"), f"{tag}_ab_selected.json")
 copy("final_parity.txt", f"{tag}_parity_vs_cv2.txt")
-copy("final_launches.csv", f"{tag}_launches_cfg2.csv")
+copy(SRC["launches"], f"{tag}_launches_cfg2.csv")
 
 launches = os.path.join(PROF, f"{tag}_launches_cfg2.csv")
 if os.path.exists(launches):
@@ -65,16 +73,16 @@ if os.path.exists(launches):
 
     stamp = ge.library_hash(ge.LIB)
     kt = {"library_stamp": stamp,
-          "cfg2": {"rhs": full_size("rhs_fold_kernel") or full_size("rhs_kernel"), "rows_fwd": full_size("rows_fwd"), "rows_inv": full_size("rows_inv"),
-                   "cols": full_size("tri_solve_kernel"), "i8_gemm_fwd": full_size("i8_gemm_pkernel<2, 4"), "i8_gemm_inv": full_size("i8_gemm_pkernel<4, 3"),
+          "cfg2": {"rhs": full_size("rhs_fold") or full_size("rhs_kernel"), "rows_fwd": full_size("rows_fwd"), "rows_inv": full_size("rows_inv"),
+                   "cols": full_size("tri_solve"), "i8_gemm_fwd": full_size("kernel<2, 4"), "i8_gemm_inv": full_size("kernel<4, 3"),
                    "_note": f"gpu__time_duration.sum (ms) of the full-size launch, profiles/{tag}_launches_cfg2.csv (ncu --metrics gpu__time_duration.sum --clock-control none: "
-                            "cold cache, serialised); cols = tri_solve_kernel alone; valid for the library whose source hash is library_stamp (bench.py drops them otherwise)"}}
+                            "cold cache, serialised); cols = the tridiagonal solve kernel alone (tri_solve_smem_kernel / tri_solve_kernel); valid for the library whose source hash is library_stamp (bench.py drops them otherwise)"}}
     json.dump(kt, open(os.path.join(PROF, "kernel_times.json"), "w"), indent=1)
     total = sum(sum(v) for v in agg.values())
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         print(f"{100 * sum(v) / total:6.2f} %  n={len(v):3d}  mean {1e3 * sum(v) / len(v):8.2f} us  max {1e3 * max(v):8.2f} us  {k[:70]}")
 
-rep = os.path.join(OUT, "final_prof.ncu-rep")
+rep = os.path.join(OUT, SRC["rep"])
 if os.path.exists(rep) and shutil.which("ncu"):
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
@@ -83,7 +91,7 @@ if os.path.exists(rep) and shutil.which("ncu"):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     out = [f"# ncu --set full --clock-control none, bench.py cfg2 (ROI 1810x1339), default engine (INT8 tensor-core DST along x + tridiagonal solve along y); "
-           "report gpurun_out/final_prof.ncu-rep (not committed)"]
+           f"report gpurun_out/{SRC['rep']} (not committed)"]
     seen, traffic = set(), {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
@@ -102,10 +110,10 @@ if os.path.exists(rep) and shutil.which("ncu"):
     open(os.path.join(PROF, f"{tag}_ncu_full_cfg2.txt"), "w").write("\n".join(out) + "\n")
     pick = lambda sub: next((v for k, v in traffic.items() if sub in k), None)
     t = {"library_stamp": ge.library_hash(ge.LIB),
-         "cfg2": {"rows_fwd": pick("rows_fwd"), "rows_inv": pick("rows_inv"), "cols": pick("tri_solve"), "rhs": pick("rhs_fold_kernel") or pick("rhs_kernel"),
-                  "i8_gemm_fwd": pick("i8_gemm_pkernel<2, 4"), "i8_gemm_inv": pick("i8_gemm_pkernel<4, 3"),
+         "cfg2": {"rows_fwd": pick("rows_fwd"), "rows_inv": pick("rows_inv"), "cols": pick("tri_solve"), "rhs": pick("rhs_fold") or pick("rhs_kernel"),
+                  "i8_gemm_fwd": pick("kernel<2, 4"), "i8_gemm_inv": pick("kernel<4, 3"),
                   "_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of bench.py cfg2, profiles/{tag}_ncu_full_cfg2.txt "
-                           "(writes mostly stay in the 126 MB L2 during ncu's kernel replay); cols = tri_solve_kernel"}}
+                           "(writes mostly stay in the 126 MB L2 during ncu's kernel replay); cols = the tridiagonal solve kernel"}}
     json.dump(t, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
 
 for w in ("cfg2", "cfg1", "cfg5", "cfg4", "cfg3"):
