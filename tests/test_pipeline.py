@@ -799,3 +799,32 @@ def test_sharded_tri_entry_points_validate_their_arguments(be):
         assert ctx.lib.scb_plan_create_ex(ctx.handle, C.byref(vm), scb.MEM_DEVICE, src.shape[0], src.shape[1], dst.shape[0], dst.shape[1], p[0], p[1], 7, C.byref(h)) == capi.SCB_ERR_UNSUPPORTED
     finally:
         ctx.close()
+
+
+def test_roi_in_the_corner_of_tightly_allocated_images(be, ctx):
+    """The ROI touches the right and the bottom edge of dst, the mask's bounding box the right and bottom edge of src, and every
+    device image is an exactly-sized allocation: the word loads of the stencil at the row ends must stay inside the buffers
+    (rhs_fold2_kernel reads up to 5 bytes past the end of a ROI row -- never of the last one).  Under tools/asan_emu.sh an
+    overrun lands in a redzone."""
+    rng = np.random.default_rng(77)
+    H, W, sh, sw = 120, 161, 90, 131
+    src, dst = so.smooth_rand(rng, sh, sw, 3.0), so.smooth_rand(rng, H, W, 3.0)
+    mask = np.zeros((sh, sw), np.uint8)
+    mask[9:sh, 20:sw] = 255  # the bounding box (after the ring is zeroed) reaches the last row / column of src
+    mask[30:40, 60:70] = 0   # a hole: both images are read inside the box
+    p = (106, 80)  # cv2's placement rule puts the 110 x 80 ROI at (51, 40): its last column / row are dst's (asserted below)
+    want = cv_blend(src, dst, mask, p)
+    host_blend = ctx.seamless_clone(src, dst, mask, p)
+    vs, hs = be.to_device(src)
+    vd, hd = be.to_device(dst)
+    vm, hm = be.to_device(mask)
+    vb, hb = be.to_device(np.zeros_like(dst))
+    plan = scb.Plan(ctx, vm, src.shape[:2], dst.shape[:2], p, scb.MEM_DEVICE)
+    g = plan.geometry
+    assert g.rx + g.w == W and g.ry + g.h == H, (g.rx, g.w, g.ry, g.h)  # the ROI really sits in the corner
+    plan.execute(vs, vd, vb, scb.MEM_DEVICE)
+    ctx.sync()
+    assert np.array_equal(be.to_host(hb), host_blend)
+    assert np.array_equal(be.to_host(hd), dst)
+    assert_matches(host_blend, want, g)
+    plan.close()

@@ -17,5 +17,5 @@ export LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1   # fibers: swapcontext is only partly supported
 SCB_LIBRARY="$OUT/libscb_emu_asan.so" python tools/sanitize_smoke.py 2>&1 | grep -v "doesn't fully support makecontext"
 if [ "$1" == "--tests" ]; then
-    SCB_EMU_LIBRARY="$OUT/libscb_emu_asan.so" python -m pytest tests/test_pipeline.py -x -q -m "not gpu" -k "emu and (transform_length or golden or flags or orientations or batch or sharded or int8 or plan_cache or two_contexts)" 2>&1 | grep -v "doesn't fully support makecontext" | tail -5
+    SCB_EMU_LIBRARY="$OUT/libscb_emu_asan.so" python -m pytest tests/test_pipeline.py -x -q -m "not gpu" -k "emu and (transform_length or golden or flags or orientations or batch or sharded or int8 or plan_cache or two_contexts or corner)" 2>&1 | grep -v "doesn't fully support makecontext" | tail -5
 fi
